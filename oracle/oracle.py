@@ -78,13 +78,16 @@ def sift_pair_count(des1, des2, ratio=RATIO):
     return int(ratio_pass_from_d2(d0, d1, ratio).sum())
 
 
-def l2sq_f32(des1, des2):
+def l2sq_f32(des1, des2, block=64):
     """Float descriptors (SURF): direct sum of squared differences, accumulated in float64 and
     reported in float64.  cv2 accumulates the same sum in float32 SIMD lanes (1.1e-7 rel)."""
     a = np.asarray(des1, dtype=np.float64)
     b = np.asarray(des2, dtype=np.float64)
-    diff = a[:, None, :] - b[None, :, :]
-    return (diff * diff).sum(2)
+    out = np.empty((a.shape[0], b.shape[0]), dtype=np.float64)
+    for s in range(0, a.shape[0], block):
+        diff = a[s:s + block, None, :] - b[None, :, :]
+        out[s:s + block] = (diff * diff).sum(2)
+    return out
 
 
 def surf_pair_count(des1, des2, ratio=RATIO, tie_rel=1e-6):

@@ -1,8 +1,26 @@
 """b200-mcl-match: B200-native (sm_100a) descriptor-matching hot path of zhangxingshuo/py-mcl.
 
-``Matcher`` / ``analyzer`` keep the reference's API (Matcher.py:35, analyze.py:32); the work is
+``Matcher`` / ``analyzer`` keep the reference's API (reference Matcher.py:35, analyze.py:32); the work is
 done by hand-written CUDA kernels in ``csrc/`` behind the C-ABI declared in ``include/mcl.h``
-(``libmcl.so``), called through ctypes.  There is no CPU fallback: importing the kernels on a box
-without the built library or without an sm_100 GPU raises.
+(``libmcl.so``), called through ctypes (``_lib``).  There is no CPU fallback: using the kernels on a box
+without the built library or without an sm_100 GPU raises ``MclError``.
+
+    from pymcl_b200 import Matcher, analyzer          # drop-in for `from Matcher import Matcher`
 """
-__all__ = ["synth"]
+from . import _lib  # noqa: F401  (does not touch the GPU or load the library at import time)
+from ._lib import MclError  # noqa: F401
+
+__all__ = ["Matcher", "analyzer", "MclError", "synth", "engine", "build"]
+
+
+def __getattr__(name):
+    # cv2 is imported only when the reference-facing classes are asked for
+    if name in ("Matcher", "analyzer"):
+        import importlib
+        cls = getattr(importlib.import_module("." + ("Matcher" if name == "Matcher" else "analyze"), __name__), name)
+        globals()[name] = cls  # the class shadows the same-named submodule, like `from Matcher import Matcher`
+        return cls
+    if name in ("synth", "engine", "build", "analyze"):
+        import importlib
+        return importlib.import_module("." + name, __name__)
+    raise AttributeError(name)

@@ -1,0 +1,391 @@
+"""ctypes binding of libmcl.so (the C-ABI in include/mcl.h).  Thin on purpose: numpy in, numpy out.
+
+There is NO CPU fallback: if the shared library is not built, or no sm_100 device is present, every
+entry point raises ``MclError``.  Nothing here imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmcl.so")
+
+SIFT, ORB, SURF, BOWQ = 0, 1, 2, 3
+U8, F32 = 0, 1
+KNN2_RATIO, CROSSCHECK = 0, 1
+ALGO_AUTO, ALGO_TENSOR, ALGO_SIMT = 0, 1, 2
+F_COMMAND, F_PREV, F_BLUR, F_BEST, F_ALL = 1, 2, 4, 8, 15
+KIND_BY_NAME = {"SIFT": SIFT, "ORB": ORB, "SURF": SURF}
+ROW_DIM = {SIFT: 128, ORB: 32, SURF: 64, BOWQ: 128}
+PROFILE_SLOTS = {"sift_tc": 0, "sift_fixup": 1, "orb": 2, "surf": 3, "bow_vq": 4, "bow_score": 5, "laplacian": 6,
+                 "ingest": 7, "sift_simt": 8}
+
+
+class MclError(RuntimeError):
+    pass
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_p = C.c_void_p
+_i64p = C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes); must list every symbol include/mcl.h declares (tests check this)
+SIGNATURES = {
+    "mcl_init": (C.c_int, [C.c_int, C.POINTER(_p)]),
+    "mcl_shutdown": (None, [_p]),
+    "mcl_last_error": (C.c_char_p, []),
+    "mcl_device_info": (C.c_int, [_p, _i64p]),
+    "mcl_sync": (C.c_int, [_p]),
+    "mcl_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_p)]),
+    "mcl_host_free": (None, [_p]),
+    "mcl_launch_count": (C.c_int64, [_p]),
+    "mcl_profile_enable": (C.c_int, [_p, C.c_int]),
+    "mcl_profile_read": (C.c_int, [_p, C.c_int, C.POINTER(C.c_double), _i64p]),
+    "mcl_map_create": (C.c_int, [_p, C.c_int, C.c_int, _i64p, _p, C.c_int, C.POINTER(_p)]),
+    "mcl_map_destroy": (None, [_p]),
+    "mcl_map_info": (C.c_int, [_p, _i64p]),
+    "mcl_queries_create": (C.c_int, [_p, C.c_int, C.c_int, _i64p, _p, C.c_int, C.POINTER(_p)]),
+    "mcl_queries_destroy": (None, [_p]),
+    "mcl_match_counts": (C.c_int, [_p, C.c_int, _i64p, _p, C.c_int, C.c_int, C.c_double, _p, C.c_int32, C.c_int, _p]),
+    "mcl_match_counts_device": (C.c_int, [_p, _p, C.c_int, C.c_double, _p, C.c_int32, C.c_int, _p, _p]),
+    "mcl_bow_create": (C.c_int, [_p, C.c_int, _i64p, _p, _p, _i64p, _p, C.c_int, C.POINTER(_p)]),
+    "mcl_bow_destroy": (None, [_p]),
+    "mcl_bow_score": (C.c_int, [_p, C.c_int, _i64p, _p, C.c_int, _p, _p]),
+    "mcl_bow_score_device": (C.c_int, [_p, _p, _p, _p, _p]),
+    "mcl_laplacian_var": (C.c_int, [_p, C.c_int, C.POINTER(_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _p]),
+    "mcl_laplacian_sums": (C.c_int, [_p, C.c_int, C.POINTER(_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _p]),
+    "mcl_filter_step": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_char, C.c_double, _p, _p, _p, _p]),
+    "mcl_microbench": (C.c_int, [_p, C.c_int, C.c_int, _p]),
+}
+
+
+def load_library():
+    """dlopen libmcl.so and type every entry point.  Does not touch the GPU."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise MclError(
+                "libmcl.so is not built (%s).  Build it with `python __graft_entry__.py` "
+                "(nvcc -gencode arch=compute_100a,code=sm_100a).  There is no CPU fallback." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load_library().mcl_last_error()
+        raise MclError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def _offsets(lengths):
+    off = np.zeros(len(lengths) + 1, dtype=np.int64)
+    if len(lengths):
+        np.cumsum(np.asarray(lengths, dtype=np.int64), out=off[1:])
+    return off
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_p) if a is not None else None
+
+
+def pack_descriptors(kind, descs):
+    """List of per-image/per-frame descriptor matrices (None or empty allowed, as cv2 returns None for an
+    image without keypoints) -> (row offsets int64, concatenated C-contiguous matrix, dtype code)."""
+    dim = ROW_DIM[kind]
+    mats = []
+    for d in descs:
+        if d is None or len(d) == 0:
+            mats.append(None)
+            continue
+        d = np.asarray(d)
+        if d.ndim != 2 or d.shape[1] != dim:
+            raise MclError("descriptor matrix has shape %r, expected (*, %d)" % (d.shape, dim))
+        mats.append(d)
+    off = _offsets([0 if m is None else len(m) for m in mats])
+    real = [m for m in mats if m is not None]
+    if kind == ORB:
+        dt, code = np.uint8, U8
+    elif kind == SURF:
+        dt, code = np.float32, F32
+    else:  # SIFT / BOWQ: cv2 gives integer-valued float32; uint8 accepted as is
+        if real and all(m.dtype == np.uint8 for m in real):
+            dt, code = np.uint8, U8
+        else:
+            dt, code = np.float32, F32
+    if real:
+        if len(real) == 1 and real[0].dtype == dt and real[0].flags.c_contiguous:
+            cat = real[0]
+        else:
+            cat = np.ascontiguousarray(np.concatenate([m.astype(dt, copy=False) for m in real], axis=0))
+    else:
+        cat = np.zeros((0, dim), dtype=dt)
+    return off, cat, code
+
+
+class Context:
+    """One CUDA context/stream on one B200 (mcl_init).  One per process (one process per GPU)."""
+
+    def __init__(self, device=None):
+        lib = load_library()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        h = _p()
+        _check(lib.mcl_init(int(device), C.byref(h)), "mcl_init")
+        self._h = h
+        self.device = int(device)
+        self._lib = lib
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mcl_shutdown(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        a = (C.c_int64 * 8)()
+        _check(self._lib.mcl_device_info(self._h, a), "mcl_device_info")
+        return {"sm_count": a[0], "cc": (a[1], a[2]), "hbm_mib": a[3], "sm_clock_khz": a[4], "l2_bytes": a[5],
+                "smem_optin": a[6]}
+
+    def sync(self):
+        _check(self._lib.mcl_sync(self._h), "mcl_sync")
+
+    def launch_count(self):
+        return int(self._lib.mcl_launch_count(self._h))
+
+    def profile_enable(self, on=True):
+        _check(self._lib.mcl_profile_enable(self._h, 1 if on else 0), "mcl_profile_enable")
+
+    def profile_read(self, which):
+        ms, n = C.c_double(), C.c_int64()
+        _check(self._lib.mcl_profile_read(self._h, PROFILE_SLOTS[which] if isinstance(which, str) else which,
+                                          C.byref(ms), C.byref(n)), "mcl_profile_read")
+        return ms.value, n.value
+
+    def microbench(self, which, iters):
+        out = (C.c_double * 2)()
+        _check(self._lib.mcl_microbench(self._h, which, iters, out), "mcl_microbench")
+        return out[0], out[1]
+
+    # ---- small stages -------------------------------------------------------------------
+    def laplacian_var(self, images):
+        """analyzer.Laplacian (analyze.py:441-445) for a list of 2-D uint8 arrays -> float64 array."""
+        return self._lap(images, False)
+
+    def laplacian_sums(self, images):
+        return self._lap(images, True)
+
+    def _lap(self, images, sums):
+        n = len(images)
+        imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        for im in imgs:
+            if im.ndim != 2:
+                raise MclError("laplacian: images must be 2-D grayscale uint8")
+        ptrs = (_p * max(n, 1))(*[im.ctypes.data for im in imgs])
+        hs = (C.c_int * max(n, 1))(*[im.shape[0] for im in imgs])
+        ws = (C.c_int * max(n, 1))(*[im.shape[1] for im in imgs])
+        st = (C.c_int * max(n, 1))(*[im.strides[0] for im in imgs])
+        if sums:
+            out = np.zeros((n, 2), dtype=np.int64)
+            _check(self._lib.mcl_laplacian_sums(self._h, n, ptrs, hs, ws, st, _ptr(out)), "mcl_laplacian_sums")
+        else:
+            out = np.zeros(n, dtype=np.float64)
+            _check(self._lib.mcl_laplacian_var(self._h, n, ptrs, hs, ws, st, _ptr(out)), "mcl_laplacian_var")
+        return out
+
+    def filter_step(self, stages, cmd, blur, prev, cur):
+        """prev, cur: (L, 1+I) float64.  Returns (prev after the command shift, out, (bestCircle, bestAngle))."""
+        prev = np.ascontiguousarray(prev, dtype=np.float64).copy()
+        cur = np.ascontiguousarray(cur, dtype=np.float64)
+        if prev.shape != cur.shape or prev.ndim != 2:
+            raise MclError("filter_step: prev/cur must both be (L, 1+I)")
+        out = np.zeros_like(prev)
+        best = np.zeros(2, dtype=np.int32)
+        c = (cmd or "s").encode()[:1]
+        _check(self._lib.mcl_filter_step(self._h, prev.shape[0], prev.shape[1] - 1, int(stages), c, float(blur),
+                                         _ptr(prev), _ptr(cur), _ptr(out), _ptr(best)), "mcl_filter_step")
+        return prev, out, (int(best[0]), int(best[1]))
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+class MapIndex:
+    """Resident descriptors of a set of map images (mcl_map): replaces the {path: (kp, des)} dicts of
+    Matcher.createFeatureIndex (Matcher.py:147-163) on the device."""
+
+    def __init__(self, ctx, kind, descs):
+        self.ctx = ctx
+        self.kind = KIND_BY_NAME[kind] if isinstance(kind, str) else int(kind)
+        off, cat, code = pack_descriptors(self.kind, descs)
+        self.n_images = len(descs)
+        self.row_offsets = off
+        h = _p()
+        _check(ctx._lib.mcl_map_create(ctx._h, self.kind, self.n_images, off.ctypes.data_as(_i64p), _ptr(cat), code,
+                                       C.byref(h)), "mcl_map_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self.ctx._lib.mcl_map_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        a = (C.c_int64 * 4)()
+        _check(self.ctx._lib.mcl_map_info(self._h, a), "mcl_map_info")
+        return {"n_images": a[0], "rows": a[1], "padded_rows": a[2], "resident_bytes": a[3]}
+
+    def match_counts(self, q_descs, mode=KNN2_RATIO, ratio=0.7, mask=None, fill_value=1, algo=ALGO_AUTO, packed=None):
+        """counts[q, i] = len(good) of *Match(query q, image i); host in / host out (H2D + kernels + D2H).
+        `packed` = (offsets, matrix, dtype code) skips the packing of q_descs."""
+        off, cat, code = packed if packed is not None else pack_descriptors(self.kind, q_descs)
+        nq = len(off) - 1
+        out = np.zeros((nq, self.n_images), dtype=np.int32)
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(mask, dtype=np.uint8)
+            if m.shape != out.shape:
+                raise MclError("mask must have shape (n_queries, n_images)")
+        _check(self.ctx._lib.mcl_match_counts(self._h, nq, off.ctypes.data_as(_i64p), _ptr(cat), code, int(mode),
+                                              float(ratio), _ptr(m), int(fill_value), int(algo), _ptr(out)),
+               "mcl_match_counts")
+        return out
+
+    def match_counts_device(self, queries, d_counts_ptr, mode=KNN2_RATIO, ratio=0.7, d_mask_ptr=None, fill_value=1,
+                            algo=ALGO_AUTO, stream=None):
+        """Asynchronous: resident queries, raw device pointers (e.g. torch tensor .data_ptr())."""
+        _check(self.ctx._lib.mcl_match_counts_device(self._h, queries._h, int(mode), float(ratio),
+                                                     _p(d_mask_ptr) if d_mask_ptr else None, int(fill_value), int(algo),
+                                                     _p(d_counts_ptr), _p(stream) if stream else None),
+               "mcl_match_counts_device")
+
+
+class QueryBatch:
+    """Resident query descriptors of a batch of frames (mcl_queries)."""
+
+    def __init__(self, ctx, kind, descs=None, packed=None):
+        self.ctx = ctx
+        self.kind = (KIND_BY_NAME.get(kind, BOWQ) if isinstance(kind, str) else int(kind))
+        off, cat, code = packed if packed is not None else pack_descriptors(self.kind, descs)
+        self.n_queries = len(off) - 1
+        self.row_offsets = off
+        h = _p()
+        _check(ctx._lib.mcl_queries_create(ctx._h, self.kind, self.n_queries, off.ctypes.data_as(_i64p), _ptr(cat), code,
+                                           C.byref(h)), "mcl_queries_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self.ctx._lib.mcl_queries_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BowIndex:
+    """Resident bag-of-words indices of n locations (mcl_bow): per location the (im_features, idf, voc) of
+    joblib.load(indexPath) in Matcher.BOWMatch (Matcher.py:236)."""
+
+    def __init__(self, ctx, locations, num_words):
+        """locations: list of (im_features (N,W) f32, idf (W,) f32, voc (<=W,128) f32)."""
+        self.ctx = ctx
+        self.W = int(num_words)
+        self.n_loc = len(locations)
+        vocs = [np.ascontiguousarray(v, dtype=np.float32) for (_, _, v) in locations]
+        idfs = [np.ascontiguousarray(i, dtype=np.float32).reshape(-1) for (_, i, _) in locations]
+        imfs = [np.ascontiguousarray(f, dtype=np.float32) for (f, _, _) in locations]
+        for i, f in zip(idfs, imfs):
+            if i.shape[0] != self.W or f.shape[1] != self.W:
+                raise MclError("idf / im_features width != num_words")
+        self.voc_off = _offsets([len(v) for v in vocs])
+        self.img_off = _offsets([len(f) for f in imfs])
+        self.total_images = int(self.img_off[-1])
+        voc = np.ascontiguousarray(np.concatenate(vocs, axis=0))
+        idf = np.ascontiguousarray(np.stack(idfs, axis=0))
+        imf = np.ascontiguousarray(np.concatenate(imfs, axis=0))
+        h = _p()
+        _check(ctx._lib.mcl_bow_create(ctx._h, self.n_loc, self.voc_off.ctypes.data_as(_i64p), _ptr(voc), _ptr(idf),
+                                       self.img_off.ctypes.data_as(_i64p), _ptr(imf), self.W, C.byref(h)), "mcl_bow_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self.ctx._lib.mcl_bow_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def score(self, q_descs, want_words=False):
+        """-> (scores (n_queries, total_images) f32, words (n_loc, total rows) int32 or None)."""
+        off, cat, code = pack_descriptors(BOWQ, q_descs)
+        nq = len(off) - 1
+        scores = np.zeros((nq, self.total_images), dtype=np.float32)
+        words = np.zeros((self.n_loc, int(off[-1])), dtype=np.int32) if want_words else None
+        _check(self.ctx._lib.mcl_bow_score(self._h, nq, off.ctypes.data_as(_i64p), _ptr(cat), code, _ptr(words),
+                                           _ptr(scores)), "mcl_bow_score")
+        return scores, words
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over cudaHostAlloc'd memory (for the end-to-end path).  Keeps the allocation alive through
+    the array's base object."""
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = _p()
+    _check(lib.mcl_host_alloc(max(n, 1), C.byref(p)), "mcl_host_alloc")
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib.mcl_host_free(self.ptr)
+            except Exception:
+                pass
+
+    owner = _Owner(p)
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    buf._owner = owner
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr

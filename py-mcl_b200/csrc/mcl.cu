@@ -1,0 +1,1010 @@
+// libmcl.so — host side of the C-ABI declared in include/mcl.h (sm_100a only, no CPU fallback).
+#include "../../include/mcl.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "prep.cuh"
+#include "sift_tc.cuh"
+#include "simt_match.cuh"
+#include "bow_lap_filter.cuh"
+#include "microbench.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(MCL_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+enum { PROF_SIFT_TC = 0, PROF_SIFT_FIX, PROF_ORB, PROF_SURF, PROF_VQ, PROF_SCORE, PROF_LAP, PROF_PREP, PROF_SIFT_SIMT, PROF_N };
+
+// growable device scratch buffer (never shrinks; avoids cudaMalloc on the per-frame path)
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(bytes, (size_t)4096);
+        want = (want + 255) & ~(size_t)255;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct mcl_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaDeviceProp prop{};
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[PROF_N];
+    // scratch
+    DevBuf stage, cand, flags /* [0]=cand_count [1]=overflow [2]=bad */, row_arg, bow_best, lap_pix, lap_meta, filt, tmp_counts,
+        tmp_mask, tmp_words, tmp_scores;
+    size_t cand_cap_entries = 0;
+    bool tc_attr_set = false;
+};
+
+struct mcl_queries {
+    mcl_ctx* ctx = nullptr;
+    int kind = 0;
+    int n_queries = 0;
+    int64_t rows = 0, padded_rows = 0;
+    std::vector<int64_t> h_off;
+    int64_t* d_off = nullptr;      // n_queries+1 (source rows == resident rows for queries)
+    void* d_desc = nullptr;        // SIFT: SW128 atoms; ORB: (rows,32) u8; SURF: (rows,64) f32; BOWQ: (rows,128) f32
+    int32_t* d_norm = nullptr;     // SIFT
+    int32_t* d_frame = nullptr;    // SIFT: frame of each resident row
+    bool borrowed = false;         // buffers belong to ctx scratch (temporary batch of mcl_match_counts)
+};
+
+struct mcl_map {
+    mcl_ctx* ctx = nullptr;
+    int kind = 0;
+    int n_images = 0;
+    int64_t rows = 0, padded_rows = 0;
+    size_t resident_bytes = 0;
+    std::vector<int64_t> h_src_off, h_dst_off;
+    int64_t* d_src_off = nullptr;
+    int64_t* d_dst_off = nullptr;
+    void* d_desc = nullptr;
+    int32_t* d_norm = nullptr;
+    int32_t* d_img_of = nullptr;
+    mcl::sifttc::TileMeta* d_meta = nullptr;
+    int n_tiles = 0;
+    // chunk tables for a few granularities (tiles per chunk), picked per call from the query batch size
+    struct ChunkSet { int target = 0; int n = 0; mcl::sifttc::Chunk* d = nullptr; };
+    std::vector<ChunkSet> chunk_sets;
+    int max_rows_per_image = 0;
+};
+
+struct mcl_bow {
+    mcl_ctx* ctx = nullptr;
+    int n_loc = 0, W = 0;
+    int64_t total_images = 0, voc_rows = 0;
+    int max_words = 0;
+    std::vector<int64_t> h_voc_off, h_img_off;
+    float* d_voc = nullptr;
+    float* d_idf = nullptr;
+    float* d_imf = nullptr;
+    int64_t* d_voc_off = nullptr;
+    int64_t* d_img_off = nullptr;
+};
+
+namespace {
+
+struct ProfScope {
+    mcl_ctx* c;
+    int which;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(mcl_ctx* c_, int w, cudaStream_t s) : c(c_), which(w), st(s) {
+        if (c->profiling) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, st);
+        }
+        c->launches++;
+    }
+    ~ProfScope() {
+        if (a) {
+            cudaEventRecord(b, st);
+            c->prof[which].push_back({a, b});
+        }
+    }
+};
+
+inline int grid_for(int64_t n, int block, int cap) {
+    int64_t g = (n + block - 1) / block;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
+}
+
+int check_offsets(const int64_t* off, int n, const char* what) {
+    if (!off) return fail(MCL_EINVAL, "%s: offsets pointer is NULL", what);
+    if (off[0] != 0) return fail(MCL_EINVAL, "%s: offsets[0] must be 0", what);
+    for (int i = 0; i < n; ++i)
+        if (off[i + 1] < off[i]) return fail(MCL_EINVAL, "%s: offsets must be non-decreasing", what);
+    return MCL_OK;
+}
+
+size_t row_bytes(int kind, int dtype) {
+    switch (kind) {
+        case MCL_SIFT: return dtype == MCL_F32 ? 512 : 128;
+        case MCL_ORB: return 32;
+        case MCL_SURF: return 256;
+        case MCL_BOWQ: return dtype == MCL_F32 ? 512 : 128;
+    }
+    return 0;
+}
+
+// ingest (n_rows,128) rows from the host into the SW128-atom layout + norms + segment ids
+int ingest_rows128(mcl_ctx* c, cudaStream_t st, const void* h_src, int dtype, int64_t n_rows, int n_seg,
+                   const int64_t* d_src_off, const int64_t* d_dst_off, int64_t padded_rows, uint8_t* d_desc,
+                   int32_t* d_norm, int32_t* d_seg) {
+    CU(cudaMemsetAsync(d_desc, 0, (size_t)padded_rows * 128, st));
+    CU(cudaMemsetAsync(d_norm, 0xFF, (size_t)padded_rows * 4, st));
+    CU(cudaMemsetAsync(d_seg, 0xFF, (size_t)padded_rows * 4, st));
+    if (n_rows == 0) return MCL_OK;
+    const size_t bytes = (size_t)n_rows * (dtype == MCL_F32 ? 512 : 128);
+    CU(c->stage.ensure(bytes));
+    CU(cudaMemcpyAsync(c->stage.p, h_src, bytes, cudaMemcpyHostToDevice, st));
+    int* bad = c->flags.as<int>() + 2;
+    CU(cudaMemsetAsync(bad, 0, 4, st));
+    {
+        ProfScope ps(c, PROF_PREP, st);
+        const int grid = grid_for(n_rows * 32, 256, c->sm_count * 8);
+        if (dtype == MCL_F32)
+            mcl::prep_rows128_kernel<true><<<grid, 256, 0, st>>>(c->stage.p, n_rows, d_src_off, d_dst_off, n_seg, d_desc, d_norm, d_seg, bad);
+        else
+            mcl::prep_rows128_kernel<false><<<grid, 256, 0, st>>>(c->stage.p, n_rows, d_src_off, d_dst_off, n_seg, d_desc, d_norm, d_seg, bad);
+    }
+    CU(cudaGetLastError());
+    if (dtype == MCL_F32) {
+        int h_bad = 0;
+        CU(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (h_bad) return fail(MCL_EDATA, "SIFT descriptors must be integer valued in [0,255]");
+    }
+    return MCL_OK;
+}
+
+void build_chunks(const mcl_map* m, int target_tiles, std::vector<mcl::sifttc::Chunk>& out) {
+    using mcl::sifttc::TILE_N;
+    out.clear();
+    int i = 0;
+    const int n = m->n_images;
+    while (i < n) {
+        // skip empty images (they never get a group; their count stays 0)
+        if (m->h_dst_off[i + 1] == m->h_dst_off[i]) { ++i; continue; }
+        mcl::sifttc::Chunk ch;
+        ch.img_begin = i;
+        ch.tile_begin = (int)(m->h_dst_off[i] / TILE_N);
+        int j = i;
+        int tile_end = ch.tile_begin;
+        while (j < n) {
+            if (m->h_dst_off[j + 1] > m->h_dst_off[j]) tile_end = (int)((m->h_dst_off[j + 1] + TILE_N - 1) / TILE_N);
+            ++j;
+            if (tile_end - ch.tile_begin >= target_tiles) break;
+        }
+        ch.img_end = j;
+        ch.tile_end = tile_end;
+        out.push_back(ch);
+        i = j;
+    }
+}
+
+const mcl_map::ChunkSet* pick_chunks(const mcl_map* m, int n_qblocks, int sm_count) {
+    // want >= ~3 waves of work items (qblocks x chunks), chunks as long as possible beyond that
+    const mcl_map::ChunkSet* best = &m->chunk_sets.back();
+    for (const auto& cs : m->chunk_sets) {  // sorted by decreasing target
+        best = &cs;
+        if ((int64_t)cs.n * n_qblocks >= (int64_t)3 * sm_count) break;
+    }
+    return best;
+}
+
+}  // namespace
+
+// ================================================================================================
+// context
+// ================================================================================================
+extern "C" const char* mcl_last_error(void) { return g_err.c_str(); }
+
+extern "C" int mcl_init(int device_id, mcl_ctx** out) {
+    if (!out) return fail(MCL_EINVAL, "mcl_init: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(MCL_ENODEV, "no CUDA device (%s); libmcl has no CPU fallback", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+    if (device_id < 0 || device_id >= n) return fail(MCL_EINVAL, "device %d out of range (have %d)", device_id, n);
+    CU(cudaSetDevice(device_id));
+    mcl_ctx* c = new (std::nothrow) mcl_ctx();
+    if (!c) return fail(MCL_EINTERNAL, "out of host memory");
+    c->device = device_id;
+    e = cudaGetDeviceProperties(&c->prop, device_id);
+    if (e != cudaSuccess) { delete c; return fail(MCL_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    if (c->prop.major != 10) {
+        const int mj = c->prop.major, mn = c->prop.minor;
+        delete c;
+        return fail(MCL_ENODEV, "device %d is sm_%d%d; libmcl is built for sm_100a only and has no fallback", device_id, mj, mn);
+    }
+    c->sm_count = c->prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(MCL_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    e = c->flags.ensure(64);
+    if (e != cudaSuccess) { delete c; return fail(MCL_ECUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    cudaMemset(c->flags.p, 0, 64);
+    *out = c;
+    return MCL_OK;
+}
+
+extern "C" void mcl_shutdown(mcl_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& v : c->prof)
+        for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    DevBuf* bufs[] = {&c->stage, &c->cand, &c->flags, &c->row_arg, &c->bow_best, &c->lap_pix, &c->lap_meta, &c->filt,
+                      &c->tmp_counts, &c->tmp_mask, &c->tmp_words, &c->tmp_scores};
+    for (DevBuf* b : bufs) b->release();
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int mcl_device_info(mcl_ctx* c, int64_t info[8]) {
+    if (!c || !info) return fail(MCL_EINVAL, "mcl_device_info: NULL argument");
+    int clk = 0;
+    cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, c->device);
+    info[0] = c->sm_count;
+    info[1] = c->prop.major;
+    info[2] = c->prop.minor;
+    info[3] = (int64_t)(c->prop.totalGlobalMem >> 20);
+    info[4] = clk;
+    info[5] = c->prop.l2CacheSize;
+    info[6] = (int64_t)c->prop.sharedMemPerBlockOptin;
+    info[7] = 0;
+    return MCL_OK;
+}
+
+extern "C" int mcl_sync(mcl_ctx* c) {
+    if (!c) return fail(MCL_EINVAL, "mcl_sync: NULL context");
+    CU(cudaStreamSynchronize(c->stream));
+    return MCL_OK;
+}
+
+extern "C" int mcl_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(MCL_EINVAL, "mcl_host_alloc: out is NULL");
+    CU(cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocDefault));
+    return MCL_OK;
+}
+extern "C" void mcl_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int64_t mcl_launch_count(mcl_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int mcl_profile_enable(mcl_ctx* c, int on) {
+    if (!c) return fail(MCL_EINVAL, "NULL context");
+    c->profiling = on != 0;
+    return MCL_OK;
+}
+
+extern "C" int mcl_profile_read(mcl_ctx* c, int which, double* ms, int64_t* launches) {
+    if (!c || which < 0 || which >= PROF_N) return fail(MCL_EINVAL, "mcl_profile_read: bad argument");
+    CU(cudaStreamSynchronize(c->stream));
+    double total = 0;
+    int64_t n = 0;
+    for (auto& pr : c->prof[which]) {
+        cudaEventSynchronize(pr.second);
+        float t = 0;
+        if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) total += t;
+        ++n;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    c->prof[which].clear();
+    if (ms) *ms = total;
+    if (launches) *launches = n;
+    return MCL_OK;
+}
+
+// ================================================================================================
+// map index
+// ================================================================================================
+extern "C" void mcl_map_destroy(mcl_map* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    cudaFree(m->d_src_off);
+    cudaFree(m->d_dst_off);
+    cudaFree(m->d_desc);
+    cudaFree(m->d_norm);
+    cudaFree(m->d_img_of);
+    cudaFree(m->d_meta);
+    for (auto& cs : m->chunk_sets) cudaFree(cs.d);
+    delete m;
+}
+
+extern "C" int mcl_map_create(mcl_ctx* c, int kind, int n_images, const int64_t* row_offsets, const void* desc,
+                              int desc_dtype, mcl_map** out) {
+    if (!c || !out) return fail(MCL_EINVAL, "mcl_map_create: NULL argument");
+    *out = nullptr;
+    if (kind != MCL_SIFT && kind != MCL_ORB && kind != MCL_SURF) return fail(MCL_EINVAL, "mcl_map_create: bad kind %d", kind);
+    if (n_images < 0) return fail(MCL_EINVAL, "mcl_map_create: n_images < 0");
+    if ((kind == MCL_ORB && desc_dtype != MCL_U8) || (kind == MCL_SURF && desc_dtype != MCL_F32) ||
+        (desc_dtype != MCL_U8 && desc_dtype != MCL_F32))
+        return fail(MCL_EINVAL, "mcl_map_create: dtype %d not valid for kind %d", desc_dtype, kind);
+    int rc = check_offsets(row_offsets, n_images, "mcl_map_create");
+    if (rc) return rc;
+    const int64_t rows = row_offsets[n_images];
+    if (rows > 0 && !desc) return fail(MCL_EINVAL, "mcl_map_create: desc is NULL");
+    if (rows >= ((int64_t)1 << 31) - 4096) return fail(MCL_EINVAL, "mcl_map_create: too many rows for one shard");
+    CU(cudaSetDevice(c->device));
+    mcl_map* m = new (std::nothrow) mcl_map();
+    if (!m) return fail(MCL_EINTERNAL, "out of host memory");
+    m->ctx = c;
+    m->kind = kind;
+    m->n_images = n_images;
+    m->rows = rows;
+    m->h_src_off.assign(row_offsets, row_offsets + n_images + 1);
+    for (int i = 0; i < n_images; ++i)
+        m->max_rows_per_image = (int)std::max<int64_t>(m->max_rows_per_image, row_offsets[i + 1] - row_offsets[i]);
+    cudaStream_t st = c->stream;
+#define MCU(expr)                                                                                                 \
+    do {                                                                                                          \
+        cudaError_t e_ = (expr);                                                                                  \
+        if (e_ != cudaSuccess) {                                                                                  \
+            mcl_map_destroy(m);                                                                                   \
+            return fail(MCL_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+        }                                                                                                         \
+    } while (0)
+    MCU(cudaMalloc(&m->d_src_off, (size_t)(n_images + 1) * 8));
+    MCU(cudaMemcpyAsync(m->d_src_off, m->h_src_off.data(), (size_t)(n_images + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (kind == MCL_SIFT) {
+        using namespace mcl::sifttc;
+        m->h_dst_off.resize(n_images + 1);
+        int64_t acc = 0;
+        for (int i = 0; i < n_images; ++i) {
+            m->h_dst_off[i] = acc;
+            const int64_t r = row_offsets[i + 1] - row_offsets[i];
+            acc += (r + GROUP - 1) / GROUP * GROUP;
+        }
+        m->h_dst_off[n_images] = acc;
+        m->padded_rows = std::max<int64_t>(TILE_N, (acc + TILE_N - 1) / TILE_N * TILE_N);
+        m->n_tiles = (int)(m->padded_rows / TILE_N);
+        MCU(cudaMalloc(&m->d_dst_off, (size_t)(n_images + 1) * 8));
+        MCU(cudaMemcpyAsync(m->d_dst_off, m->h_dst_off.data(), (size_t)(n_images + 1) * 8, cudaMemcpyHostToDevice, st));
+        MCU(cudaMalloc(&m->d_desc, (size_t)m->padded_rows * 128));
+        MCU(cudaMalloc(&m->d_norm, (size_t)m->padded_rows * 4));
+        MCU(cudaMalloc(&m->d_img_of, (size_t)m->padded_rows * 4));
+        MCU(cudaMalloc(&m->d_meta, (size_t)m->n_tiles * sizeof(TileMeta)));
+        rc = ingest_rows128(c, st, desc, desc_dtype, rows, n_images, m->d_src_off, m->d_dst_off, m->padded_rows,
+                            (uint8_t*)m->d_desc, m->d_norm, m->d_img_of);
+        if (rc) { mcl_map_destroy(m); return rc; }
+        {
+            ProfScope ps(c, PROF_PREP, st);
+            build_meta_kernel<<<m->n_tiles, TILE_N, 0, st>>>(m->d_norm, m->d_img_of, m->d_src_off, m->n_tiles, m->d_meta);
+        }
+        MCU(cudaGetLastError());
+        std::vector<Chunk> ch;
+        int last_n = -1;
+        for (int target : {64, 32, 16, 8, 4, 2, 1}) {
+            build_chunks(m, target, ch);
+            if ((int)ch.size() == last_n) continue;
+            last_n = (int)ch.size();
+            mcl_map::ChunkSet cs;
+            cs.target = target;
+            cs.n = (int)ch.size();
+            if (cs.n) {
+                MCU(cudaMalloc(&cs.d, ch.size() * sizeof(Chunk)));
+                MCU(cudaMemcpyAsync(cs.d, ch.data(), ch.size() * sizeof(Chunk), cudaMemcpyHostToDevice, st));
+                MCU(cudaStreamSynchronize(st));  // ch is reused by the next iteration
+            }
+            m->chunk_sets.push_back(cs);
+        }
+        m->resident_bytes = (size_t)m->padded_rows * (128 + 8) + (size_t)m->n_tiles * sizeof(TileMeta);
+    } else {
+        const size_t rb = row_bytes(kind, desc_dtype);
+        m->padded_rows = rows;
+        MCU(cudaMalloc(&m->d_desc, std::max<size_t>((size_t)rows * rb, 256)));
+        if (rows) MCU(cudaMemcpyAsync(m->d_desc, desc, (size_t)rows * rb, cudaMemcpyHostToDevice, st));
+        m->resident_bytes = (size_t)rows * rb;
+    }
+    MCU(cudaStreamSynchronize(st));
+#undef MCU
+    *out = m;
+    return MCL_OK;
+}
+
+extern "C" int mcl_map_info(mcl_map* m, int64_t info[4]) {
+    if (!m || !info) return fail(MCL_EINVAL, "mcl_map_info: NULL argument");
+    info[0] = m->n_images;
+    info[1] = m->rows;
+    info[2] = m->padded_rows;
+    info[3] = (int64_t)m->resident_bytes;
+    return MCL_OK;
+}
+
+// ================================================================================================
+// query batch
+// ================================================================================================
+extern "C" void mcl_queries_destroy(mcl_queries* q) {
+    if (!q) return;
+    cudaSetDevice(q->ctx->device);
+    cudaStreamSynchronize(q->ctx->stream);
+    cudaFree(q->d_off);
+    cudaFree(q->d_desc);
+    cudaFree(q->d_norm);
+    cudaFree(q->d_frame);
+    delete q;
+}
+
+extern "C" int mcl_queries_create(mcl_ctx* c, int kind, int n_queries, const int64_t* q_row_offsets, const void* q_desc,
+                                  int q_dtype, mcl_queries** out) {
+    if (!c || !out) return fail(MCL_EINVAL, "mcl_queries_create: NULL argument");
+    *out = nullptr;
+    if (kind < MCL_SIFT || kind > MCL_BOWQ) return fail(MCL_EINVAL, "mcl_queries_create: bad kind %d", kind);
+    if (n_queries < 0) return fail(MCL_EINVAL, "mcl_queries_create: n_queries < 0");
+    if ((kind == MCL_ORB && q_dtype != MCL_U8) || (kind == MCL_SURF && q_dtype != MCL_F32) ||
+        (q_dtype != MCL_U8 && q_dtype != MCL_F32))
+        return fail(MCL_EINVAL, "mcl_queries_create: dtype %d not valid for kind %d", q_dtype, kind);
+    int rc = check_offsets(q_row_offsets, n_queries, "mcl_queries_create");
+    if (rc) return rc;
+    const int64_t rows = q_row_offsets[n_queries];
+    if (rows > 0 && !q_desc) return fail(MCL_EINVAL, "mcl_queries_create: q_desc is NULL");
+    if (rows >= ((int64_t)1 << 31) - 4096) return fail(MCL_EINVAL, "mcl_queries_create: too many rows");
+    CU(cudaSetDevice(c->device));
+    mcl_queries* q = new (std::nothrow) mcl_queries();
+    if (!q) return fail(MCL_EINTERNAL, "out of host memory");
+    q->ctx = c;
+    q->kind = kind;
+    q->n_queries = n_queries;
+    q->rows = rows;
+    q->h_off.assign(q_row_offsets, q_row_offsets + n_queries + 1);
+    cudaStream_t st = c->stream;
+#define QCU(expr)                                                                                                 \
+    do {                                                                                                          \
+        cudaError_t e_ = (expr);                                                                                  \
+        if (e_ != cudaSuccess) {                                                                                  \
+            mcl_queries_destroy(q);                                                                               \
+            return fail(MCL_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+        }                                                                                                         \
+    } while (0)
+    QCU(cudaMalloc(&q->d_off, (size_t)(n_queries + 1) * 8));
+    QCU(cudaMemcpyAsync(q->d_off, q->h_off.data(), (size_t)(n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (kind == MCL_SIFT) {
+        using namespace mcl::sifttc;
+        q->padded_rows = std::max<int64_t>(QBLK, (rows + QBLK - 1) / QBLK * QBLK);
+        QCU(cudaMalloc(&q->d_desc, (size_t)q->padded_rows * 128));
+        QCU(cudaMalloc(&q->d_norm, (size_t)q->padded_rows * 4));
+        QCU(cudaMalloc(&q->d_frame, (size_t)q->padded_rows * 4));
+        rc = ingest_rows128(c, st, q_desc, q_dtype, rows, n_queries, q->d_off, q->d_off, q->padded_rows,
+                            (uint8_t*)q->d_desc, q->d_norm, q->d_frame);
+        if (rc) { mcl_queries_destroy(q); return rc; }
+    } else if (kind == MCL_BOWQ) {
+        q->padded_rows = rows;
+        QCU(cudaMalloc(&q->d_desc, std::max<size_t>((size_t)rows * 512, 256)));
+        if (rows) {
+            if (q_dtype == MCL_F32) {
+                QCU(cudaMemcpyAsync(q->d_desc, q_desc, (size_t)rows * 512, cudaMemcpyHostToDevice, st));
+            } else {
+                QCU(c->stage.ensure((size_t)rows * 128));
+                QCU(cudaMemcpyAsync(c->stage.p, q_desc, (size_t)rows * 128, cudaMemcpyHostToDevice, st));
+                ProfScope ps(c, PROF_PREP, st);
+                mcl::u8_to_f32_kernel<<<grid_for(rows * 128, 256, c->sm_count * 8), 256, 0, st>>>(
+                    c->stage.as<uint8_t>(), (float*)q->d_desc, rows * 128);
+            }
+        }
+    } else {
+        const size_t rb = row_bytes(kind, q_dtype);
+        q->padded_rows = rows;
+        QCU(cudaMalloc(&q->d_desc, std::max<size_t>((size_t)rows * rb, 256)));
+        if (rows) QCU(cudaMemcpyAsync(q->d_desc, q_desc, (size_t)rows * rb, cudaMemcpyHostToDevice, st));
+    }
+    QCU(cudaStreamSynchronize(st));
+#undef QCU
+    *out = q;
+    return MCL_OK;
+}
+
+// ================================================================================================
+// matching
+// ================================================================================================
+namespace {
+
+int launch_sift_tc(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, cudaStream_t st) {
+    using namespace mcl::sifttc;
+    mcl_ctx* c = m->ctx;
+    const size_t smem = sizeof(Smem) + 1024;
+    if (!c->tc_attr_set) {
+        CU(cudaFuncSetAttribute(sift_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->tc_attr_set = true;
+    }
+    const int n_qblocks_total = (int)(q->padded_rows / QBLK);
+    // candidate buffer: sized for 1/4 of all (query row, image) pairs of a batch being candidates; an overflow is
+    // detected on the device and repaired by the exact SIMT kernel (see below), so this is only a performance knob.
+    const int64_t pairs_total = q->padded_rows * (int64_t)std::max(1, m->n_images);
+    const int64_t want = std::min<int64_t>(std::max<int64_t>(pairs_total / 4, 1 << 16), (int64_t)48 << 20);
+    if ((size_t)want > c->cand_cap_entries) {
+        CU(c->cand.ensure((size_t)want * sizeof(int4)));
+        c->cand_cap_entries = (size_t)want;
+    }
+    const int64_t cap = (int64_t)c->cand_cap_entries;
+    int batch_qblocks = (int)std::max<int64_t>(1, cap * 4 / ((int64_t)std::max(1, m->n_images) * QBLK));
+    batch_qblocks = std::min(batch_qblocks, n_qblocks_total);
+    unsigned int* d_cand_count = c->flags.as<unsigned int>();
+    int* d_overflow = c->flags.as<int>() + 1;
+    CU(cudaMemsetAsync(d_overflow, 0, 4, st));
+    for (int qb0 = 0; qb0 < n_qblocks_total; qb0 += batch_qblocks) {
+        const int nqb = std::min(batch_qblocks, n_qblocks_total - qb0);
+        const mcl_map::ChunkSet* cs = pick_chunks(m, nqb, c->sm_count);
+        if (cs->n == 0) break;
+        CU(cudaMemsetAsync(d_cand_count, 0, 4, st));
+        Params p;
+        p.q_desc = (const uint8_t*)q->d_desc + (size_t)qb0 * QBLK_BYTES;
+        p.q_norm = q->d_norm + (size_t)qb0 * QBLK;
+        p.m_desc = (const uint8_t*)m->d_desc;
+        p.m_meta = m->d_meta;
+        p.chunks = cs->d;
+        p.n_qblocks = nqb;
+        p.n_chunks = cs->n;
+        p.ratio = ratio;
+        p.cand = c->cand.as<int4>();
+        p.cand_count = d_cand_count;
+        p.cand_cap = (unsigned)cap;
+        p.overflow = d_overflow;
+        p.q_row_base = qb0 * QBLK;
+        const int64_t n_items = (int64_t)nqb * cs->n;
+        const int grid = (int)std::min<int64_t>(n_items, c->sm_count);
+        {
+            ProfScope ps(c, PROF_SIFT_TC, st);
+            sift_tc_kernel<<<grid, THREADS, smem, st>>>(p);
+        }
+        CU(cudaGetLastError());
+        {
+            ProfScope ps(c, PROF_SIFT_FIX, st);
+            sift_fixup_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->cand.as<int4>(), d_cand_count, (unsigned)cap,
+                                                              (const uint8_t*)q->d_desc, q->d_norm, q->d_frame,
+                                                              (const uint8_t*)m->d_desc, m->d_norm, ratio, m->n_images,
+                                                              d_counts);
+        }
+        CU(cudaGetLastError());
+    }
+    // exact repair if (and only if) a candidate list overflowed: the SIMT kernel overwrites every count
+    {
+        ProfScope ps(c, PROF_SIFT_SIMT, st);
+        dim3 grid(std::max(1, m->n_images), std::max(1, q->n_queries));
+        mcl::sift_simt_kernel<<<grid, 128, 0, st>>>((const uint8_t*)q->d_desc, q->d_norm, q->d_off, (const uint8_t*)m->d_desc,
+                                                    m->d_norm, m->d_dst_off, m->d_src_off, m->n_images, ratio, nullptr,
+                                                    d_overflow, d_counts);
+    }
+    CU(cudaGetLastError());
+    return MCL_OK;
+}
+
+int match_device(mcl_map* m, mcl_queries* q, int mode, double ratio, const uint8_t* d_mask, int32_t fill, int algo,
+                 int32_t* d_counts, cudaStream_t st) {
+    mcl_ctx* c = m->ctx;
+    const int nf = q->n_queries, ni = m->n_images;
+    const int64_t n_out = (int64_t)nf * ni;
+    if (n_out == 0) return MCL_OK;
+    if (nf > 65535) return fail(MCL_EINVAL, "at most 65535 query frames per call (got %d)", nf);
+    CU(cudaMemsetAsync(d_counts, 0, (size_t)n_out * 4, st));
+    if (q->rows > 0 && m->rows > 0) {
+        if (m->kind == MCL_SIFT) {
+            if (mode != MCL_KNN2_RATIO) return fail(MCL_EINVAL, "SIFT supports mode MCL_KNN2_RATIO only");
+            int use = algo;
+            if (use == MCL_ALGO_AUTO) {
+                // tensor cores pay off once the tile pipeline has work for every SM; DOR masks (<= 30 of the images per
+                // frame) and single small frames go to the SIMT kernel, which skips masked pairs entirely
+                const double macs = (double)q->rows * (double)m->rows;
+                use = (d_mask || macs < 4.0e6) ? MCL_ALGO_SIMT : MCL_ALGO_TENSOR;
+            }
+            if (use == MCL_ALGO_TENSOR) {
+                int rc = launch_sift_tc(m, q, ratio, d_counts, st);
+                if (rc) return rc;
+            } else {
+                ProfScope ps(c, PROF_SIFT_SIMT, st);
+                dim3 grid(ni, nf);
+                mcl::sift_simt_kernel<<<grid, 128, 0, st>>>((const uint8_t*)q->d_desc, q->d_norm, q->d_off,
+                                                            (const uint8_t*)m->d_desc, m->d_norm, m->d_dst_off, m->d_src_off,
+                                                            ni, ratio, d_mask, nullptr, d_counts);
+            }
+            CU(cudaGetLastError());
+        } else {
+            int64_t max_q = 0;
+            for (int f = 0; f < nf; ++f) max_q = std::max(max_q, q->h_off[f + 1] - q->h_off[f]);
+            const int zq = (int)std::max<int64_t>(1, (max_q + 127) / 128);
+            if (zq > 65535 || ni > 2147483647) return fail(MCL_EINVAL, "query frame too large");
+            dim3 grid(ni, nf, zq);
+            if (m->kind == MCL_ORB) {
+                if (mode == MCL_KNN2_RATIO) {
+                    ProfScope ps(c, PROF_ORB, st);
+                    mcl::orb_knn_kernel<<<grid, 128, 0, st>>>((const uint4*)q->d_desc, q->d_off, (const uint4*)m->d_desc,
+                                                              m->d_src_off, ni, ratio, d_mask, d_counts);
+                } else if (mode == MCL_CROSSCHECK) {
+                    CU(c->row_arg.ensure((size_t)q->rows * ni * 4));
+                    {
+                        ProfScope ps(c, PROF_ORB, st);
+                        mcl::orb_rowargmin_kernel<<<grid, 128, 0, st>>>((const uint4*)q->d_desc, q->d_off,
+                                                                        (const uint4*)m->d_desc, m->d_src_off, ni, d_mask,
+                                                                        c->row_arg.as<int32_t>());
+                    }
+                    CU(cudaGetLastError());
+                    const int zm = std::max(1, (m->max_rows_per_image + 127) / 128);
+                    dim3 grid2(ni, nf, zm);
+                    ProfScope ps(c, PROF_ORB, st);
+                    mcl::orb_crosscheck_kernel<<<grid2, 128, 0, st>>>((const uint4*)q->d_desc, q->d_off,
+                                                                      (const uint4*)m->d_desc, m->d_src_off, ni, d_mask,
+                                                                      c->row_arg.as<int32_t>(), d_counts);
+                } else {
+                    return fail(MCL_EINVAL, "bad mode %d", mode);
+                }
+            } else {  // SURF
+                if (mode != MCL_KNN2_RATIO) return fail(MCL_EINVAL, "SURF supports mode MCL_KNN2_RATIO only");
+                ProfScope ps(c, PROF_SURF, st);
+                mcl::surf_knn_kernel<<<grid, 128, 0, st>>>((const float4*)q->d_desc, q->d_off, (const float4*)m->d_desc,
+                                                           m->d_src_off, ni, ratio, d_mask, d_counts);
+            }
+            CU(cudaGetLastError());
+        }
+    }
+    if (d_mask) {
+        c->launches++;
+        mcl::apply_mask_kernel<<<grid_for(n_out, 256, c->sm_count * 4), 256, 0, st>>>(d_counts, d_mask, n_out, fill);
+        CU(cudaGetLastError());
+    }
+    return MCL_OK;
+}
+
+}  // namespace
+
+extern "C" int mcl_match_counts_device(mcl_map* m, mcl_queries* q, int mode, double ratio, const uint8_t* d_mask,
+                                       int32_t fill_value, int algo, int32_t* d_counts, void* stream) {
+    if (!m || !q || !d_counts) return fail(MCL_EINVAL, "mcl_match_counts_device: NULL argument");
+    if (m->ctx != q->ctx) return fail(MCL_EINVAL, "map and queries belong to different contexts");
+    if (m->kind != q->kind) return fail(MCL_EINVAL, "map kind %d != query kind %d", m->kind, q->kind);
+    if (!(ratio > 0.0) || !(ratio <= 1.0)) return fail(MCL_EINVAL, "ratio must be in (0,1]");
+    CU(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->ctx->stream;
+    return match_device(m, q, mode, ratio, d_mask, fill_value, algo, d_counts, st);
+}
+
+extern "C" int mcl_match_counts(mcl_map* m, int n_queries, const int64_t* q_row_offsets, const void* q_desc, int q_dtype,
+                                int mode, double ratio, const uint8_t* mask, int32_t fill_value, int algo,
+                                int32_t* out_counts) {
+    if (!m || !out_counts) return fail(MCL_EINVAL, "mcl_match_counts: NULL argument");
+    if (!(ratio > 0.0) || !(ratio <= 1.0)) return fail(MCL_EINVAL, "ratio must be in (0,1]");
+    mcl_ctx* c = m->ctx;
+    mcl_queries* q = nullptr;
+    int rc = mcl_queries_create(c, m->kind, n_queries, q_row_offsets, q_desc, q_dtype, &q);
+    if (rc) return rc;
+    const size_t n_out = (size_t)n_queries * m->n_images;
+    cudaStream_t st = c->stream;
+    auto body = [&]() -> int {
+        if (n_out == 0) return MCL_OK;
+        CU(c->tmp_counts.ensure(n_out * 4));
+        uint8_t* d_mask = nullptr;
+        if (mask) {
+            CU(c->tmp_mask.ensure(n_out));
+            CU(cudaMemcpyAsync(c->tmp_mask.p, mask, n_out, cudaMemcpyHostToDevice, st));
+            d_mask = c->tmp_mask.as<uint8_t>();
+        }
+        int r = match_device(m, q, mode, ratio, d_mask, fill_value, algo, c->tmp_counts.as<int32_t>(), st);
+        if (r) return r;
+        CU(cudaMemcpyAsync(out_counts, c->tmp_counts.p, n_out * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return MCL_OK;
+    };
+    rc = body();
+    mcl_queries_destroy(q);
+    return rc;
+}
+
+// ================================================================================================
+// bag of words
+// ================================================================================================
+extern "C" void mcl_bow_destroy(mcl_bow* b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    cudaFree(b->d_voc);
+    cudaFree(b->d_idf);
+    cudaFree(b->d_imf);
+    cudaFree(b->d_voc_off);
+    cudaFree(b->d_img_off);
+    delete b;
+}
+
+extern "C" int mcl_bow_create(mcl_ctx* c, int n_locations, const int64_t* voc_row_offsets, const float* voc,
+                              const float* idf, const int64_t* img_offsets, const float* im_features, int W,
+                              mcl_bow** out) {
+    if (!c || !out || !voc || !idf || !im_features) return fail(MCL_EINVAL, "mcl_bow_create: NULL argument");
+    *out = nullptr;
+    if (n_locations <= 0 || W <= 0) return fail(MCL_EINVAL, "mcl_bow_create: n_locations and W must be positive");
+    if ((size_t)W * 4 > 200 * 1024) return fail(MCL_EINVAL, "mcl_bow_create: W=%d does not fit the shared-memory histogram", W);
+    int rc = check_offsets(voc_row_offsets, n_locations, "mcl_bow_create(voc)");
+    if (rc) return rc;
+    rc = check_offsets(img_offsets, n_locations, "mcl_bow_create(images)");
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    mcl_bow* b = new (std::nothrow) mcl_bow();
+    if (!b) return fail(MCL_EINTERNAL, "out of host memory");
+    b->ctx = c;
+    b->n_loc = n_locations;
+    b->W = W;
+    b->h_voc_off.assign(voc_row_offsets, voc_row_offsets + n_locations + 1);
+    b->h_img_off.assign(img_offsets, img_offsets + n_locations + 1);
+    b->voc_rows = voc_row_offsets[n_locations];
+    b->total_images = img_offsets[n_locations];
+    for (int l = 0; l < n_locations; ++l) {
+        const int64_t nw = voc_row_offsets[l + 1] - voc_row_offsets[l];
+        if (nw > W) { delete b; return fail(MCL_EINVAL, "location %d has %lld words > W=%d", l, (long long)nw, W); }
+        if (nw <= 0) { delete b; return fail(MCL_EINVAL, "location %d has an empty vocabulary", l); }
+        b->max_words = (int)std::max<int64_t>(b->max_words, nw);
+    }
+    cudaStream_t st = c->stream;
+#define BCU(expr)                                                                                                 \
+    do {                                                                                                          \
+        cudaError_t e_ = (expr);                                                                                  \
+        if (e_ != cudaSuccess) {                                                                                  \
+            mcl_bow_destroy(b);                                                                                   \
+            return fail(MCL_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+        }                                                                                                         \
+    } while (0)
+    BCU(cudaMalloc(&b->d_voc, (size_t)b->voc_rows * 512));
+    BCU(cudaMalloc(&b->d_idf, (size_t)n_locations * W * 4));
+    BCU(cudaMalloc(&b->d_imf, std::max<size_t>((size_t)b->total_images * W * 4, 256)));
+    BCU(cudaMalloc(&b->d_voc_off, (size_t)(n_locations + 1) * 8));
+    BCU(cudaMalloc(&b->d_img_off, (size_t)(n_locations + 1) * 8));
+    BCU(cudaMemcpyAsync(b->d_voc, voc, (size_t)b->voc_rows * 512, cudaMemcpyHostToDevice, st));
+    BCU(cudaMemcpyAsync(b->d_idf, idf, (size_t)n_locations * W * 4, cudaMemcpyHostToDevice, st));
+    if (b->total_images)
+        BCU(cudaMemcpyAsync(b->d_imf, im_features, (size_t)b->total_images * W * 4, cudaMemcpyHostToDevice, st));
+    BCU(cudaMemcpyAsync(b->d_voc_off, b->h_voc_off.data(), (size_t)(n_locations + 1) * 8, cudaMemcpyHostToDevice, st));
+    BCU(cudaMemcpyAsync(b->d_img_off, b->h_img_off.data(), (size_t)(n_locations + 1) * 8, cudaMemcpyHostToDevice, st));
+    BCU(cudaFuncSetAttribute(mcl::bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W * 4));
+    BCU(cudaStreamSynchronize(st));
+#undef BCU
+    *out = b;
+    return MCL_OK;
+}
+
+extern "C" int mcl_bow_score_device(mcl_bow* b, mcl_queries* q, int32_t* d_words, float* d_scores, void* stream) {
+    if (!b || !q || !d_scores) return fail(MCL_EINVAL, "mcl_bow_score_device: NULL argument");
+    if (q->kind != MCL_BOWQ) return fail(MCL_EINVAL, "mcl_bow_score_device: queries must be of kind MCL_BOWQ");
+    if (b->ctx != q->ctx) return fail(MCL_EINVAL, "bow index and queries belong to different contexts");
+    mcl_ctx* c = b->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const int n_q = (int)q->rows;
+    const int nf = q->n_queries;
+    if (nf == 0) return MCL_OK;
+    if (nf > 65535) return fail(MCL_EINVAL, "at most 65535 query frames per call");
+    const size_t nbest = (size_t)b->n_loc * std::max(1, n_q);
+    CU(c->bow_best.ensure(nbest * 8));
+    CU(cudaMemsetAsync(c->bow_best.p, 0xFF, nbest * 8, st));
+    if (n_q > 0) {
+        dim3 grid((b->max_words + mcl::VQ_WORDS - 1) / mcl::VQ_WORDS, (n_q + 127) / 128, b->n_loc);
+        if (grid.y > 65535 || grid.z > 65535) return fail(MCL_EINVAL, "bow batch too large");
+        ProfScope ps(c, PROF_VQ, st);
+        mcl::bow_vq_kernel<<<grid, 128, 0, st>>>((const float4*)q->d_desc, n_q, (const float4*)b->d_voc, b->d_voc_off,
+                                                 c->bow_best.as<unsigned long long>());
+    }
+    CU(cudaGetLastError());
+    {
+        dim3 grid(b->n_loc, nf);
+        ProfScope ps(c, PROF_SCORE, st);
+        mcl::bow_score_kernel<<<grid, 256, (size_t)b->W * 4, st>>>(c->bow_best.as<unsigned long long>(), n_q, q->d_off, b->d_idf,
+                                                                   b->d_imf, b->d_img_off, b->W, (int)b->total_images,
+                                                                   d_words, d_scores);
+    }
+    CU(cudaGetLastError());
+    return MCL_OK;
+}
+
+extern "C" int mcl_bow_score(mcl_bow* b, int n_queries, const int64_t* q_row_offsets, const void* q_desc, int q_dtype,
+                             int32_t* out_words, float* out_scores) {
+    if (!b || !out_scores) return fail(MCL_EINVAL, "mcl_bow_score: NULL argument");
+    mcl_ctx* c = b->ctx;
+    mcl_queries* q = nullptr;
+    int rc = mcl_queries_create(c, MCL_BOWQ, n_queries, q_row_offsets, q_desc, q_dtype, &q);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    auto body = [&]() -> int {
+        const size_t n_scores = (size_t)n_queries * b->total_images;
+        const size_t n_words = (size_t)b->n_loc * q->rows;
+        if (n_queries == 0) return MCL_OK;
+        CU(c->tmp_scores.ensure(std::max<size_t>(n_scores * 4, 256)));
+        int32_t* d_words = nullptr;
+        if (out_words && n_words) {
+            CU(c->tmp_words.ensure(n_words * 4));
+            d_words = c->tmp_words.as<int32_t>();
+        }
+        int r = mcl_bow_score_device(b, q, d_words, c->tmp_scores.as<float>(), st);
+        if (r) return r;
+        if (n_scores) CU(cudaMemcpyAsync(out_scores, c->tmp_scores.p, n_scores * 4, cudaMemcpyDeviceToHost, st));
+        if (d_words) CU(cudaMemcpyAsync(out_words, d_words, n_words * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return MCL_OK;
+    };
+    rc = body();
+    mcl_queries_destroy(q);
+    return rc;
+}
+
+// ================================================================================================
+// small stages
+// ================================================================================================
+namespace {
+int laplacian_common(mcl_ctx* c, int n, const uint8_t* const* imgs, const int* h, const int* w, const int* stride,
+                     int64_t* sums_out, double* var_out) {
+    if (!c || (n > 0 && (!imgs || !h || !w))) return fail(MCL_EINVAL, "mcl_laplacian: NULL argument");
+    if (n <= 0) return MCL_OK;
+    if (n > 65535) return fail(MCL_EINVAL, "at most 65535 images per call");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    std::vector<int64_t> off(n + 1, 0);
+    int max_h = 0, max_w = 0;
+    for (int i = 0; i < n; ++i) {
+        if (h[i] <= 0 || w[i] <= 0 || !imgs[i]) return fail(MCL_EINVAL, "image %d: bad size or NULL pointer", i);
+        if (stride && stride[i] < w[i]) return fail(MCL_EINVAL, "image %d: stride < width", i);
+        off[i + 1] = off[i] + (((int64_t)h[i] * w[i] + 15) & ~(int64_t)15);
+        max_h = std::max(max_h, h[i]);
+        max_w = std::max(max_w, w[i]);
+    }
+    CU(c->lap_pix.ensure((size_t)off[n]));
+    // meta: off (n+1 int64) | h (n int) | w (n int) | sums (2n int64) | var (n double)
+    const size_t o_h = (size_t)(n + 1) * 8, o_w = o_h + (size_t)n * 4, o_s = (o_w + (size_t)n * 4 + 7) & ~(size_t)7,
+                 o_v = o_s + (size_t)n * 16, total = o_v + (size_t)n * 8;
+    CU(c->lap_meta.ensure(total));
+    uint8_t* mb = c->lap_meta.as<uint8_t>();
+    for (int i = 0; i < n; ++i) {
+        const int s = stride ? stride[i] : w[i];
+        CU(cudaMemcpy2DAsync(c->lap_pix.as<uint8_t>() + off[i], (size_t)w[i], imgs[i], (size_t)s, (size_t)w[i], (size_t)h[i],
+                             cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaMemcpyAsync(mb, off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(mb + o_h, h, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(mb + o_w, w, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(mb + o_s, 0, (size_t)n * 16, st));
+    {
+        dim3 grid((max_w + mcl::LAP_TW - 1) / mcl::LAP_TW, (max_h + mcl::LAP_TH - 1) / mcl::LAP_TH, n);
+        ProfScope ps(c, PROF_LAP, st);
+        mcl::laplacian_sums_kernel<<<grid, 256, 0, st>>>(c->lap_pix.as<uint8_t>(), (const int64_t*)mb, (const int*)(mb + o_h),
+                                                         (const int*)(mb + o_w), (long long*)(mb + o_s));
+    }
+    CU(cudaGetLastError());
+    if (var_out) {
+        c->launches++;
+        mcl::laplacian_var_kernel<<<(n + 127) / 128, 128, 0, st>>>((const long long*)(mb + o_s), (const int*)(mb + o_h),
+                                                                   (const int*)(mb + o_w), n, (double*)(mb + o_v));
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(var_out, mb + o_v, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (sums_out) CU(cudaMemcpyAsync(sums_out, mb + o_s, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MCL_OK;
+}
+}  // namespace
+
+extern "C" int mcl_laplacian_var(mcl_ctx* c, int n, const uint8_t* const* imgs, const int* h, const int* w, const int* stride,
+                                 double* out) {
+    if (n > 0 && !out) return fail(MCL_EINVAL, "mcl_laplacian_var: out is NULL");
+    return laplacian_common(c, n, imgs, h, w, stride, nullptr, out);
+}
+extern "C" int mcl_laplacian_sums(mcl_ctx* c, int n, const uint8_t* const* imgs, const int* h, const int* w, const int* stride,
+                                  int64_t* sums) {
+    if (n > 0 && !sums) return fail(MCL_EINVAL, "mcl_laplacian_sums: sums is NULL");
+    return laplacian_common(c, n, imgs, h, w, stride, sums, nullptr);
+}
+
+extern "C" int mcl_filter_step(mcl_ctx* c, int L, int I, int stages, char cmd, double blur, double* prev, const double* cur,
+                               double* out, int* best) {
+    if (!c || !prev || !cur || !out || !best) return fail(MCL_EINVAL, "mcl_filter_step: NULL argument");
+    if (L <= 0 || I <= 0) return fail(MCL_EINVAL, "mcl_filter_step: L and I must be positive");
+    if (stages <= 0 || stages > MCL_F_ALL) return fail(MCL_EINVAL, "mcl_filter_step: bad stages mask");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t n = (size_t)L * (1 + I);
+    // layout: prev | cur | out | scratch | factor (I) | best (2 ints)
+    const size_t total = (4 * n + I) * 8 + 16;
+    CU(c->filt.ensure(total));
+    double* d = c->filt.as<double>();
+    double *d_prev = d, *d_cur = d + n, *d_out = d + 2 * n, *d_scr = d + 3 * n, *d_fac = d + 4 * n;
+    int* d_best = reinterpret_cast<int*>(d_fac + I);
+    std::vector<double> fac(I);
+    for (int k = 0; k < I; ++k) fac[k] = 0.05 * std::fabs(std::sin((double)(k * 15 * 180) / M_PI));  // analyze.py:331 (sic)
+    CU(cudaMemcpyAsync(d_prev, prev, n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_cur, cur, n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_fac, fac.data(), (size_t)I * 8, cudaMemcpyHostToDevice, st));
+    c->launches++;
+    mcl::filter_step_kernel<<<1, 256, 0, st>>>(L, I, stages, (int)cmd, blur, d_prev, d_cur, d_fac, d_out, d_best, d_scr);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(prev, d_prev, n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(best, d_best, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MCL_OK;
+}
+
+// ================================================================================================
+// peak microbenchmarks (roofline denominators that MEASURED_PEAKS.json does not carry: int8 tensor pipe, popc pipe)
+// ================================================================================================
+extern "C" int mcl_microbench(mcl_ctx* c, int which, int iters, double* out /* [0]=ops/s, [1]=ms */) {
+    if (!c || !out) return fail(MCL_EINVAL, "mcl_microbench: NULL argument");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    double ops = 0;
+    CU(c->stage.ensure(1 << 20));
+    if (which == 0) {  // tcgen05 kind::i8, 128x128x32 MMAs back to back from shared memory, one CTA per SM
+        const size_t smem = 2 * 16384 + 1024 + 64;
+        CU(cudaFuncSetAttribute(mcl::i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mcl::i8_peak_kernel<<<c->sm_count, 128, smem, st>>>(iters / 8 + 1, c->stage.as<int>());  // warm-up
+        CU(cudaEventRecord(a, st));
+        mcl::i8_peak_kernel<<<c->sm_count, 128, smem, st>>>(iters, c->stage.as<int>());
+        CU(cudaEventRecord(b, st));
+        ops = 2.0 * 128 * 128 * 32 * 16.0 * (double)iters * c->sm_count;
+    } else if (which == 1) {  // popc.b32 + xor issue rate
+        mcl::popc_peak_kernel<<<c->sm_count * 8, 256, 0, st>>>(iters / 8 + 1, c->stage.as<int>());
+        CU(cudaEventRecord(a, st));
+        mcl::popc_peak_kernel<<<c->sm_count * 8, 256, 0, st>>>(iters, c->stage.as<int>());
+        CU(cudaEventRecord(b, st));
+        ops = 16.0 * (double)iters * 256.0 * c->sm_count * 8;  // popc32 results
+    } else {
+        return fail(MCL_EINVAL, "mcl_microbench: which must be 0 (int8 tensor) or 1 (popc)");
+    }
+    c->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaEventSynchronize(b));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    out[0] = ops / (ms * 1e-3);
+    out[1] = ms;
+    return MCL_OK;
+}

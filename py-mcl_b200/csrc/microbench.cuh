@@ -1,0 +1,74 @@
+// Peak microbenchmarks for the two pipes that bound the hot path and that MEASURED_PEAKS.json does not carry.
+#pragma once
+#include "common.cuh"
+
+namespace mcl {
+
+// tcgen05.mma kind::i8 (u8 x u8 -> s32), M=128 N=128 K=32 per instruction, operands resident in shared memory.
+// One CTA per SM, one issuing thread; 16 MMAs per iteration into two accumulators (256 TMEM columns).
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int* __restrict__ sink) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* a = base;
+    uint8_t* b = base + 16384;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + 32768);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(base + 32768 + 16);
+    for (int i = threadIdx.x; i < 32768 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0x01010101u * (i & 3);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    // make the generic-proxy smem writes visible to the async proxy (tensor core reads)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (threadIdx.x < 32) tmem_alloc<256>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (threadIdx.x == 0) {
+        constexpr uint32_t idesc = umma_idesc(2, 0, 0, 128, 128);
+        const uint64_t da = umma_desc_sw128(smem_u32(a));
+        const uint64_t db = umma_desc_sw128(smem_u32(b));
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_i8(tmem + (r & 1) * 128, da + 2 * k, db + 2 * k, idesc, (it | r | k) != 0);
+            }
+        }
+        tc_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    uint32_t v[16];
+    tmem_ld16(tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16), v);
+    tmem_ld_wait(v);
+    if (v[0] == 0xdeadbeefu) sink[blockIdx.x] = (int)v[1];
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<256>(tmem);
+}
+
+// XOR + popc.b32: 16 independent results per iteration per thread
+__global__ void __launch_bounds__(256) popc_peak_kernel(int iters, int* __restrict__ sink) {
+    unsigned x[16];
+    int acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        x[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
+        acc[i] = 0;
+    }
+    unsigned y = threadIdx.x ^ 0x9e3779b9u;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] += __popc(x[i] ^ y);
+        y += 0x7f4a7c15u;
+    }
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 0x7fffffff) sink[0] = s;
+}
+
+}  // namespace mcl

@@ -1,0 +1,93 @@
+"""Sharding of the map across the GPUs of one box (one process per GPU, torch.distributed).
+
+Every (query descriptor, map image) top-2 is independent of every other map image, so whole images are
+partitioned across ranks (contiguous slices balanced by descriptor count); the query batch is identical on
+every rank (same files, same deterministic cv2 extraction, or broadcast by the caller); each rank matches
+against its slice and ONE all-gather of the int32 per-image counts follows.  There is no
+other data-path collective.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def shard_bounds(rows_per_image, world):
+    """Contiguous image ranges [(lo, hi)] * world, balanced by descriptor rows (+1 per image so that empty
+    images spread too): image i goes to the rank whose share of the total weight holds i's midpoint.
+    Deterministic; every rank computes the same table."""
+    n = len(rows_per_image)
+    if n == 0:
+        return [(0, 0)] * world
+    w = np.asarray(rows_per_image, dtype=np.int64) + 1
+    csum = np.cumsum(w)
+    total = int(csum[-1])
+    mid2 = 2 * csum - w                      # 2 * midpoint, exact integers
+    owner = np.minimum((mid2 * world) // (2 * total), world - 1)
+    edges = np.searchsorted(owner, np.arange(world + 1), side="left")
+    return [(int(edges[r]), int(edges[r + 1])) for r in range(world)]
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist
+    except Exception:
+        pass
+    return None
+
+
+class ShardedMap(object):
+    """All map images of all locations, flattened, with this rank's slice resident on its GPU."""
+
+    def __init__(self, kind, descs, ctx=None, local_factory=None, group=None):
+        self.kind = kind
+        self.n_images = len(descs)
+        self.group = group
+        d = _dist()
+        self.world = d.get_world_size(group) if d else 1
+        self.rank = d.get_rank(group) if d else 0
+        rows = [0 if x is None else len(x) for x in descs]
+        self.bounds = shard_bounds(rows, self.world)
+        lo, hi = self.bounds[self.rank]
+        self.lo, self.hi = lo, hi
+        if local_factory is None:
+            ctx = ctx or _lib.default_context()
+            self.local = _lib.MapIndex(ctx, kind, descs[lo:hi])
+        else:
+            self.local = local_factory(descs[lo:hi])
+
+    def close(self):
+        if hasattr(self.local, "close"):
+            self.local.close()
+
+    def match_counts(self, q_descs, mode=_lib.KNN2_RATIO, ratio=0.7, mask=None, fill_value=1, algo=_lib.ALGO_AUTO):
+        """(n_queries, n_images) int32 on every rank."""
+        lo, hi = self.lo, self.hi
+        local_mask = None if mask is None else np.ascontiguousarray(np.asarray(mask)[:, lo:hi])
+        local = self.local.match_counts(q_descs, mode=mode, ratio=ratio, mask=local_mask, fill_value=fill_value, algo=algo)
+        return self.gather(local)
+
+    def gather(self, local):
+        """all-gather of the per-image counts: local (F, hi-lo) -> (F, n_images)."""
+        if self.world == 1:
+            return local
+        import torch
+        d = _dist()
+        F = local.shape[0]
+        maxw = max(h - l for l, h in self.bounds)
+        pad = np.zeros((F, maxw), dtype=local.dtype)
+        pad[:, :local.shape[1]] = local
+        t = torch.from_numpy(pad)
+        cuda = d.get_backend(self.group) == "nccl"
+        if cuda:
+            t = t.cuda()
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        d.all_gather_into_tensor(out, t, group=self.group)
+        out = out.cpu().numpy()
+        full = np.empty((F, self.n_images), dtype=local.dtype)
+        for r, (l, h) in enumerate(self.bounds):
+            full[:, l:h] = out[r][:, :h - l]
+        return full

@@ -1,0 +1,322 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via ctypes) against the CPU oracle on the same seeded
+inputs, and against the golden fixtures produced by the unmodified reference (tests/golden/, oracle/make_golden.py).
+Bit-exact for SIFT / ORB counts, Laplacian sums and the filter update; SURF / BOW under the stated tolerances."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle  # oracle/oracle.py: test infrastructure only
+import pymcl_b200  # noqa: F401
+from pymcl_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def split(mat, off):
+    return [mat[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
+def oracle_counts(fn, qs, ms):
+    return np.array([[fn(q, m) for m in ms] for q in qs], dtype=np.int32)
+
+
+# ------------------------------------------------------------------------------------------------
+# SIFT
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", [_lib.ALGO_SIMT, _lib.ALGO_TENSOR, _lib.ALGO_AUTO])
+def test_sift_golden_reference_counts(ctx, golden_dir, algo):
+    """Descriptors extracted by the reference run + the reference's own SIFTMatch counts (exact search)."""
+    z = np.load(os.path.join(golden_dir, "sift_desc_case.npz"))
+    qs, ms = split(z["q"], z["q_off"]), split(z["m"], z["m_off"])
+    m = _lib.MapIndex(ctx, "SIFT", ms)
+    got = m.match_counts(qs, algo=algo)
+    assert np.array_equal(got, z["counts"])
+    # float32 integer-valued input (what cv2 hands over) takes the same path
+    got32 = m.match_counts([q.astype(np.float32) for q in qs], algo=algo)
+    assert np.array_equal(got32, z["counts"])
+    m.close()
+
+
+@pytest.mark.parametrize("algo", [_lib.ALGO_SIMT, _lib.ALGO_TENSOR])
+@pytest.mark.parametrize("nm,nq,n_images,n_frames", [(256, 256, 12, 5), (300, 150, 9, 3), (37, 61, 20, 4),
+                                                     (1000, 700, 3, 2)])
+def test_sift_synthetic_vs_oracle(ctx, algo, nm, nq, n_images, n_frames):
+    map_des, frames = synth.sift_map_and_frames(11 + nm, n_images, nm, n_frames, nq)
+    want = oracle_counts(oracle.sift_pair_count, frames, map_des)
+    m = _lib.MapIndex(ctx, "SIFT", map_des)
+    got = m.match_counts(frames, algo=algo)
+    m.close()
+    assert want.sum() > 0
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("algo", [_lib.ALGO_SIMT, _lib.ALGO_TENSOR])
+def test_sift_ragged_and_edge_cases(ctx, algo):
+    """Variable descriptors per image incl. 0, 1, 2, 15, 16, 17, 128, 129 rows; empty frames; duplicates."""
+    rng = np.random.default_rng(5)
+    sizes = [0, 1, 2, 15, 16, 17, 128, 129, 0, 255, 3, 640]
+    map_des = [synth.sift_like(rng, n) if n else None for n in sizes]
+    map_des[4][3] = map_des[4][9]  # duplicate rows inside one image: d0 == d1 -> never a match
+    frames = [synth.sift_like(rng, 200), None, synth.sift_like(rng, 1), synth.sift_like(rng, 513)]
+    frames[0][:50] = synth.sift_noisy_copy(rng, map_des[11][:50], 4.0)
+    frames[3][:100] = synth.sift_noisy_copy(rng, map_des[9][:100], 3.0)
+    frames[3][100:110] = map_des[3][:10]  # exact copies (d0 = 0)
+    want = oracle_counts(oracle.sift_pair_count, frames, map_des)
+    m = _lib.MapIndex(ctx, "SIFT", map_des)
+    got = m.match_counts(frames, algo=algo)
+    m.close()
+    assert np.array_equal(got, want)
+    assert got[1].sum() == 0 and got[:, 0].sum() == 0 and got[:, 1].sum() == 0
+
+
+def test_sift_ratio_known_answers(ctx, golden_dir):
+    """The cv2 ratio semantics float(sqrtf(d0^2)) < 0.7*float(sqrtf(d1^2)) on the survey's integer pairs:
+    build 1 query row and 2 map rows with exactly those squared distances."""
+    kat = json.load(open(os.path.join(golden_dir, "kat.json")))["sift_ratio"]
+
+    def rows_with_d2(d2):
+        # decompose d2 into a sum of squares <= 255^2 spread over 128 dims
+        v = np.zeros(128, dtype=np.int64)
+        rem = d2
+        i = 0
+        while rem > 0:
+            s = min(255, int(np.floor(np.sqrt(rem))))
+            v[i] = s
+            rem -= s * s
+            i += 1
+        assert i <= 128
+        return v
+
+    for algo in (_lib.ALGO_SIMT, _lib.ALGO_TENSOR):
+        for d0, d1, expect in kat:
+            q = np.zeros((1, 128), np.uint8)
+            m = np.stack([rows_with_d2(d0), rows_with_d2(d1)]).astype(np.uint8)
+            assert oracle.sift_pair_count(q, m) == int(expect)
+            mi = _lib.MapIndex(ctx, "SIFT", [m])
+            got = mi.match_counts([q], algo=algo)
+            mi.close()
+            assert int(got[0, 0]) == int(expect), (d0, d1, algo)
+
+
+def test_sift_mask_fill(ctx):
+    map_des, frames = synth.sift_map_and_frames(3, 10, 120, 4, 90)
+    want = oracle_counts(oracle.sift_pair_count, frames, map_des)
+    rng = np.random.default_rng(0)
+    mask = (rng.random((4, 10)) < 0.4).astype(np.uint8)
+    m = _lib.MapIndex(ctx, "SIFT", map_des)
+    for algo in (_lib.ALGO_AUTO, _lib.ALGO_TENSOR, _lib.ALGO_SIMT):
+        got = m.match_counts(frames, mask=mask, fill_value=1, algo=algo)
+        assert np.array_equal(got, np.where(mask > 0, want, 1))
+    m.close()
+
+
+def test_sift_rejects_non_integer(ctx):
+    bad = np.full((4, 128), 0.5, dtype=np.float32)
+    with pytest.raises(_lib.MclError):
+        _lib.MapIndex(ctx, "SIFT", [bad])
+
+
+def test_sift_full_size_properties(ctx):
+    """BASELINE cfg3 tile shape (2048 x 2048 per pair) at a reduced image count: size-independent properties.
+    (a) planted copies are found: the planted image gets >= 90% of its planted rows, others stay near 0;
+    (b) permuting the map images permutes the counts; (c) tensor-core and SIMT paths agree bit-exactly."""
+    map_des, frames = synth.sift_map_and_frames(3, 6, 2048, 2, 2048, planted_frac=0.25, sigma=4.0)
+    m = _lib.MapIndex(ctx, "SIFT", map_des)
+    tc = m.match_counts(frames, algo=_lib.ALGO_TENSOR)
+    simt = m.match_counts(frames, algo=_lib.ALGO_SIMT)
+    m.close()
+    assert np.array_equal(tc, simt)
+    for f in range(2):
+        planted = (f * 7) % 6
+        assert tc[f, planted] >= 0.9 * 512
+        assert np.delete(tc[f], planted).max() < 64
+    perm = [3, 0, 5, 1, 4, 2]
+    m2 = _lib.MapIndex(ctx, "SIFT", [map_des[i] for i in perm])
+    tc2 = m2.match_counts(frames, algo=_lib.ALGO_TENSOR)
+    m2.close()
+    assert np.array_equal(tc2, tc[:, perm])
+
+
+# ------------------------------------------------------------------------------------------------
+# ORB
+# ------------------------------------------------------------------------------------------------
+def test_orb_golden_reference_counts(ctx, golden_dir):
+    z = np.load(os.path.join(golden_dir, "orb_desc_case.npz"))
+    qs, ms = split(z["q"], z["q_off"]), split(z["m"], z["m_off"])
+    m = _lib.MapIndex(ctx, "ORB", ms)
+    assert np.array_equal(m.match_counts(qs, mode=_lib.KNN2_RATIO), z["counts_knn"])
+    assert np.array_equal(m.match_counts(qs, mode=_lib.CROSSCHECK), z["counts_crosscheck"])
+    m.close()
+
+
+def test_orb_cfg1_vs_oracle(ctx):
+    """BASELINE config 1 at full size: one (500,32) query vs 50 images of (500,32)."""
+    map_des, q = synth.orb_map_and_query(1)
+    m = _lib.MapIndex(ctx, "ORB", map_des)
+    want_knn = oracle_counts(oracle.orb_pair_count_knn, [q], map_des)
+    want_cc = oracle_counts(oracle.orb_pair_count_crosscheck, [q], map_des)
+    assert want_knn.sum() > 50
+    assert np.array_equal(m.match_counts([q], mode=_lib.KNN2_RATIO), want_knn)
+    assert np.array_equal(m.match_counts([q], mode=_lib.CROSSCHECK), want_cc)
+    m.close()
+
+
+def test_orb_ragged_ties_and_mask(ctx):
+    rng = np.random.default_rng(9)
+    sizes = [0, 1, 2, 3, 127, 128, 129, 257, 700]
+    map_des = [synth.orb_like(rng, n) if n else None for n in sizes]
+    # low-entropy rows -> many distance ties (first-index tie-breaking matters for crossCheck)
+    map_des[6] = (rng.integers(0, 2, size=(129, 32)) * 255).astype(np.uint8)
+    frames = [synth.orb_like(rng, 300), (rng.integers(0, 2, size=(140, 32)) * 255).astype(np.uint8), None,
+              synth.orb_like(rng, 1)]
+    frames[0][:80] = synth.orb_flip(rng, map_des[8][:80], 30)
+    want_knn = oracle_counts(oracle.orb_pair_count_knn, frames, map_des)
+    want_cc = oracle_counts(oracle.orb_pair_count_crosscheck, frames, map_des)
+    m = _lib.MapIndex(ctx, "ORB", map_des)
+    assert np.array_equal(m.match_counts(frames, mode=_lib.KNN2_RATIO), want_knn)
+    assert np.array_equal(m.match_counts(frames, mode=_lib.CROSSCHECK), want_cc)
+    mask = (rng.random(want_knn.shape) < 0.5).astype(np.uint8)
+    assert np.array_equal(m.match_counts(frames, mode=_lib.KNN2_RATIO, mask=mask, fill_value=1),
+                          np.where(mask > 0, want_knn, 1))
+    assert np.array_equal(m.match_counts(frames, mode=_lib.CROSSCHECK, mask=mask, fill_value=7),
+                          np.where(mask > 0, want_cc, 7))
+    m.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# SURF (float L2; tolerance: rows whose ratio is within 1e-6 relative of the threshold may flip)
+# ------------------------------------------------------------------------------------------------
+def test_surf_vs_oracle_with_tie_tolerance(ctx):
+    rng = np.random.default_rng(4)
+    map_des = [synth.surf_like(rng, n) for n in (300, 64, 1024, 2, 1, 513)]
+    frames = [synth.surf_like(rng, 400), synth.surf_like(rng, 1024)]
+    frames[0][:120] = synth.surf_noisy_copy(rng, map_des[0][:120])
+    frames[1][:300] = synth.surf_noisy_copy(rng, map_des[2][:300])
+    m = _lib.MapIndex(ctx, "SURF", map_des)
+    got = m.match_counts(frames)
+    m.close()
+    for f, q in enumerate(frames):
+        for i, d in enumerate(map_des):
+            want, ambiguous = oracle.surf_pair_count(q, d, tie_rel=1e-6)
+            assert abs(int(got[f, i]) - want) <= ambiguous, (f, i, got[f, i], want, ambiguous)
+    assert got[0, 0] >= 100 and got[1, 2] >= 250 and got[:, 4].sum() == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# BOW
+# ------------------------------------------------------------------------------------------------
+def test_bow_golden_reference(ctx, golden_dir):
+    z = np.load(os.path.join(golden_dir, "bow_case.npz"))
+    W = int(z["num_words"])
+    # the reference's own histogram width is self.numWords; the golden index was built with numWords=200
+    bow = _lib.BowIndex(ctx, [(z["im_features"], z["idf"], z["voc"])], z["im_features"].shape[1])
+    scores, words = bow.score([z["qdes"]], want_words=True)
+    bow.close()
+    ow, gap = oracle.bow_words(z["qdes"], z["voc"])
+    differ = words[0] != z["words"]
+    assert np.all(gap[differ] < 1e-5), "visual words may differ from scipy's only on fp32 near-ties"
+    if not differ.any():
+        assert np.allclose(scores, z["score"], rtol=0, atol=1e-6)
+    assert W == z["im_features"].shape[1]
+
+
+def test_bow_multi_location_vs_oracle(ctx):
+    W = 256
+    locs, dess = [], []
+    for l in range(3):
+        im, idf, voc, des = synth.bow_index(50 + l, n_images=6 + l, num_words=W, voc_rows=W - 3 * l, des_per_image=120)
+        locs.append((im, idf, voc))
+        dess.append(des)
+    rng = np.random.default_rng(8)
+    frames = [synth.sift_noisy_copy(rng, dess[1][2], 3.0), synth.sift_like(rng, 77), None]
+    bow = _lib.BowIndex(ctx, locs, W)
+    scores, words = bow.score(frames, want_words=True)
+    bow.close()
+    allq = np.vstack([f for f in frames if f is not None])
+    col = 0
+    for l, (im, idf, voc) in enumerate(locs):
+        ow, gap = oracle.bow_words(allq, voc)
+        differ = words[l] != ow
+        assert np.all(gap[differ] < 1e-5)
+        pos = 0
+        for f, q in enumerate(frames):
+            n = 0 if q is None else len(q)
+            want = oracle.bow_score_from_words(words[l, pos:pos + n], idf, im, W)
+            assert np.allclose(scores[f, col:col + len(im)], want[0], rtol=0, atol=2e-6)
+            pos += n
+        col += len(im)
+    # frame 0 re-observes image 2 of location 1: it must win there
+    off1 = len(locs[0][0])
+    assert int(np.argmax(scores[0, off1:off1 + len(locs[1][0])])) == 2
+
+
+# ------------------------------------------------------------------------------------------------
+# Laplacian variance
+# ------------------------------------------------------------------------------------------------
+def test_laplacian_sums_exact_and_var(ctx):
+    import cv2
+    rng = np.random.default_rng(2)
+    imgs = [rng.integers(0, 256, size=s, dtype=np.uint8) for s in [(600, 800), (1, 1), (1, 7), (9, 1), (2, 2), (33, 129),
+                                                                    (240, 320), (481, 641)]]
+    imgs.append(cv2.GaussianBlur(imgs[0], (0, 0), 2.0))
+    imgs.append(np.full((50, 60), 200, np.uint8))
+    sums = ctx.laplacian_sums(imgs)
+    var = ctx.laplacian_var(imgs)
+    for im, s, v in zip(imgs, sums, var):
+        s1, s2, n = oracle.laplacian_sums(im)
+        assert (int(s[0]), int(s[1])) == (s1, s2)
+        assert v == oracle.laplacian_var(im)
+        ref = oracle.cv2_laplacian_var(im)
+        assert abs(v - ref) <= 1e-9 * max(1.0, abs(ref))
+    # non-contiguous rows (stride > width)
+    big = rng.integers(0, 256, size=(100, 300), dtype=np.uint8)
+    view = big[:, 17:217]
+    assert ctx.laplacian_var([view])[0] == oracle.laplacian_var(np.ascontiguousarray(view))
+
+
+# ------------------------------------------------------------------------------------------------
+# particle filter update
+# ------------------------------------------------------------------------------------------------
+def _state(rng, L, I):
+    return [[float(rng.integers(1, 400)), list(rng.random(I))] for _ in range(L)]
+
+
+@pytest.mark.parametrize("L,I", [(7, 25), (3, 25), (64, 50)])
+def test_filter_step_bit_exact(ctx, L, I):
+    import copy
+    rng = np.random.default_rng(L * 100 + I)
+    for trial in range(12):
+        prev = _state(rng, L, I)
+        cur = _state(rng, L, I)
+        cmd = "lrfbs"[trial % 5]
+        blur = [0.0, 37.5, 199.999, 200.0, 200.1, 913.2][trial % 6]
+        if cmd == "f" and I == 25:  # make both forward branches fire
+            bc = 0 if trial % 2 else L - 1
+            prev[bc][0] = 1000.0
+            prev[bc][1][3 if trial % 2 else 20] = 2.0
+        o_prev = copy.deepcopy(prev)
+        if I == 25:
+            adj, best = oracle.filter_step(cmd, o_prev, cur, blur)
+        else:  # oracle is written for 15-degree steps too; generalised sizes share the code
+            adj, best = oracle.filter_step(cmd, o_prev, cur, blur)
+        p = np.array([[c[0]] + c[1] for c in prev])
+        c = np.array([[x[0]] + x[1] for x in cur])
+        prev2, out, gbest = ctx.filter_step(_lib.F_ALL, cmd, blur, p, c)
+        want = np.array([[a[0]] + a[1] for a in adj])
+        wprev = np.array([[a[0]] + a[1] for a in o_prev])
+        assert np.array_equal(out, want), (cmd, blur)
+        assert np.array_equal(prev2, wprev)
+        assert gbest == tuple(best)
+
+
+def test_filter_forward_factor_table(ctx):
+    """0.05*|sin(k*15*180/pi)| (sic, analyze.py:331) through the kernel: bump of the neighbour's total."""
+    for k in range(1, 12):
+        prev = [[1.0, [0.0] * 25] for _ in range(3)]
+        prev[0][0] = 5.0
+        prev[0][1][k] = 1.0
+        p = np.array([[c[0]] + c[1] for c in prev])
+        prev2, _, _ = ctx.filter_step(_lib.F_COMMAND, "f", 0.0, p, p)
+        assert prev2[1, 0] == 1.0 * (1 + oracle.forward_factor(k))
