@@ -218,7 +218,9 @@ def main():
     packed_pinned = (packed[0], pin, packed[2])
     queries = _lib.QueryBatch(ctx, "SIFT", packed=packed_pinned)   # resident copy for `value`
 
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library launches on it, torch's events and NCCL see the same stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     d_counts = torch.zeros((n_frames, n_images), dtype=torch.int32, device="cuda")
     d_all = torch.zeros((world, n_frames, n_images), dtype=torch.int32, device="cuda") if world > 1 else None
 

@@ -49,6 +49,9 @@ int mcl_sync(mcl_ctx* ctx);
 /* pinned host memory for the end-to-end path (cudaHostAlloc) */
 int mcl_host_alloc(size_t bytes, void** out);
 void mcl_host_free(void* p);
+/* tuning / diagnostic switches (development aid, no reference counterpart).  option 0: SIFT tensor-core kernel
+ * epilogue variant, 0 = product, 1 = TMEM-read-only, 2 = max-only (1 and 2 give meaningless counts; profiling only). */
+int mcl_set_option(mcl_ctx* ctx, int option, int value);
 /* number of kernels this library launched since mcl_init (bench.py's gpu_launches) */
 int64_t mcl_launch_count(mcl_ctx* ctx);
 /* per-kernel device timing with CUDA events on the launching stream.  which: 0 = SIFT tensor-core kernel,

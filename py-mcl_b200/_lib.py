@@ -45,6 +45,7 @@ SIGNATURES = {
     "mcl_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_p)]),
     "mcl_host_free": (None, [_p]),
     "mcl_launch_count": (C.c_int64, [_p]),
+    "mcl_set_option": (C.c_int, [_p, C.c_int, C.c_int]),
     "mcl_profile_enable": (C.c_int, [_p, C.c_int]),
     "mcl_profile_read": (C.c_int, [_p, C.c_int, C.POINTER(C.c_double), _i64p]),
     "mcl_map_create": (C.c_int, [_p, C.c_int, C.c_int, _i64p, _p, C.c_int, C.POINTER(_p)]),
@@ -167,6 +168,9 @@ class Context:
 
     def sync(self):
         _check(self._lib.mcl_sync(self._h), "mcl_sync")
+
+    def set_option(self, option, value):
+        _check(self._lib.mcl_set_option(self._h, int(option), int(value)), "mcl_set_option")
 
     def launch_count(self):
         return int(self._lib.mcl_launch_count(self._h))

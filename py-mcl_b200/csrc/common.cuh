@@ -131,6 +131,31 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) {
     for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(v[i]));
 }
 
+// 32 consecutive 32-bit TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr)
+                 : "memory");
+}
+// Same, issued while the previous buffer `keep` is still live: `keep` is listed read-write so that the compiler
+// must hold both buffers in distinct registers and cannot move the consumers of `keep` above this load
+// (true double buffering: the load's latency overlaps the arithmetic on `keep`).
+__device__ __forceinline__ void tmem_ld32_keep(uint32_t taddr, uint32_t (&v)[32], uint32_t (&keep)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%64];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "+r"(keep[0]), "+r"(keep[1]), "+r"(keep[2]), "+r"(keep[3]), "+r"(keep[4]), "+r"(keep[5]), "+r"(keep[6]), "+r"(keep[7]), "+r"(keep[8]), "+r"(keep[9]), "+r"(keep[10]), "+r"(keep[11]), "+r"(keep[12]), "+r"(keep[13]), "+r"(keep[14]), "+r"(keep[15]), "+r"(keep[16]), "+r"(keep[17]), "+r"(keep[18]), "+r"(keep[19]), "+r"(keep[20]), "+r"(keep[21]), "+r"(keep[22]), "+r"(keep[23]), "+r"(keep[24]), "+r"(keep[25]), "+r"(keep[26]), "+r"(keep[27]), "+r"(keep[28]), "+r"(keep[29]), "+r"(keep[30]), "+r"(keep[31])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_all() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// compiler-only fence: uses of v[] may not be scheduled before this point (i.e. before the preceding wait)
+__device__ __forceinline__ void tmem_fence_regs(uint32_t (&v)[32]) {
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]) : : "memory");
+}
+__device__ __forceinline__ void tmem_wait32(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]) : : "memory");
+}
+
 __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
 // cv2 semantics of the ratio test on exact squared distances (Matcher.py:280 on BFMatcher output):

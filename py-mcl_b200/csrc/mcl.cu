@@ -79,9 +79,10 @@ struct mcl_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[PROF_N];
     // scratch
     DevBuf stage, cand, flags /* [0]=cand_count [1]=overflow [2]=bad */, row_arg, bow_best, lap_pix, lap_meta, filt, tmp_counts,
-        tmp_mask, tmp_words, tmp_scores;
+        tmp_mask, tmp_words, tmp_scores, tq_off, tq_desc, tq_norm, tq_frame;
     size_t cand_cap_entries = 0;
     bool tc_attr_set = false;
+    int opt[8] = {0};  // mcl_set_option: [0] = sift_tc diagnostic mode
 };
 
 struct mcl_queries {
@@ -285,7 +286,8 @@ extern "C" void mcl_shutdown(mcl_ctx* c) {
     for (auto& v : c->prof)
         for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     DevBuf* bufs[] = {&c->stage, &c->cand, &c->flags, &c->row_arg, &c->bow_best, &c->lap_pix, &c->lap_meta, &c->filt,
-                      &c->tmp_counts, &c->tmp_mask, &c->tmp_words, &c->tmp_scores};
+                      &c->tmp_counts, &c->tmp_mask, &c->tmp_words, &c->tmp_scores, &c->tq_off, &c->tq_desc, &c->tq_norm,
+                      &c->tq_frame};
     for (DevBuf* b : bufs) b->release();
     cudaStreamDestroy(c->stream);
     delete c;
@@ -319,6 +321,12 @@ extern "C" int mcl_host_alloc(size_t bytes, void** out) {
 }
 extern "C" void mcl_host_free(void* p) {
     if (p) cudaFreeHost(p);
+}
+
+extern "C" int mcl_set_option(mcl_ctx* c, int option, int value) {
+    if (!c || option < 0 || option >= 8) return fail(MCL_EINVAL, "mcl_set_option: bad argument");
+    c->opt[option] = value;
+    return MCL_OK;
 }
 
 extern "C" int64_t mcl_launch_count(mcl_ctx* c) { return c ? c->launches : 0; }
@@ -470,29 +478,33 @@ extern "C" int mcl_map_info(mcl_map* m, int64_t info[4]) {
 // ================================================================================================
 extern "C" void mcl_queries_destroy(mcl_queries* q) {
     if (!q) return;
-    cudaSetDevice(q->ctx->device);
-    cudaStreamSynchronize(q->ctx->stream);
-    cudaFree(q->d_off);
-    cudaFree(q->d_desc);
-    cudaFree(q->d_norm);
-    cudaFree(q->d_frame);
+    if (!q->borrowed) {
+        cudaSetDevice(q->ctx->device);
+        cudaStreamSynchronize(q->ctx->stream);
+        cudaFree(q->d_off);
+        cudaFree(q->d_desc);
+        cudaFree(q->d_norm);
+        cudaFree(q->d_frame);
+    }
     delete q;
 }
 
-extern "C" int mcl_queries_create(mcl_ctx* c, int kind, int n_queries, const int64_t* q_row_offsets, const void* q_desc,
-                                  int q_dtype, mcl_queries** out) {
-    if (!c || !out) return fail(MCL_EINVAL, "mcl_queries_create: NULL argument");
+namespace {
+// borrowed = true: device buffers come from the context's growable scratch (the per-call batch of mcl_match_counts /
+// mcl_bow_score: no cudaMalloc / cudaFree on the per-frame path); false: owned allocations (resident batch).
+int queries_build(mcl_ctx* c, int kind, int n_queries, const int64_t* q_row_offsets, const void* q_desc, int q_dtype,
+                  bool borrowed, mcl_queries** out) {
     *out = nullptr;
-    if (kind < MCL_SIFT || kind > MCL_BOWQ) return fail(MCL_EINVAL, "mcl_queries_create: bad kind %d", kind);
-    if (n_queries < 0) return fail(MCL_EINVAL, "mcl_queries_create: n_queries < 0");
+    if (kind < MCL_SIFT || kind > MCL_BOWQ) return fail(MCL_EINVAL, "queries: bad kind %d", kind);
+    if (n_queries < 0) return fail(MCL_EINVAL, "queries: n_queries < 0");
     if ((kind == MCL_ORB && q_dtype != MCL_U8) || (kind == MCL_SURF && q_dtype != MCL_F32) ||
         (q_dtype != MCL_U8 && q_dtype != MCL_F32))
-        return fail(MCL_EINVAL, "mcl_queries_create: dtype %d not valid for kind %d", q_dtype, kind);
-    int rc = check_offsets(q_row_offsets, n_queries, "mcl_queries_create");
+        return fail(MCL_EINVAL, "queries: dtype %d not valid for kind %d", q_dtype, kind);
+    int rc = check_offsets(q_row_offsets, n_queries, "queries");
     if (rc) return rc;
     const int64_t rows = q_row_offsets[n_queries];
-    if (rows > 0 && !q_desc) return fail(MCL_EINVAL, "mcl_queries_create: q_desc is NULL");
-    if (rows >= ((int64_t)1 << 31) - 4096) return fail(MCL_EINVAL, "mcl_queries_create: too many rows");
+    if (rows > 0 && !q_desc) return fail(MCL_EINVAL, "queries: q_desc is NULL");
+    if (rows >= ((int64_t)1 << 31) - 4096) return fail(MCL_EINVAL, "queries: too many rows");
     CU(cudaSetDevice(c->device));
     mcl_queries* q = new (std::nothrow) mcl_queries();
     if (!q) return fail(MCL_EINTERNAL, "out of host memory");
@@ -500,6 +512,7 @@ extern "C" int mcl_queries_create(mcl_ctx* c, int kind, int n_queries, const int
     q->kind = kind;
     q->n_queries = n_queries;
     q->rows = rows;
+    q->borrowed = borrowed;
     q->h_off.assign(q_row_offsets, q_row_offsets + n_queries + 1);
     cudaStream_t st = c->stream;
 #define QCU(expr)                                                                                                 \
@@ -510,20 +523,29 @@ extern "C" int mcl_queries_create(mcl_ctx* c, int kind, int n_queries, const int
             return fail(MCL_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);   \
         }                                                                                                         \
     } while (0)
-    QCU(cudaMalloc(&q->d_off, (size_t)(n_queries + 1) * 8));
+    auto get = [&](DevBuf& scratch, void** dst, size_t bytes) -> cudaError_t {
+        bytes = std::max<size_t>(bytes, 256);
+        if (borrowed) {
+            cudaError_t e = scratch.ensure(bytes);
+            *dst = scratch.p;
+            return e;
+        }
+        return cudaMalloc(dst, bytes);
+    };
+    QCU(get(c->tq_off, (void**)&q->d_off, (size_t)(n_queries + 1) * 8));
     QCU(cudaMemcpyAsync(q->d_off, q->h_off.data(), (size_t)(n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
     if (kind == MCL_SIFT) {
         using namespace mcl::sifttc;
         q->padded_rows = std::max<int64_t>(QBLK, (rows + QBLK - 1) / QBLK * QBLK);
-        QCU(cudaMalloc(&q->d_desc, (size_t)q->padded_rows * 128));
-        QCU(cudaMalloc(&q->d_norm, (size_t)q->padded_rows * 4));
-        QCU(cudaMalloc(&q->d_frame, (size_t)q->padded_rows * 4));
+        QCU(get(c->tq_desc, &q->d_desc, (size_t)q->padded_rows * 128));
+        QCU(get(c->tq_norm, (void**)&q->d_norm, (size_t)q->padded_rows * 4));
+        QCU(get(c->tq_frame, (void**)&q->d_frame, (size_t)q->padded_rows * 4));
         rc = ingest_rows128(c, st, q_desc, q_dtype, rows, n_queries, q->d_off, q->d_off, q->padded_rows,
                             (uint8_t*)q->d_desc, q->d_norm, q->d_frame);
         if (rc) { mcl_queries_destroy(q); return rc; }
     } else if (kind == MCL_BOWQ) {
         q->padded_rows = rows;
-        QCU(cudaMalloc(&q->d_desc, std::max<size_t>((size_t)rows * 512, 256)));
+        QCU(get(c->tq_desc, &q->d_desc, (size_t)rows * 512));
         if (rows) {
             if (q_dtype == MCL_F32) {
                 QCU(cudaMemcpyAsync(q->d_desc, q_desc, (size_t)rows * 512, cudaMemcpyHostToDevice, st));
@@ -538,13 +560,21 @@ extern "C" int mcl_queries_create(mcl_ctx* c, int kind, int n_queries, const int
     } else {
         const size_t rb = row_bytes(kind, q_dtype);
         q->padded_rows = rows;
-        QCU(cudaMalloc(&q->d_desc, std::max<size_t>((size_t)rows * rb, 256)));
+        QCU(get(c->tq_desc, &q->d_desc, (size_t)rows * rb));
         if (rows) QCU(cudaMemcpyAsync(q->d_desc, q_desc, (size_t)rows * rb, cudaMemcpyHostToDevice, st));
     }
+    // the host offsets/descriptors are caller-owned: the copies must have been consumed before we return
     QCU(cudaStreamSynchronize(st));
 #undef QCU
     *out = q;
     return MCL_OK;
+}
+}  // namespace
+
+extern "C" int mcl_queries_create(mcl_ctx* c, int kind, int n_queries, const int64_t* q_row_offsets, const void* q_desc,
+                                  int q_dtype, mcl_queries** out) {
+    if (!c || !out) return fail(MCL_EINVAL, "mcl_queries_create: NULL argument");
+    return queries_build(c, kind, n_queries, q_row_offsets, q_desc, q_dtype, false, out);
 }
 
 // ================================================================================================
@@ -557,7 +587,11 @@ int launch_sift_tc(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, 
     mcl_ctx* c = m->ctx;
     const size_t smem = sizeof(Smem) + 1024;
     if (!c->tc_attr_set) {
-        CU(cudaFuncSetAttribute(sift_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->tc_attr_set = true;
     }
     const int n_qblocks_total = (int)(q->padded_rows / QBLK);
@@ -598,7 +632,11 @@ int launch_sift_tc(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, 
         const int grid = (int)std::min<int64_t>(n_items, c->sm_count);
         {
             ProfScope ps(c, PROF_SIFT_TC, st);
-            sift_tc_kernel<<<grid, THREADS, smem, st>>>(p);
+            if (c->opt[0] == 1) sift_tc_kernel<1><<<grid, THREADS, smem, st>>>(p);
+            else if (c->opt[0] == 2) sift_tc_kernel<2><<<grid, THREADS, smem, st>>>(p);
+            else if (c->opt[0] == 3) sift_tc_kernel<3><<<grid, THREADS, smem, st>>>(p);
+            else if (c->opt[0] == 4) sift_tc_kernel<4><<<grid, THREADS, smem, st>>>(p);
+            else sift_tc_kernel<0><<<grid, THREADS, smem, st>>>(p);
         }
         CU(cudaGetLastError());
         {
@@ -717,7 +755,7 @@ extern "C" int mcl_match_counts(mcl_map* m, int n_queries, const int64_t* q_row_
     if (!(ratio > 0.0) || !(ratio <= 1.0)) return fail(MCL_EINVAL, "ratio must be in (0,1]");
     mcl_ctx* c = m->ctx;
     mcl_queries* q = nullptr;
-    int rc = mcl_queries_create(c, m->kind, n_queries, q_row_offsets, q_desc, q_dtype, &q);
+    int rc = queries_build(c, m->kind, n_queries, q_row_offsets, q_desc, q_dtype, true, &q);
     if (rc) return rc;
     const size_t n_out = (size_t)n_queries * m->n_images;
     cudaStream_t st = c->stream;
@@ -848,7 +886,7 @@ extern "C" int mcl_bow_score(mcl_bow* b, int n_queries, const int64_t* q_row_off
     if (!b || !out_scores) return fail(MCL_EINVAL, "mcl_bow_score: NULL argument");
     mcl_ctx* c = b->ctx;
     mcl_queries* q = nullptr;
-    int rc = mcl_queries_create(c, MCL_BOWQ, n_queries, q_row_offsets, q_desc, q_dtype, &q);
+    int rc = queries_build(c, MCL_BOWQ, n_queries, q_row_offsets, q_desc, q_dtype, true, &q);
     if (rc) return rc;
     cudaStream_t st = c->stream;
     auto body = [&]() -> int {

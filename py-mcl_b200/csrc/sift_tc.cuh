@@ -24,7 +24,7 @@ namespace mcl {
 namespace sifttc {
 
 constexpr int TILE_N = 128;        // map rows per tile (= MMA N)
-constexpr int GROUP = 16;          // columns per group; images are padded to a multiple of GROUP rows
+constexpr int GROUP = 32;          // columns per group; images are padded to a multiple of GROUP rows
 constexpr int GROUPS = TILE_N / GROUP;
 constexpr int QTILE = 128;         // query rows per MMA (= MMA M)
 constexpr int QBLK = 2 * QTILE;    // query rows per work item (two A tiles share every B tile)
@@ -34,7 +34,7 @@ constexpr int QBLK_BYTES = QBLK * ROW_BYTES;    // 32 KB
 constexpr int B_STAGES = 6;
 constexpr int META_STAGES = 4;
 constexpr int ACC_STAGES = 2;
-constexpr int META_INTS = 152;     // bias[128] img[8] nval[8] end_mask pad[7]
+constexpr int META_INTS = 140;     // bias[128] img[4] nval[4] end_mask pad[3]
 constexpr int META_BYTES = META_INTS * 4;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
@@ -47,7 +47,7 @@ struct TileMeta {
     int32_t img[GROUPS];    // image id of each group (-1: padding group)
     int32_t nval[GROUPS];   // number of real descriptors of that image
     int32_t end_mask;       // bit g: group g is the last group of its image
-    int32_t pad[7];
+    int32_t pad[3];
 };
 static_assert(sizeof(TileMeta) == META_BYTES, "meta size");
 
@@ -109,7 +109,7 @@ __global__ void build_meta_kernel(const int32_t* __restrict__ m_norm, const int3
             if (im >= 0 && nx != im) mask |= 1 << gg;
         }
         meta[t].end_mask = mask;
-        for (int k = 0; k < 7; ++k) meta[t].pad[k] = 0;
+        for (int k = 0; k < 3; ++k) meta[t].pad[k] = 0;
     }
 }
 
@@ -136,23 +136,53 @@ __device__ __noinline__ void finalize_image(const Params& p, int lane, bool row_
     }
 }
 
-// max over one 16-column group of key = 2*acc - |m|^2
-__device__ __forceinline__ int group_max(const uint32_t (&v)[16], const int32_t* __restrict__ bias) {
-    const int4* b4 = reinterpret_cast<const int4*>(bias);
-    const int4 c0 = b4[0], c1 = b4[1], c2 = b4[2], c3 = b4[3];
-    int gm = max3((int)v[0] * 2 + c0.x, (int)v[1] * 2 + c0.y, (int)v[2] * 2 + c0.z);
-    gm = max3(gm, (int)v[3] * 2 + c0.w, (int)v[4] * 2 + c1.x);
-    gm = max3(gm, (int)v[5] * 2 + c1.y, (int)v[6] * 2 + c1.z);
-    gm = max3(gm, (int)v[7] * 2 + c1.w, (int)v[8] * 2 + c2.x);
-    gm = max3(gm, (int)v[9] * 2 + c2.y, (int)v[10] * 2 + c2.z);
-    gm = max3(gm, (int)v[11] * 2 + c2.w, (int)v[12] * 2 + c3.x);
-    gm = max3(gm, (int)v[13] * 2 + c3.y, (int)v[14] * 2 + c3.z);
-    return max(gm, (int)v[15] * 2 + c3.w);
+// max over one 32-column group of key = 2*acc - |m|^2.
+// The add runs as IMAD on the FMA pipe for NFMA of every 8 columns (multiplier `two` is opaque to the compiler,
+// which would otherwise fold it into IADD3 on the ALU pipe, where the 3-input max already runs) and as IADD3 on the
+// ALU pipe for the rest: the two pipes issue side by side.
+constexpr int NFMA = 6;
+template <int MODE>
+__device__ __forceinline__ int group_max(const uint32_t (&v)[32], const int32_t* bias /* shared */, int two) {
+    if (MODE == 3 || MODE == 4) return (int)(v[0] | v[31]);  // diagnostic: no arithmetic (3: not even the TMEM read)
+    if (MODE == 1) {  // diagnostic: TMEM read + minimal arithmetic (results are meaningless)
+        uint32_t x = 0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) x = x | v[i] | v[i + 1];
+        return (int)x;
+    }
+    if (MODE == 2) {  // diagnostic: 3-input max only (no bias add)
+        int l[11];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) l[i] = max3((int)v[3 * i], (int)v[3 * i + 1], (int)v[3 * i + 2]);
+        l[10] = max((int)v[30], (int)v[31]);
+        const int a0 = max3(l[0], l[1], l[2]), a1 = max3(l[3], l[4], l[5]), a2 = max3(l[6], l[7], l[8]);
+        return max3(max3(a0, a1, a2), l[9], l[10]);
+    }
+    int k[32];
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        const int4 c = *reinterpret_cast<const int4*>(bias + i);
+        const int cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int a = (int)v[i + j];
+            k[i + j] = ((i + j) & 7) < NFMA ? a * two + cc[j] : a + a + cc[j];
+        }
+    }
+    // 3-input max tree (depth 4 instead of a 16-long chain)
+    int l1[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) l1[i] = max3(k[3 * i], k[3 * i + 1], k[3 * i + 2]);
+    l1[10] = max(k[30], k[31]);
+    const int a0 = max3(l1[0], l1[1], l1[2]), a1 = max3(l1[3], l1[4], l1[5]), a2 = max3(l1[6], l1[7], l1[8]);
+    return max3(max3(a0, a1, a2), l1[9], l1[10]);
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1) sift_tc_kernel(const __grid_constant__ Params p) {
-    extern __shared__ uint8_t smem_raw[];
-    Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B operands need 1024-byte alignment
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
@@ -237,6 +267,8 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc_kernel(const __grid_consta
         const int row_in_blk = atile * QTILE + lane_base + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)lane_base << 16) + atile * TILE_N;
         uint32_t mn = 0, an = 0;
+        int two = 2;
+        asm volatile("" : "+r"(two));  // opaque: keeps the key computation an IMAD (FMA pipe), see group_max
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int qb = item % p.n_qblocks;
             const Chunk ch = p.chunks[item / p.n_qblocks];
@@ -253,42 +285,39 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc_kernel(const __grid_consta
                 mbar_wait(&s.acc_full[as], aph);
                 tc_fence_after();
                 const uint32_t tcol = t_lane + as * (2 * TILE_N);
-                uint32_t va[16], vb[16];
-                tmem_ld16(tcol, va);
+                // One TMEM round trip per tile: the four 32-column loads are issued back to back and waited for once
+                // (an LDTM -> wait round trip costs ~230 cycles however much it moves), then the accumulator stage goes
+                // back to the MMA warp before any arithmetic starts.
+                uint32_t v[GROUPS][32];
+                if (MODE != 3) {
 #pragma unroll
-                for (int g = 0; g < GROUPS; g += 2) {
-                    tmem_ld_wait(va);
-                    tmem_ld16(tcol + (g + 1) * GROUP, vb);
-                    {
-                        const int gm = group_max(va, &mt.bias[g * GROUP]);
-                        pos = gm > M1 ? t * GROUPS + g : pos;
-                        M2 = max(M2, min(M1, gm));
-                        M1 = max(M1, gm);
-                        if (end_mask & (1 << g)) {
-                            finalize_image(p, lane, row_valid, Q, qrow, M1, M2, pos, mt.img[g], mt.nval[g], ch);
-                            M1 = NEG_KEY; M2 = NEG_KEY;
-                        }
-                    }
-                    tmem_ld_wait(vb);
-                    if (g + 2 < GROUPS) tmem_ld16(tcol + (g + 2) * GROUP, va);
-                    {
-                        const int gm = group_max(vb, &mt.bias[(g + 1) * GROUP]);
-                        pos = gm > M1 ? t * GROUPS + g + 1 : pos;
-                        M2 = max(M2, min(M1, gm));
-                        M1 = max(M1, gm);
-                        if (end_mask & (2 << g)) {
-                            finalize_image(p, lane, row_valid, Q, qrow, M1, M2, pos, mt.img[g + 1], mt.nval[g + 1], ch);
-                            M1 = NEG_KEY; M2 = NEG_KEY;
-                        }
-                    }
+                    for (int g = 0; g < GROUPS; ++g) tmem_ld32(tcol + g * GROUP, v[g]);
+                    tmem_wait_all();
+#pragma unroll
+                    for (int g = 0; g < GROUPS; ++g) tmem_fence_regs(v[g]);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < GROUPS; ++g)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[g][i] = 0;
                 }
-                // release the accumulator stage and the metadata slot
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&s.acc_empty[as]);
-                    mbar_arrive(&s.meta_empty[ms]);
+                if (lane == 0) mbar_arrive(&s.acc_empty[as]);
+#pragma unroll
+                for (int g = 0; g < GROUPS; ++g) {
+                    const int gm = group_max<MODE>(v[g], &mt.bias[g * GROUP], two);
+                    pos = gm > M1 ? t * GROUPS + g : pos;
+                    M2 = max(M2, min(M1, gm));
+                    M1 = max(M1, gm);
+                    if (end_mask & (1 << g)) {
+                        finalize_image(p, lane, row_valid, Q, qrow, M1, M2, pos, mt.img[g], mt.nval[g], ch);
+                        M1 = NEG_KEY; M2 = NEG_KEY;
+                    }
                 }
+                // release the metadata slot
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.meta_empty[ms]);
             }
         }
     }
@@ -298,8 +327,8 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
-// exact resolution of candidates: second best inside the winning 16-row group, ratio test, count.
-// One warp per candidate; lane l handles half (l&1) of map row (l>>1) of the group.
+// exact resolution of candidates: second best inside the winning 32-row group, ratio test, count.
+// One warp per candidate; lane l owns map row l of the group.
 // ------------------------------------------------------------------------------------------
 __global__ void sift_fixup_kernel(const int4* __restrict__ cand, const unsigned int* __restrict__ cand_count,
                                   unsigned int cand_cap, const uint8_t* __restrict__ q_desc,
@@ -312,21 +341,17 @@ __global__ void sift_fixup_kernel(const int4* __restrict__ cand, const unsigned 
     for (unsigned c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < n; c += n_warps) {
         const int4 cd = cand[c];
         const int64_t qrow = cd.x;
-        const int64_t mrow = (int64_t)cd.y + (lane >> 1);
-        const int half = lane & 1;
+        const int64_t mrow = (int64_t)cd.y + lane;
         unsigned dot = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int chunk = half * 4 + k;
+        for (int chunk = 0; chunk < 8; ++chunk) {
             const uint4 a = *reinterpret_cast<const uint4*>(q_desc + sw128_chunk_offset(qrow, chunk));
             const uint4 b = *reinterpret_cast<const uint4*>(m_desc + sw128_chunk_offset(mrow, chunk));
             dot = __dp4a(a.x, b.x, dot); dot = __dp4a(a.y, b.y, dot);
             dot = __dp4a(a.z, b.z, dot); dot = __dp4a(a.w, b.w, dot);
         }
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
         const int nm = m_norm[mrow];
-        int v = (nm >= 0) ? (int)(2u * dot) - nm : INT_MIN;
-        if (half) v = INT_MIN;  // keep one copy per map row
+        const int v = (nm >= 0) ? (int)(2u * dot) - nm : INT_MIN;
         int m1 = v;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m1 = max(m1, __shfl_xor_sync(0xffffffffu, m1, o));
