@@ -310,7 +310,7 @@ def main():
         peak = 2.0 * pk["bf16_sustained"]
         i8_rate, _ = ctx.microbench(0, 4000)
         roofline = {
-            "bound": "tensor", "kernel": "sift_tc_kernel (tcgen05.mma kind::i8 u8xu8->s32, fused top-2 epilogue)",
+            "bound": "tensor", "kernel": "sift_tc2_kernel (tcgen05.mma kind::i8 u8xu8->s32, A in TMEM, K extended 128->160 for the norm term, fused top-2 epilogue)",
             "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
             "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s); int8 dense = 2 x bf16 rate" % pk["src"],
             "frac_of_2x_bf16_burst": achieved / (2.0 * pk["bf16_burst"]),

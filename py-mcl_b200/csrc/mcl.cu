@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "prep.cuh"
 #include "sift_tc.cuh"
+#include "sift_tc2.cuh"
 #include "simt_match.cuh"
 #include "bow_lap_filter.cuh"
 #include "microbench.cuh"
@@ -42,6 +43,7 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 enum { PROF_SIFT_TC = 0, PROF_SIFT_FIX, PROF_ORB, PROF_SURF, PROF_VQ, PROF_SCORE, PROF_LAP, PROF_PREP, PROF_SIFT_SIMT, PROF_N };
+constexpr int QROW_PAD = 768;  // lcm of the two tensor-core kernels' query blocks (256, 384)
 
 // growable device scratch buffer (never shrinks; avoids cudaMalloc on the per-frame path)
 struct DevBuf {
@@ -78,10 +80,10 @@ struct mcl_ctx {
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[PROF_N];
     // scratch
-    DevBuf stage, cand, flags /* [0]=cand_count [1]=overflow [2]=bad */, row_arg, bow_best, lap_pix, lap_meta, filt, tmp_counts,
+    DevBuf stage, cand, flags /* [0]=cand_count [1]=overflow [2]=bad [3]=rescans [4]=norm min [5]=norm max */, row_arg, bow_best, lap_pix, lap_meta, filt, tmp_counts,
         tmp_mask, tmp_words, tmp_scores, tq_off, tq_desc, tq_norm, tq_frame;
     size_t cand_cap_entries = 0;
-    bool tc_attr_set = false;
+    bool tc_attr_set = false, tc2_attr_set = false;
     int opt[8] = {0};  // mcl_set_option: [0] = sift_tc diagnostic mode
 };
 
@@ -114,7 +116,12 @@ struct mcl_map {
     int n_tiles = 0;
     // chunk tables for a few granularities (tiles per chunk), picked per call from the query batch size
     struct ChunkSet { int target = 0; int n = 0; mcl::sifttc::Chunk* d = nullptr; };
-    std::vector<ChunkSet> chunk_sets;
+    std::vector<ChunkSet> chunk_sets;    // sift_tc  (128-row tiles)
+    std::vector<ChunkSet> chunk_sets2;   // sift_tc2 (64-row tiles)
+    uint8_t* d_ext2 = nullptr;           // sift_tc2: per 64-row tile, extension bytes + metadata
+    int n_tiles2 = 0;
+    int key_c = 0;                       // sift_tc2: true key = 2*acc - key_c (+ parity)
+    bool ext_ok = false;                 // the norms' range fits the extension encoding
     int max_rows_per_image = 0;
 };
 
@@ -208,8 +215,7 @@ int ingest_rows128(mcl_ctx* c, cudaStream_t st, const void* h_src, int dtype, in
     return MCL_OK;
 }
 
-void build_chunks(const mcl_map* m, int target_tiles, std::vector<mcl::sifttc::Chunk>& out) {
-    using mcl::sifttc::TILE_N;
+void build_chunks(const mcl_map* m, int TILE_N, int target_tiles, std::vector<mcl::sifttc::Chunk>& out) {
     out.clear();
     int i = 0;
     const int n = m->n_images;
@@ -233,10 +239,10 @@ void build_chunks(const mcl_map* m, int target_tiles, std::vector<mcl::sifttc::C
     }
 }
 
-const mcl_map::ChunkSet* pick_chunks(const mcl_map* m, int n_qblocks, int sm_count) {
+const mcl_map::ChunkSet* pick_chunks(const std::vector<mcl_map::ChunkSet>& sets, int n_qblocks, int sm_count) {
     // want >= ~3 waves of work items (qblocks x chunks), chunks as long as possible beyond that
-    const mcl_map::ChunkSet* best = &m->chunk_sets.back();
-    for (const auto& cs : m->chunk_sets) {  // sorted by decreasing target
+    const mcl_map::ChunkSet* best = &sets.back();
+    for (const auto& cs : sets) {  // sorted by decreasing target
         best = &cs;
         if ((int64_t)cs.n * n_qblocks >= (int64_t)3 * sm_count) break;
     }
@@ -370,6 +376,8 @@ extern "C" void mcl_map_destroy(mcl_map* m) {
     cudaFree(m->d_img_of);
     cudaFree(m->d_meta);
     for (auto& cs : m->chunk_sets) cudaFree(cs.d);
+    for (auto& cs : m->chunk_sets2) cudaFree(cs.d);
+    cudaFree(m->d_ext2);
     delete m;
 }
 
@@ -435,22 +443,52 @@ extern "C" int mcl_map_create(mcl_ctx* c, int kind, int n_images, const int64_t*
         }
         MCU(cudaGetLastError());
         std::vector<Chunk> ch;
-        int last_n = -1;
-        for (int target : {64, 32, 16, 8, 4, 2, 1}) {
-            build_chunks(m, target, ch);
-            if ((int)ch.size() == last_n) continue;
-            last_n = (int)ch.size();
-            mcl_map::ChunkSet cs;
-            cs.target = target;
-            cs.n = (int)ch.size();
-            if (cs.n) {
-                MCU(cudaMalloc(&cs.d, ch.size() * sizeof(Chunk)));
-                MCU(cudaMemcpyAsync(cs.d, ch.data(), ch.size() * sizeof(Chunk), cudaMemcpyHostToDevice, st));
-                MCU(cudaStreamSynchronize(st));  // ch is reused by the next iteration
+        auto make_sets = [&](std::vector<mcl_map::ChunkSet>& sets, int tile_rows, std::initializer_list<int> targets) -> cudaError_t {
+            int last_n = -1;
+            for (int target : targets) {
+                build_chunks(m, tile_rows, target, ch);
+                if ((int)ch.size() == last_n) continue;
+                last_n = (int)ch.size();
+                mcl_map::ChunkSet cs;
+                cs.target = target;
+                cs.n = (int)ch.size();
+                if (cs.n) {
+                    cudaError_t e = cudaMalloc(&cs.d, ch.size() * sizeof(Chunk));
+                    if (e != cudaSuccess) return e;
+                    e = cudaMemcpy(cs.d, ch.data(), ch.size() * sizeof(Chunk), cudaMemcpyHostToDevice);
+                    if (e != cudaSuccess) return e;
+                }
+                sets.push_back(cs);
             }
-            m->chunk_sets.push_back(cs);
+            return cudaSuccess;
+        };
+        MCU(make_sets(m->chunk_sets, TILE_N, {64, 32, 16, 8, 4, 2, 1}));
+        MCU(make_sets(m->chunk_sets2, mcl::sifttc2::TILE_N, {256, 128, 64, 32, 16, 8, 4, 2, 1}));
+        // ---- second-generation kernel: norm range -> C, extension bytes + metadata per 64-row tile
+        {
+            int* mm = c->flags.as<int>() + 4;
+            const int init[2] = {INT_MAX, -1};
+            MCU(cudaMemcpyAsync(mm, init, 8, cudaMemcpyHostToDevice, st));
+            c->launches++;
+            mcl::sifttc2::norm_minmax_kernel<<<c->sm_count * 4, 256, 0, st>>>(m->d_norm, m->padded_rows, mm);
+            int h_mm[2];
+            MCU(cudaMemcpyAsync(h_mm, mm, 8, cudaMemcpyDeviceToHost, st));
+            MCU(cudaStreamSynchronize(st));
+            m->n_tiles2 = (int)(m->padded_rows / mcl::sifttc2::TILE_N);
+            if (h_mm[1] >= 0) {
+                m->key_c = h_mm[1] + 3;
+                m->ext_ok = (m->key_c - h_mm[0]) / 2 <= mcl::sifttc2::EXT_CAP;
+            }
+            if (m->ext_ok) {
+                MCU(cudaMalloc(&m->d_ext2, (size_t)m->n_tiles2 * mcl::sifttc2::EXT_META_BYTES));
+                ProfScope ps(c, PROF_PREP, st);
+                mcl::sifttc2::build_ext_kernel<<<m->n_tiles2, mcl::sifttc2::TILE_N, 0, st>>>(
+                    m->d_norm, m->d_img_of, m->d_src_off, m->n_tiles2, m->key_c, m->d_ext2);
+            }
+            MCU(cudaGetLastError());
         }
-        m->resident_bytes = (size_t)m->padded_rows * (128 + 8) + (size_t)m->n_tiles * sizeof(TileMeta);
+        m->resident_bytes = (size_t)m->padded_rows * (128 + 8) + (size_t)m->n_tiles * sizeof(TileMeta) +
+                            (m->d_ext2 ? (size_t)m->n_tiles2 * mcl::sifttc2::EXT_META_BYTES : 0);
     } else {
         const size_t rb = row_bytes(kind, desc_dtype);
         m->padded_rows = rows;
@@ -536,7 +574,7 @@ int queries_build(mcl_ctx* c, int kind, int n_queries, const int64_t* q_row_offs
     QCU(cudaMemcpyAsync(q->d_off, q->h_off.data(), (size_t)(n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
     if (kind == MCL_SIFT) {
         using namespace mcl::sifttc;
-        q->padded_rows = std::max<int64_t>(QBLK, (rows + QBLK - 1) / QBLK * QBLK);
+        q->padded_rows = std::max<int64_t>(QROW_PAD, (rows + QROW_PAD - 1) / QROW_PAD * QROW_PAD);
         QCU(get(c->tq_desc, &q->d_desc, (size_t)q->padded_rows * 128));
         QCU(get(c->tq_norm, (void**)&q->d_norm, (size_t)q->padded_rows * 4));
         QCU(get(c->tq_frame, (void**)&q->d_frame, (size_t)q->padded_rows * 4));
@@ -611,7 +649,7 @@ int launch_sift_tc(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, 
     CU(cudaMemsetAsync(d_overflow, 0, 4, st));
     for (int qb0 = 0; qb0 < n_qblocks_total; qb0 += batch_qblocks) {
         const int nqb = std::min(batch_qblocks, n_qblocks_total - qb0);
-        const mcl_map::ChunkSet* cs = pick_chunks(m, nqb, c->sm_count);
+        const mcl_map::ChunkSet* cs = pick_chunks(m->chunk_sets, nqb, c->sm_count);
         if (cs->n == 0) break;
         CU(cudaMemsetAsync(d_cand_count, 0, 4, st));
         Params p;
@@ -660,6 +698,79 @@ int launch_sift_tc(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, 
     return MCL_OK;
 }
 
+int launch_sift_tc2(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, cudaStream_t st) {
+    using namespace mcl::sifttc2;
+    mcl_ctx* c = m->ctx;
+    const size_t smem = sizeof(Smem);
+    if (!c->tc2_attr_set) {
+        CU(cudaFuncSetAttribute(sift_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->tc2_attr_set = true;
+    }
+    const int n_qblocks_total = (int)(q->padded_rows / QBLK);
+    const int64_t pairs_total = q->padded_rows * (int64_t)std::max(1, m->n_images);
+    const int64_t want = std::min<int64_t>(std::max<int64_t>(pairs_total / 4, 1 << 16), (int64_t)48 << 20);
+    if ((size_t)want > c->cand_cap_entries) {
+        CU(c->cand.ensure((size_t)want * sizeof(int4)));
+        c->cand_cap_entries = (size_t)want;
+    }
+    const int64_t cap = (int64_t)c->cand_cap_entries;
+    int batch_qblocks = (int)std::max<int64_t>(1, cap * 4 / ((int64_t)std::max(1, m->n_images) * QBLK));
+    batch_qblocks = std::min(batch_qblocks, n_qblocks_total);
+    unsigned int* d_cand_count = c->flags.as<unsigned int>();
+    int* d_overflow = c->flags.as<int>() + 1;
+    unsigned int* d_rescans = c->flags.as<unsigned int>() + 3;
+    CU(cudaMemsetAsync(d_overflow, 0, 4, st));
+    for (int qb0 = 0; qb0 < n_qblocks_total; qb0 += batch_qblocks) {
+        const int nqb = std::min(batch_qblocks, n_qblocks_total - qb0);
+        const mcl_map::ChunkSet* cs = pick_chunks(m->chunk_sets2, nqb, c->sm_count);
+        if (cs->n == 0) break;
+        CU(cudaMemsetAsync(d_cand_count, 0, 4, st));
+        Params p;
+        p.q_desc = (const uint8_t*)q->d_desc + (size_t)qb0 * QBLK * 128;
+        p.q_norm = q->d_norm + (size_t)qb0 * QBLK;
+        p.m_desc = (const uint8_t*)m->d_desc;
+        p.m_ext = m->d_ext2;
+        p.chunks = cs->d;
+        p.n_qblocks = nqb;
+        p.n_chunks = cs->n;
+        p.key_c = m->key_c;
+        p.ratio = ratio;
+        p.cand = c->cand.as<int4>();
+        p.cand_count = d_cand_count;
+        p.cand_cap = (unsigned)cap;
+        p.overflow = d_overflow;
+        p.q_row_base = qb0 * QBLK;
+        const int64_t n_items = (int64_t)nqb * cs->n;
+        const int grid = (int)std::min<int64_t>(n_items, c->sm_count);
+        {
+            ProfScope ps(c, PROF_SIFT_TC, st);
+            if (c->opt[0] == 3) sift_tc2_kernel<3><<<grid, THREADS, smem, st>>>(p);
+            else if (c->opt[0] == 4) sift_tc2_kernel<4><<<grid, THREADS, smem, st>>>(p);
+            else sift_tc2_kernel<0><<<grid, THREADS, smem, st>>>(p);
+        }
+        CU(cudaGetLastError());
+        {
+            ProfScope ps(c, PROF_SIFT_FIX, st);
+            sift_fixup2_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->cand.as<int4>(), d_cand_count, (unsigned)cap,
+                                                               (const uint8_t*)q->d_desc, q->d_norm, q->d_frame,
+                                                               (const uint8_t*)m->d_desc, m->d_norm, m->d_dst_off, m->key_c,
+                                                               ratio, m->n_images, d_counts, d_rescans);
+        }
+        CU(cudaGetLastError());
+    }
+    {
+        ProfScope ps(c, PROF_SIFT_SIMT, st);
+        dim3 grid(std::max(1, m->n_images), std::max(1, q->n_queries));
+        mcl::sift_simt_kernel<<<grid, 128, 0, st>>>((const uint8_t*)q->d_desc, q->d_norm, q->d_off, (const uint8_t*)m->d_desc,
+                                                    m->d_norm, m->d_dst_off, m->d_src_off, m->n_images, ratio, nullptr,
+                                                    d_overflow, d_counts);
+    }
+    CU(cudaGetLastError());
+    return MCL_OK;
+}
+
 int match_device(mcl_map* m, mcl_queries* q, int mode, double ratio, const uint8_t* d_mask, int32_t fill, int algo,
                  int32_t* d_counts, cudaStream_t st) {
     mcl_ctx* c = m->ctx;
@@ -678,7 +789,11 @@ int match_device(mcl_map* m, mcl_queries* q, int mode, double ratio, const uint8
                 const double macs = (double)q->rows * (double)m->rows;
                 use = (d_mask || macs < 4.0e6) ? MCL_ALGO_SIMT : MCL_ALGO_TENSOR;
             }
+            if (use == MCL_ALGO_TENSOR && !m->ext_ok) use = MCL_ALGO_TENSOR_V1;  // norm range too wide for the K extension
             if (use == MCL_ALGO_TENSOR) {
+                int rc = launch_sift_tc2(m, q, ratio, d_counts, st);
+                if (rc) return rc;
+            } else if (use == MCL_ALGO_TENSOR_V1) {
                 int rc = launch_sift_tc(m, q, ratio, d_counts, st);
                 if (rc) return rc;
             } else {
@@ -1032,6 +1147,23 @@ extern "C" int mcl_microbench(mcl_ctx* c, int which, int iters, double* out /* [
         mcl::popc_peak_kernel<<<c->sm_count * 8, 256, 0, st>>>(iters, c->stage.as<int>());
         CU(cudaEventRecord(b, st));
         ops = 16.0 * (double)iters * 256.0 * c->sm_count * 8;  // popc32 results
+    } else if (which >= 100) {  // development probe: which = 100 + n/64 (1,2,4) + 10*ts + 100*ext
+        const int w = which - 100;
+        const int n = (w % 10) * 64, ts = (w / 10) % 10, ext = (w / 100) % 10;
+        const size_t smem = 16384 + 32768 + 8192 + 1024 + 64;
+        void (*k)(int, int*) = nullptr;
+#define PICK(N_, TS_, EXT_) if (n == N_ && ts == TS_ && ext == EXT_) k = mcl::mma_probe_kernel<N_, TS_, EXT_>;
+        PICK(64, 0, 0) PICK(64, 1, 0) PICK(64, 0, 1) PICK(64, 1, 1)
+        PICK(128, 0, 0) PICK(128, 1, 0) PICK(128, 0, 1) PICK(128, 1, 1)
+        PICK(256, 0, 0) PICK(256, 1, 0) PICK(256, 0, 1) PICK(256, 1, 1)
+#undef PICK
+        if (!k) return fail(MCL_EINVAL, "mcl_microbench: unknown probe variant");
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<c->sm_count, 128, smem, st>>>(iters / 8 + 1, c->stage.as<int>());
+        CU(cudaEventRecord(a, st));
+        k<<<c->sm_count, 128, smem, st>>>(iters, c->stage.as<int>());
+        CU(cudaEventRecord(b, st));
+        ops = 2.0 * 128 * n * 32 * 15.0 * (double)iters * c->sm_count;
     } else {
         return fail(MCL_EINVAL, "mcl_microbench: which must be 0 (int8 tensor) or 1 (popc)");
     }

@@ -50,6 +50,61 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, int* __restr
     if (threadIdx.x < 32) tmem_dealloc<256>(tmem);
 }
 
+// tcgen05 shape probe: N (64/128/256), A from shared memory (TS=0) or tensor memory (TS=1); with EXT every 5th MMA
+// reads a no-swizzle 32-byte-row B operand (the K-extension step of sift_tc2).  15 MMAs per iteration, fully unrolled,
+// issued by the elected lane of a converged warp (uniform operands).  The host times it.
+template <int N, int TS, int EXT>
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int iters, int* __restrict__ sink) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* a = base;                  // 128 x 128 B
+    uint8_t* b = base + 16384;          // 256 x 128 B
+    uint8_t* e = base + 16384 + 32768;  // 256 x 32 B no-swizzle
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + 16384 + 32768 + 8192);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+    for (int i = threadIdx.x; i < (16384 + 32768 + 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0x01010101u * (i & 3);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int warp = warp_id_uniform();
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (warp == 0) {
+        const uint32_t leader = (threadIdx.x & 31) == 0;
+        constexpr uint32_t idesc = umma_idesc(2, 0, 0, 128, N);
+        const uint64_t da = umma_desc_sw128(smem_u32(a));
+        const uint64_t db = umma_desc_sw128(smem_u32(b));
+        const uint64_t de = umma_desc_noswizzle(smem_u32(e), 128, 256);
+        constexpr int NACC = N >= 256 ? 1 : (N == 128 ? 2 : 3);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 15; ++r) {
+                const int k = r % 5;
+                const uint32_t d = tmem + 128 + ((r / 5) % NACC) * N;
+                const uint64_t bd = (EXT && k == 4) ? de : db + 2 * (k & 3);
+                if (TS) umma_i8_ts_if(leader, d, tmem + 8 * k, bd, idesc, 1);
+                else umma_i8_if(leader, d, da + 2 * (k & 3), bd, idesc, 1);
+            }
+        }
+        tc_commit_if(leader, bar);
+        mbar_wait(bar, 0);
+    }
+    __syncthreads();
+    tc_fence_after();
+    uint32_t v[16];
+    tmem_ld16(tmem + 128 + ((uint32_t)((threadIdx.x >> 5) * 32) << 16), v);
+    tmem_ld_wait(v);
+    if (v[0] == 0xdeadbeefu) sink[blockIdx.x] = (int)v[1];
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 // XOR + popc.b32: 16 independent results per iteration per thread
 __global__ void __launch_bounds__(256) popc_peak_kernel(int iters, int* __restrict__ sink) {
     unsigned x[16];

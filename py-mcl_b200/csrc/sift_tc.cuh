@@ -183,8 +183,9 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc_kernel(const __grid_consta
     extern __shared__ __align__(1024) uint8_t smem_raw[];   // SWIZZLE_128B operands need 1024-byte alignment
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_id_uniform();
     const int lane = threadIdx.x & 31;
+    const uint32_t leader = lane == 0;
 
     if (threadIdx.x == 0) {
         mbar_init(&s.a_full, 1);
@@ -209,23 +210,17 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc_kernel(const __grid_consta
             const int qb = item % p.n_qblocks;
             const Chunk ch = p.chunks[item / p.n_qblocks];
             mbar_wait(&s.a_empty, (item_n & 1) ^ 1);
-            if (lane == 0) {
-                mbar_arrive_expect_tx(&s.a_full, QBLK_BYTES);
-                bulk_g2s(s.a, p.q_desc + (size_t)qb * QBLK_BYTES, QBLK_BYTES, &s.a_full);
-            }
+            mbar_arrive_expect_tx_if(leader, &s.a_full, QBLK_BYTES);
+            bulk_g2s_if(leader, s.a, p.q_desc + (size_t)qb * QBLK_BYTES, QBLK_BYTES, &s.a_full);
             for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn, ++mn) {
                 const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
                 const uint32_t ms = mn % META_STAGES, mph = (mn / META_STAGES) & 1;
                 mbar_wait(&s.meta_empty[ms], mph ^ 1);
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&s.meta_full[ms], META_BYTES);
-                    bulk_g2s(&s.meta[ms], p.m_meta + t, META_BYTES, &s.meta_full[ms]);
-                }
+                mbar_arrive_expect_tx_if(leader, &s.meta_full[ms], META_BYTES);
+                bulk_g2s_if(leader, &s.meta[ms], p.m_meta + t, META_BYTES, &s.meta_full[ms]);
                 mbar_wait(&s.b_empty[bs], bph ^ 1);
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&s.b_full[bs], TILE_BYTES);
-                    bulk_g2s(s.b[bs], p.m_desc + (size_t)t * TILE_BYTES, TILE_BYTES, &s.b_full[bs]);
-                }
+                mbar_arrive_expect_tx_if(leader, &s.b_full[bs], TILE_BYTES);
+                bulk_g2s_if(leader, s.b[bs], p.m_desc + (size_t)t * TILE_BYTES, TILE_BYTES, &s.b_full[bs]);
             }
         }
     } else if (warp == EPI_WARPS + 1) {
@@ -243,21 +238,21 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc_kernel(const __grid_consta
                 mbar_wait(&s.b_full[bs], bph);
                 mbar_wait(&s.acc_empty[as], aph ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
+                {
                     const uint64_t b_desc = umma_desc_sw128(smem_u32(s.b[bs]));
                     const uint32_t d0 = tmem_base + as * (2 * TILE_N);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)  // K = 4 x 32 bytes; +2 in the (addr>>4) field per step
-                        umma_i8(d0, a_desc0 + 2 * k, b_desc + 2 * k, idesc, k > 0);
+                        umma_i8_if(leader, d0, a_desc0 + 2 * k, b_desc + 2 * k, idesc, k > 0);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_i8(d0 + TILE_N, a_desc1 + 2 * k, b_desc + 2 * k, idesc, k > 0);
-                    tc_commit(&s.b_empty[bs]);
-                    tc_commit(&s.acc_full[as]);
+                        umma_i8_if(leader, d0 + TILE_N, a_desc1 + 2 * k, b_desc + 2 * k, idesc, k > 0);
+                    tc_commit_if(leader, &s.b_empty[bs]);
+                    tc_commit_if(leader, &s.acc_full[as]);
                 }
                 __syncwarp();
             }
-            if (lane == 0) tc_commit(&s.a_empty);
+            tc_commit_if(leader, &s.a_empty);
             __syncwarp();
         }
     } else {

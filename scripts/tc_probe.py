@@ -9,18 +9,19 @@ import bench
 ctx = _lib.Context(0)
 n_images, n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 200, int(sys.argv[2]) if len(sys.argv) > 2 else 100
 modes = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2]
+algo = int(sys.argv[4]) if len(sys.argv) > 4 else _lib.ALGO_TENSOR
 map_des, frames = bench.make_workload(0, n_images, n_frames)
 resident = _lib.MapIndex(ctx, "SIFT", map_des)
 q = _lib.QueryBatch(ctx, "SIFT", frames)
 import torch
 out = torch.zeros((n_frames, n_images), dtype=torch.int32, device="cuda")
 ops = 2.0 * 2048 * 2048 * 128 * n_images * n_frames
-tiles_per_sm = (n_frames * 2048 / 256) * (n_images * 2048 / 128) / 148
+tiles_per_sm = (n_frames * 2048 / 256) * (n_images * 2048 / 128) / 148  # in 256x128 units: 512 cycles at the int8 peak
 for mode in modes:
     ctx.set_option(0, mode)
     ctx.profile_enable(True)
     for _ in range(3):
-        resident.match_counts_device(q, out.data_ptr(), algo=_lib.ALGO_TENSOR)
+        resident.match_counts_device(q, out.data_ptr(), algo=algo)
     ctx.sync()
     ms, n = ctx.profile_read("sift_tc")
     ctx.profile_enable(False)
