@@ -82,7 +82,7 @@ void mcl_queries_destroy(mcl_queries* q);
 
 /* ---- matching ------------------------------------------------------------------------------------------
  * out_counts[q*n_images + i] = len(good) of SIFTMatch/SURFMatch/ORBMatch(query q, image i)
- * (Matcher.py:169-194, 196-230, 262-291), i.e. what Matcher.run's loop (Matcher.py:309-318) collects.
+ * (Matcher.py:169-194, Matcher.py:196-230, Matcher.py:262-291), i.e. what Matcher.run's loop (Matcher.py:309-318) collects.
  * mask (optional, n_queries*n_images bytes): 0 = image not matched for that query -> fill_value
  * (optRun's "numMatches = 1", Matcher.py:359,369).  Images with fewer than 2 descriptors count 0.
  * mcl_match_counts: host in / host out, includes H2D, ingest, kernels, D2H.

@@ -5,22 +5,20 @@ done by hand-written CUDA kernels in ``csrc/`` behind the C-ABI declared in ``in
 (``libmcl.so``), called through ctypes (``_lib``).  There is no CPU fallback: using the kernels on a box
 without the built library or without an sm_100 GPU raises ``MclError``.
 
-    from pymcl_b200 import Matcher, analyzer          # drop-in for `from Matcher import Matcher`
+    from pymcl_b200.Matcher import Matcher            # drop-in for `from Matcher import Matcher`
+    from pymcl_b200.analyze import analyzer           # drop-in for `from analyze import analyzer`
 """
 from . import _lib  # noqa: F401  (does not touch the GPU or load the library at import time)
 from ._lib import MclError  # noqa: F401
 
-__all__ = ["Matcher", "analyzer", "MclError", "synth", "engine", "build"]
+__all__ = ["Matcher", "analyze", "MclError", "synth", "engine", "build"]
 
 
 def __getattr__(name):
-    # cv2 is imported only when the reference-facing classes are asked for
-    if name in ("Matcher", "analyzer"):
-        import importlib
-        cls = getattr(importlib.import_module("." + ("Matcher" if name == "Matcher" else "analyze"), __name__), name)
-        globals()[name] = cls  # the class shadows the same-named submodule, like `from Matcher import Matcher`
-        return cls
-    if name in ("synth", "engine", "build", "analyze"):
+    # submodules are imported on first use (cv2 is only needed by the reference-facing classes):
+    #   from pymcl_b200.Matcher import Matcher      # drop-in for `from Matcher import Matcher`
+    #   from pymcl_b200.analyze import analyzer     # drop-in for `from analyze import analyzer`
+    if name in ("Matcher", "analyze", "synth", "engine", "build"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

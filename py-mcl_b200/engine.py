@@ -84,9 +84,9 @@ class ShardedMap(object):
         cuda = d.get_backend(self.group) == "nccl"
         if cuda:
             t = t.cuda()
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        out = torch.empty((self.world * F, maxw), dtype=t.dtype, device=t.device)   # concatenation along dim 0
         d.all_gather_into_tensor(out, t, group=self.group)
-        out = out.cpu().numpy()
+        out = out.cpu().numpy().reshape(self.world, F, maxw)
         full = np.empty((F, self.n_images), dtype=local.dtype)
         for r, (l, h) in enumerate(self.bounds):
             full[:, l:h] = out[r][:, :h - l]

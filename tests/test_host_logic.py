@@ -1,0 +1,138 @@
+"""Host-side logic that needs no GPU: packing, sharding, the DOR window, the reference-facing signatures, and the
+world_size-2 (gloo) path of ShardedMap with an oracle-backed local matcher standing in for the GPU."""
+import inspect
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+import pymcl_b200  # noqa: F401
+from pymcl_b200 import _lib, engine, synth
+from pymcl_b200.Matcher import Matcher, angle_window
+from conftest import REPO
+
+
+def test_angle_window_equals_reference_logic():
+    for k in range(25):
+        assert angle_window(k) == oracle.opt_window(k)
+
+
+def test_matcher_signature_and_positional_quirk():
+    """Matcher(algorithm, index=None, width=800, height=600): positional ('SIFT', 320, 240) sets index=320, w=240."""
+    sig = inspect.signature(Matcher.__init__)
+    assert list(sig.parameters) == ["self", "algorithm", "index", "width", "height"]
+    m = Matcher("SIFT", 320, 240)
+    assert (m.index, m.w, m.h, m.numWords) == (320, 240, 600, 10000)
+    m = Matcher("ORB", width=320, height=240)
+    assert (m.index, m.w, m.h) == (None, 320, 240)
+    for name in ("setQuery", "setDirectory", "setIndex", "createFeatureIndex", "run", "optRun", "SIFTMatch", "SURFMatch",
+                 "ORBMatch", "BOWMatch", "createIndex", "writeIndices"):
+        assert callable(getattr(Matcher, name))
+
+
+def test_analyzer_signature():
+    from pymcl_b200.analyze import analyzer
+    sig = inspect.signature(analyzer.__init__)
+    assert list(sig.parameters)[:4] == ["self", "method", "width", "height"]
+    for name in ("createIndex", "createRawP", "processRaw", "optP", "probUpdate", "prevWeight", "accountCommand",
+                 "writeProb", "readProb", "readCommand", "readBestGuess", "Laplacian"):
+        assert callable(getattr(analyzer, name))
+
+
+def test_pack_descriptors():
+    rng = np.random.default_rng(0)
+    a, b = synth.sift_like(rng, 5), synth.sift_like(rng, 3)
+    off, cat, code = _lib.pack_descriptors(_lib.SIFT, [a, None, b, np.zeros((0, 128), np.float32)])
+    assert off.tolist() == [0, 5, 5, 8, 8] and cat.shape == (8, 128) and code == _lib.F32 and cat.dtype == np.float32
+    off, cat, code = _lib.pack_descriptors(_lib.SIFT, [a.astype(np.uint8)])
+    assert code == _lib.U8 and cat.dtype == np.uint8
+    off, cat, code = _lib.pack_descriptors(_lib.ORB, [None, None])
+    assert off.tolist() == [0, 0, 0] and cat.shape == (0, 32)
+    with pytest.raises(_lib.MclError):
+        _lib.pack_descriptors(_lib.ORB, [np.zeros((4, 31), np.uint8)])
+
+
+def test_shard_bounds_cover_and_balance():
+    rng = np.random.default_rng(1)
+    for world in (1, 2, 3, 4, 8):
+        for n in (0, 1, 5, 64, 175, 3200):
+            rows = rng.integers(0, 3000, size=n).tolist()
+            b = engine.shard_bounds(rows, world)
+            assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            if n >= 64 * world:
+                w = [sum(rows[l:h]) + (h - l) for l, h in b]
+                assert max(w) <= 1.25 * (sum(w) / world) + 3001
+    assert engine.shard_bounds([2048] * 3200, 8) == [(i * 400, (i + 1) * 400) for i in range(8)]
+
+
+class OracleLocal(object):
+    """Stands in for _lib.MapIndex in CPU tests: same match_counts contract, computed by the oracle."""
+
+    def __init__(self, descs):
+        self.descs = descs
+        self.n_images = len(descs)
+
+    def match_counts(self, q_descs, mode=0, ratio=0.7, mask=None, fill_value=1, algo=0):
+        out = np.zeros((len(q_descs), len(self.descs)), dtype=np.int32)
+        for f, q in enumerate(q_descs):
+            for i, m in enumerate(self.descs):
+                if mask is not None and not mask[f, i]:
+                    out[f, i] = fill_value
+                else:
+                    out[f, i] = oracle.sift_pair_count(q, m, ratio)
+        return out
+
+
+def test_sharded_map_single_process_matches_unsharded():
+    map_des, frames = synth.sift_map_and_frames(2, 9, 60, 3, 50)
+    sm = engine.ShardedMap("SIFT", map_des, local_factory=OracleLocal)
+    want = OracleLocal(map_des).match_counts(frames)
+    assert np.array_equal(sm.match_counts(frames), want)
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, {repo!r}); sys.path.insert(0, os.path.join({repo!r}, "oracle")); sys.path.insert(0, os.path.join({repo!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import pymcl_b200
+from pymcl_b200 import engine, synth
+from test_host_logic import OracleLocal
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+sizes = [40, 0, 75, 33, 64, 1, 90, 55, 20, 61, 48]
+rng = np.random.default_rng(3)
+map_des = [synth.sift_like(rng, n) if n else None for n in sizes]
+frames = [synth.sift_like(rng, 70), synth.sift_like(rng, 30), None]
+frames[0][:30] = synth.sift_noisy_copy(rng, map_des[6][:30], 4.0)
+frames[1][:20] = synth.sift_noisy_copy(rng, map_des[2][:20], 4.0)
+sm = engine.ShardedMap("SIFT", map_des, local_factory=OracleLocal)
+assert sm.world == world and sm.bounds[rank] == (sm.lo, sm.hi)
+mask = (np.random.default_rng(4).random((3, len(sizes))) < 0.6).astype(np.uint8)
+got = sm.match_counts(frames)
+got_m = sm.match_counts(frames, mask=mask, fill_value=1)
+want = OracleLocal(map_des).match_counts(frames)
+assert np.array_equal(got, want), (rank, got, want)
+assert np.array_equal(got_m, np.where(mask > 0, want, 1))
+assert want[0, 6] >= 20 and want[1, 2] >= 10
+# every rank holds a strict subset and only the counts travelled
+assert sm.hi - sm.lo < len(sizes)
+dist.barrier()
+if rank == 0:
+    print("SHARD_OK", sm.bounds)
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_map_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(repo=REPO))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "SHARD_OK" in r.stdout
