@@ -175,8 +175,10 @@ def run_reference(args):
         "impl": "reference", "metric": "map-image matches/sec", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SIFT 800x600 whole-map matching (BASELINE config 3): %d x %d descriptors per pair" % (NQ, NM),
-                   "pairs_per_step": per_step, "cv2": cv2.__version__},
+        "config": {"workload": "SIFT 800x600 whole-map matching (BASELINE config 3): %d frames x %d descriptors vs "
+                               "%d map images x %d descriptors per GPU (%d locations x %d images), 2-NN + ratio 0.7 + count"
+                               % (args.frames, NQ, args.images, NM, max(1, args.images // IMG_PER_LOC), IMG_PER_LOC),
+                   "sample_pairs_per_step": per_step, "cv2": cv2.__version__},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
                          "sample": "%d (frame,image) pairs of %dx%dx128 per step, cv2.BFMatcher(NORM_L2).knnMatch(k=2)"
                                    " + ratio lambda, cv2.setNumThreads(%d)" % (per_step, NQ, NM, threads)},

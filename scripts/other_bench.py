@@ -1,0 +1,140 @@
+"""Side benchmarks of the other BASELINE.json configs (ORB cfg1, SIFT cfg2, SURF cfg4, BOW cfg5, Laplacian), each with its
+roofline and the cv2/scipy CPU routine timed beside it.  python scripts/other_bench.py [names...]  -> JSON lines."""
+import json, os, sys, time
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "oracle"))
+import numpy as np
+import pymcl_b200
+from pymcl_b200 import _lib, synth
+import oracle
+
+ctx = _lib.Context(0)
+names = sys.argv[1:] or ["orb", "orb_batch", "sift_cfg2", "surf", "bow", "laplacian"]
+POPC_PEAK = None
+
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    ctx.sync()
+    return (time.perf_counter() - t0) / reps
+
+
+def prof(fn, slot, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ctx.profile_enable(True)
+    for _ in range(reps):
+        fn()
+    ms, n = ctx.profile_read(slot)
+    ctx.profile_enable(False)
+    return ms / reps
+
+
+def cpu_rate(fn, budget=5.0):
+    fn()
+    t0 = time.perf_counter(); n = 0
+    while time.perf_counter() - t0 < budget:
+        fn(); n += 1
+    return n / (time.perf_counter() - t0)
+
+
+out = []
+if "orb" in names or "orb_batch" in names:
+    POPC_PEAK, _ = ctx.microbench(1, 20000)
+if "orb" in names:   # cfg1: one (500,32) query vs 50 x (500,32)
+    import cv2
+    map_des, q = synth.orb_map_and_query(1)
+    m = _lib.MapIndex(ctx, "ORB", map_des)
+    for mode, tag in ((_lib.KNN2_RATIO, "knn"), (_lib.CROSSCHECK, "crosscheck")):
+        e2e = timeit(lambda: m.match_counts([q], mode=mode), reps=50)
+        k_ms = prof(lambda: m.match_counts([q], mode=mode), "orb", reps=50)
+        popc = 500 * 500 * 8 * 50 * (1 if mode == _lib.KNN2_RATIO else 2)
+        f = (lambda: [oracle.cv2_orb_pair_count_knn(q, d) for d in map_des]) if mode == _lib.KNN2_RATIO else \
+            (lambda: [oracle.cv2_orb_pair_count_crosscheck(q, d) for d in map_des])
+        cpu = cpu_rate(f, 3.0) * 50
+        out.append({"config": "cfg1 ORB 1x50 " + tag, "e2e_pairs_per_s": 50 / e2e, "e2e_ms": e2e * 1e3, "kernel_ms": k_ms,
+                    "popc_per_s": popc / (k_ms * 1e-3), "frac_popc_peak": popc / (k_ms * 1e-3) / POPC_PEAK,
+                    "cpu_pairs_per_s": cpu, "cpu_threads": cv2.getNumThreads()})
+    m.close()
+if "orb_batch" in names:   # throughput shape: 200 frames x 400 images of 500 rows
+    rng = np.random.default_rng(1)
+    map_des = [synth.orb_like(rng, 500) for _ in range(400)]
+    frames = [synth.orb_like(rng, 500) for _ in range(200)]
+    m = _lib.MapIndex(ctx, "ORB", map_des)
+    for mode, tag in ((_lib.KNN2_RATIO, "knn"), (_lib.CROSSCHECK, "crosscheck")):
+        k_ms = prof(lambda: m.match_counts(frames, mode=mode), "orb", reps=3, warm=1)
+        popc = 500 * 500 * 8 * 400 * 200 * (1 if mode == _lib.KNN2_RATIO else 2)
+        out.append({"config": "ORB 200x400 " + tag, "kernel_ms": k_ms, "pairs_per_s": 80000 / (k_ms * 1e-3),
+                    "popc_per_s": popc / (k_ms * 1e-3), "frac_popc_peak": popc / (k_ms * 1e-3) / POPC_PEAK,
+                    "popc_peak_measured": POPC_PEAK})
+    m.close()
+if "sift_cfg2" in names:   # cfg2: 200 frames x 256 rows vs 8 loc x 50 img x 256 rows
+    map_des, frames = synth.sift_map_and_frames(2, 400, 256, 200, 256)
+    m = _lib.MapIndex(ctx, "SIFT", map_des)
+    res = {}
+    for algo, tag in ((_lib.ALGO_TENSOR, "tc2"), (_lib.ALGO_TENSOR_V1, "tc1"), (_lib.ALGO_SIMT, "simt")):
+        e2e = timeit(lambda: m.match_counts(frames, algo=algo), reps=5, warm=2)
+        res[tag + "_e2e_ms"] = e2e * 1e3
+    k_ms = prof(lambda: m.match_counts(frames, algo=_lib.ALGO_TENSOR), "sift_tc", reps=5, warm=2)
+    ops = 2.0 * 256 * 256 * 128 * 80000
+    import cv2
+    cpu = cpu_rate(lambda: [oracle.cv2_l2_pair_count(frames[0], d) for d in map_des[:50]], 3.0) * 50
+    res.update({"config": "cfg2 SIFT 200x400 (256x256)", "kernel_ms": k_ms, "kernel_TOPs": ops / (k_ms * 1e-3) / 1e12,
+                "e2e_pairs_per_s": 80000 / (res["tc2_e2e_ms"] * 1e-3), "cpu_pairs_per_s": cpu, "cpu_threads": cv2.getNumThreads()})
+    out.append(res)
+    m.close()
+if "surf" in names:   # cfg4 shape: 1024 x 1024 x 64 f32, one frame vs 30 images (a DOR step) and vs 175
+    rng = np.random.default_rng(4)
+    map_des = [synth.surf_like(rng, 1024) for _ in range(175)]
+    q = synth.surf_like(rng, 1024)
+    m = _lib.MapIndex(ctx, "SURF", map_des)
+    mask = np.zeros((1, 175), np.uint8); mask[0, :30] = 1
+    for tag, kw, n in (("175 images", {}, 175), ("30 of 175 (DOR mask)", {"mask": mask}, 30)):
+        e2e = timeit(lambda: m.match_counts([q], **kw), reps=20)
+        k_ms = prof(lambda: m.match_counts([q], **kw), "surf", reps=20)
+        flop = 3.0 * 1024 * 1024 * 64 * n
+        out.append({"config": "cfg4 SURF 1 frame vs " + tag, "e2e_ms": e2e * 1e3, "kernel_ms": k_ms,
+                    "tflops": flop / (k_ms * 1e-3) / 1e12, "pairs_per_s_e2e": n / e2e})
+    import cv2
+    cpu = cpu_rate(lambda: [oracle.cv2_l2_pair_count(q, d) for d in map_des[:10]], 3.0) * 10
+    out[-1]["cpu_pairs_per_s"] = cpu
+    m.close()
+if "bow" in names:   # cfg5 scaled: 16 locations x 100 images, W = 10000, Nq = 300
+    L = 16
+    locs = []
+    for l in range(L):
+        rng = np.random.default_rng(500 + l)
+        voc = (synth.sift_like(rng, 10000) + rng.normal(0, 0.3, size=(10000, 128))).astype(np.float32)
+        im = rng.random((100, 10000), dtype=np.float32) * (rng.random((100, 10000)) < 0.03)
+        im /= np.maximum(np.linalg.norm(im, axis=1, keepdims=True), 1e-9)
+        idf = rng.random(10000, dtype=np.float32) + 0.5
+        locs.append((im.astype(np.float32), idf, voc))
+    bow = _lib.BowIndex(ctx, locs, 10000)
+    rng = np.random.default_rng(9)
+    q = synth.sift_like(rng, 300)
+    e2e = timeit(lambda: bow.score([q]), reps=5, warm=2)
+    vq_ms = prof(lambda: bow.score([q]), "bow_vq", reps=5, warm=2)
+    sc_ms = prof(lambda: bow.score([q]), "bow_score", reps=5, warm=2)
+    from scipy.cluster.vq import vq
+    cpu = cpu_rate(lambda: oracle.scipy_bow_score(q, locs[0][2], locs[0][1], locs[0][0], 10000), 3.0)
+    out.append({"config": "cfg5 BOW 1 frame x %d locations x 100 images (W=10000, Nq=300)" % L, "e2e_ms": e2e * 1e3,
+                "vq_ms": vq_ms, "score_ms": sc_ms, "vq_tflops_fp32": 3.0 * 300 * 10000 * 128 * L / (vq_ms * 1e-3) / 1e12,
+                "score_GBps": L * 100 * 10000 * 4 / (sc_ms * 1e-3) / 1e9, "locations_per_s_e2e": L / e2e,
+                "cpu_locations_per_s": cpu})
+    bow.close()
+if "laplacian" in names:
+    import cv2
+    rng = np.random.default_rng(6)
+    imgs = [rng.integers(0, 256, size=(600, 800), dtype=np.uint8) for _ in range(200)]
+    e2e = timeit(lambda: ctx.laplacian_var(imgs), reps=5, warm=2)
+    k_ms = prof(lambda: ctx.laplacian_var(imgs), "laplacian", reps=5, warm=2)
+    cpu = cpu_rate(lambda: [oracle.cv2_laplacian_var(i) for i in imgs[:20]], 3.0) * 20
+    out.append({"config": "Laplacian 200 x 800x600", "e2e_ms": e2e * 1e3, "kernel_ms": k_ms,
+                "kernel_GBps": 200 * 480000 / (k_ms * 1e-3) / 1e9, "images_per_s_e2e": 200 / e2e, "cpu_images_per_s": cpu})
+for o in out:
+    print(json.dumps(o))
