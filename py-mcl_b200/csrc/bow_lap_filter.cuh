@@ -47,17 +47,26 @@ __global__ void __launch_bounds__(128) bow_vq_kernel(
 }
 
 // tf-idf scoring (Matcher.py:249-258): histogram of words, *idf, L2 normalise, dot with every image row.
-// grid = (n_locations, n_frames), block = 256; dynamic smem = W floats.
+// The query vector has at most (rows of the frame) non-zeros out of W = 10000 words, so after normalisation it is
+// compacted, in word order (deterministic summation order), into a (word, value) list and every image row is only
+// gathered at those words: ~300 x 100 gathers per location instead of a dense 4 MB read.
+// grid = (n_locations, n_frames), block = 256; dynamic smem = W floats + list_cap x (int + float).
 __global__ void __launch_bounds__(256) bow_score_kernel(
     const unsigned long long* __restrict__ best /* [n_loc][n_q] */, int n_q, const int64_t* __restrict__ q_off /* frames */,
     const float* __restrict__ idf /* [n_loc][W] */, const float* __restrict__ im_features /* rows of W */,
-    const int64_t* __restrict__ img_off /* n_loc+1 */, int W, int total_images, int32_t* __restrict__ out_words,
-    float* __restrict__ out_scores /* [n_frames][total_images] */) {
+    const int64_t* __restrict__ img_off /* n_loc+1 */, int W, int total_images, int list_cap,
+    int32_t* __restrict__ out_words, float* __restrict__ out_scores /* [n_frames][total_images] */) {
     extern __shared__ float hist[];
+    int* nz_word = reinterpret_cast<int*>(hist + W);
+    float* nz_val = reinterpret_cast<float*>(nz_word + list_cap);
     __shared__ float red[8];
     __shared__ float inv_norm_s;
+    __shared__ int warp_cnt[8];
+    __shared__ int nz_total;
     const int loc = blockIdx.x, frame = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int w = threadIdx.x; w < W; w += blockDim.x) hist[w] = 0.f;
+    if (threadIdx.x == 0) nz_total = 0;
     __syncthreads();
     const int64_t q0 = q_off[frame], q1 = q_off[frame + 1];
     for (int64_t i = q0 + threadIdx.x; i < q1; i += blockDim.x) {
@@ -74,7 +83,7 @@ __global__ void __launch_bounds__(256) bow_score_kernel(
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    if (lane == 0) red[warp] = ss;
     __syncthreads();
     if (threadIdx.x == 0) {
         float t = 0.f;
@@ -84,14 +93,35 @@ __global__ void __launch_bounds__(256) bow_score_kernel(
     }
     __syncthreads();
     const float nrm = inv_norm_s;
-    for (int w = threadIdx.x; w < W; w += blockDim.x) hist[w] = hist[w] / nrm;
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ordered compaction of the non-zeros
+    for (int base = 0; base < W; base += blockDim.x) {
+        const int w = base + threadIdx.x;
+        const float v = w < W ? hist[w] : 0.f;
+        const bool nz = v != 0.f;
+        const unsigned bal = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = nz_total;
+        for (int k = 0; k < warp; ++k) off += warp_cnt[k];
+        if (nz) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1u));
+            nz_word[pos] = w;
+            nz_val[pos] = v / nrm;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int k = 0; k < 8; ++k) t += warp_cnt[k];
+            nz_total += t;
+        }
+        __syncthreads();
+    }
+    const int n_nz = nz_total;
     const int64_t i0 = img_off[loc], i1 = img_off[loc + 1];
     for (int64_t im = i0 + warp; im < i1; im += 8) {
         const float* row = im_features + im * W;
         float acc = 0.f;
-        for (int w = lane; w < W; w += 32) acc = fmaf(hist[w], row[w], acc);
+        for (int k = lane; k < n_nz; k += 32) acc = fmaf(nz_val[k], row[nz_word[k]], acc);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) out_scores[(int64_t)frame * total_images + im] = acc;
@@ -100,10 +130,13 @@ __global__ void __launch_bounds__(256) bow_score_kernel(
 
 // ------------------------------------------------------------------------------------------
 // variance of the Laplacian (analyze.py:441-445): 4-neighbour kernel, BORDER_REFLECT_101, population var.
-// Shared-memory staged 32x128 tiles with a 1-pixel halo; exact integer sums (sum L in s64, sum L^2 in u64).
-// grid = (tiles_x, tiles_y, n_images).
+// HBM-bound by nature (one byte per pixel).  Each thread owns a 16-pixel-wide column block over LAP_RY rows and slides a
+// three-row window down it: one aligned 128-bit load per row (rows are stored with a 16-byte pitch), each row unpacked
+// to ints once and used three times from registers; ~6 integer instructions per pixel.  Exact integer sums
+// (sum L in s64, sum L^2 in u64; per-thread partials fit 32 bits).
+// grid = (ceil(W/1024), ceil(H/(4*LAP_RY)), n_images), block = (64, 4).
 // ------------------------------------------------------------------------------------------
-constexpr int LAP_TW = 128, LAP_TH = 32;
+constexpr int LAP_RY = 16;
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
@@ -112,41 +145,66 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
+struct LapRow {
+    int px[16];
+    int lh, rh;  // the pixels left of px[0] and right of px[15] (already border-reflected)
+};
+
+__device__ __forceinline__ void lap_load_row(const uint8_t* __restrict__ img, int pitch, int W, int y, int x0, LapRow& r) {
+    const uint8_t* row = img + (int64_t)y * pitch;
+    const uint4 v = *reinterpret_cast<const uint4*>(row + x0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r.px[i] = (int)((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
+    r.lh = x0 > 0 ? (int)row[x0 - 1] : (W > 1 ? r.px[1] : r.px[0]);
+    r.rh = x0 + 16 < W ? (int)row[x0 + 16] : 0;  // only read when the block's last pixel has an in-image right neighbour
+}
+
 __global__ void __launch_bounds__(256) laplacian_sums_kernel(const uint8_t* __restrict__ pixels,
                                                              const int64_t* __restrict__ img_off,
+                                                             const int* __restrict__ pitches,
                                                              const int* __restrict__ hs, const int* __restrict__ ws,
                                                              long long* __restrict__ sums /* [n][2] */) {
     const int im = blockIdx.z;
-    const int H = hs[im], W = ws[im];
-    const int x0 = blockIdx.x * LAP_TW, y0 = blockIdx.y * LAP_TH;
-    if (x0 >= W || y0 >= H) return;
-    const uint8_t* src = pixels + img_off[im];
-    __shared__ uint8_t tile[LAP_TH + 2][LAP_TW + 2 + 2];
-    for (int i = threadIdx.x; i < (LAP_TH + 2) * (LAP_TW + 2); i += blockDim.x) {
-        const int ty = i / (LAP_TW + 2), tx = i % (LAP_TW + 2);
-        const int y = reflect101(y0 + ty - 1, H), x = reflect101(x0 + tx - 1, W);
-        tile[ty][tx] = src[(int64_t)y * W + x];
-    }
-    __syncthreads();
-    long long s1 = 0;
-    unsigned long long s2 = 0;
-    for (int i = threadIdx.x; i < LAP_TH * LAP_TW; i += blockDim.x) {
-        const int ty = i / LAP_TW, tx = i % LAP_TW;
-        if (y0 + ty < H && x0 + tx < W) {
-            const int l = (int)tile[ty][tx + 1] + (int)tile[ty + 2][tx + 1] + (int)tile[ty + 1][tx] +
-                          (int)tile[ty + 1][tx + 2] - 4 * (int)tile[ty + 1][tx + 1];
-            s1 += l;
-            s2 += (unsigned long long)(l * l);
+    const int H = hs[im], W = ws[im], pitch = pitches[im];
+    const int x0 = (blockIdx.x * 64 + threadIdx.x) * 16;
+    const int ys = (blockIdx.y * 4 + threadIdx.y) * LAP_RY;
+    int s1 = 0;
+    unsigned s2 = 0;
+    if (x0 < W && ys < H) {
+        const uint8_t* img = pixels + img_off[im];
+        const int ye = min(H, ys + LAP_RY);
+        LapRow up, mid, dn;
+        lap_load_row(img, pitch, W, reflect101(ys - 1, H), x0, up);
+        lap_load_row(img, pitch, W, ys, x0, mid);
+        for (int y = ys; y < ye; ++y) {
+            lap_load_row(img, pitch, W, reflect101(y + 1, H), x0, dn);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int x = x0 + i;
+                const int left = i == 0 ? mid.lh : mid.px[i - 1];
+                int right = i == 15 ? mid.rh : mid.px[i + 1];
+                if (x == W - 1) right = W > 1 ? left : mid.px[i];  // REFLECT_101: the neighbour beyond the edge mirrors x-1
+                const int l = up.px[i] + dn.px[i] + left + right - 4 * mid.px[i];
+                if (x < W) {
+                    s1 += l;
+                    s2 += (unsigned)(l * l);
+                }
+            }
+            up = mid;
+            mid = dn;
         }
     }
+    long long t1 = s1;
+    unsigned long long t2 = s2;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(reinterpret_cast<unsigned long long*>(&sums[2 * im]), (unsigned long long)s1);
-        atomicAdd(reinterpret_cast<unsigned long long*>(&sums[2 * im + 1]), s2);
+    if (threadIdx.x % 32 == 0 && (t1 != 0 || t2 != 0)) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&sums[2 * im]), (unsigned long long)t1);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&sums[2 * im + 1]), t2);
     }
 }
 

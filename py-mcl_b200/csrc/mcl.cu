@@ -76,6 +76,8 @@ struct mcl_ctx {
     int sm_count = 0;
     cudaDeviceProp prop{};
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // H2D + ingest of the next part of a host batch while the current part is matched
+    std::vector<cudaEvent_t> part_events;
     int64_t launches = 0;
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[PROF_N];
@@ -187,26 +189,30 @@ size_t row_bytes(int kind, int dtype) {
 // ingest (n_rows,128) rows from the host into the SW128-atom layout + norms + segment ids
 int ingest_rows128(mcl_ctx* c, cudaStream_t st, const void* h_src, int dtype, int64_t n_rows, int n_seg,
                    const int64_t* d_src_off, const int64_t* d_dst_off, int64_t padded_rows, uint8_t* d_desc,
-                   int32_t* d_norm, int32_t* d_seg) {
+                   int32_t* d_norm, int32_t* d_seg, uint8_t* d_stage = nullptr /* null: the context's staging buffer */,
+                   bool check_now = true) {
     CU(cudaMemsetAsync(d_desc, 0, (size_t)padded_rows * 128, st));
     CU(cudaMemsetAsync(d_norm, 0xFF, (size_t)padded_rows * 4, st));
     CU(cudaMemsetAsync(d_seg, 0xFF, (size_t)padded_rows * 4, st));
     if (n_rows == 0) return MCL_OK;
     const size_t bytes = (size_t)n_rows * (dtype == MCL_F32 ? 512 : 128);
-    CU(c->stage.ensure(bytes));
-    CU(cudaMemcpyAsync(c->stage.p, h_src, bytes, cudaMemcpyHostToDevice, st));
+    if (!d_stage) {
+        CU(c->stage.ensure(bytes));
+        d_stage = c->stage.as<uint8_t>();
+    }
+    CU(cudaMemcpyAsync(d_stage, h_src, bytes, cudaMemcpyHostToDevice, st));
     int* bad = c->flags.as<int>() + 2;
-    CU(cudaMemsetAsync(bad, 0, 4, st));
+    if (check_now) CU(cudaMemsetAsync(bad, 0, 4, st));
     {
         ProfScope ps(c, PROF_PREP, st);
         const int grid = grid_for(n_rows * 32, 256, c->sm_count * 8);
         if (dtype == MCL_F32)
-            mcl::prep_rows128_kernel<true><<<grid, 256, 0, st>>>(c->stage.p, n_rows, d_src_off, d_dst_off, n_seg, d_desc, d_norm, d_seg, bad);
+            mcl::prep_rows128_kernel<true><<<grid, 256, 0, st>>>(d_stage, n_rows, d_src_off, d_dst_off, n_seg, d_desc, d_norm, d_seg, bad);
         else
-            mcl::prep_rows128_kernel<false><<<grid, 256, 0, st>>>(c->stage.p, n_rows, d_src_off, d_dst_off, n_seg, d_desc, d_norm, d_seg, bad);
+            mcl::prep_rows128_kernel<false><<<grid, 256, 0, st>>>(d_stage, n_rows, d_src_off, d_dst_off, n_seg, d_desc, d_norm, d_seg, bad);
     }
     CU(cudaGetLastError());
-    if (dtype == MCL_F32) {
+    if (dtype == MCL_F32 && check_now) {
         int h_bad = 0;
         CU(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -295,6 +301,8 @@ extern "C" void mcl_shutdown(mcl_ctx* c) {
                       &c->tmp_counts, &c->tmp_mask, &c->tmp_words, &c->tmp_scores, &c->tq_off, &c->tq_desc, &c->tq_norm,
                       &c->tq_frame};
     for (DevBuf* b : bufs) b->release();
+    for (cudaEvent_t e : c->part_events) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -863,12 +871,111 @@ extern "C" int mcl_match_counts_device(mcl_map* m, mcl_queries* q, int mode, dou
     return match_device(m, q, mode, ratio, d_mask, fill_value, algo, d_counts, st);
 }
 
+namespace {
+// Host batch of SIFT frames, large enough to be worth pipelining: the frames are cut into up to 8 parts; part p+1 is
+// copied (H2D) and ingested on the copy stream while part p is matched on the main stream.  Returns 1 if the batch is
+// too small (caller takes the plain path).
+int match_counts_sift_pipelined(mcl_map* m, int n_queries, const int64_t* offs, const void* q_desc, int q_dtype, int mode,
+                                double ratio, const uint8_t* mask, int32_t fill_value, int algo, int32_t* out_counts) {
+    mcl_ctx* c = m->ctx;
+    const int64_t total_rows = offs[n_queries];
+    int P = (int)std::min<int64_t>(8, total_rows / 32768);
+    P = std::min(P, n_queries);
+    if (P <= 1 || m->n_images == 0) return 1;
+    CU(cudaSetDevice(c->device));
+    if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    while ((int)c->part_events.size() < P) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->part_events.push_back(e);
+    }
+    // frame ranges with about equal rows
+    std::vector<int> fb(P + 1, n_queries);
+    fb[0] = 0;
+    for (int p = 1, f = 0; p < P; ++p) {
+        const int64_t target = total_rows * p / P;
+        while (f < n_queries && offs[f] < target) ++f;
+        fb[p] = std::max(f, fb[p - 1]);
+    }
+    const size_t row_b = q_dtype == MCL_F32 ? 512 : 128;
+    const int ni = m->n_images;
+    const size_t n_out = (size_t)n_queries * ni;
+    std::vector<int64_t> region(P + 1, 0);
+    for (int p = 0; p < P; ++p) {
+        const int64_t rows = offs[fb[p + 1]] - offs[fb[p]];
+        region[p + 1] = region[p] + std::max<int64_t>(QROW_PAD, (rows + QROW_PAD - 1) / QROW_PAD * QROW_PAD);
+    }
+    CU(c->tq_desc.ensure((size_t)region[P] * 128));
+    CU(c->tq_norm.ensure((size_t)region[P] * 4));
+    CU(c->tq_frame.ensure((size_t)region[P] * 4));
+    CU(c->tq_off.ensure((size_t)(n_queries + P) * 8));
+    CU(c->stage.ensure((size_t)total_rows * row_b));
+    CU(c->tmp_counts.ensure(n_out * 4));
+    cudaStream_t st = c->stream, cs = c->copy_stream;
+    uint8_t* d_mask = nullptr;
+    if (mask) {
+        CU(c->tmp_mask.ensure(n_out));
+        CU(cudaMemcpyAsync(c->tmp_mask.p, mask, n_out, cudaMemcpyHostToDevice, st));
+        d_mask = c->tmp_mask.as<uint8_t>();
+    }
+    int* bad = c->flags.as<int>() + 2;
+    CU(cudaMemsetAsync(bad, 0, 4, cs));
+    std::vector<mcl_queries> parts(P);
+    int rc = MCL_OK;
+    for (int p = 0; p < P && rc == MCL_OK; ++p) {
+        mcl_queries& q = parts[p];
+        const int f0 = fb[p], f1 = fb[p + 1];
+        q.ctx = c;
+        q.kind = MCL_SIFT;
+        q.borrowed = true;
+        q.n_queries = f1 - f0;
+        q.h_off.resize(q.n_queries + 1);
+        for (int f = f0; f <= f1; ++f) q.h_off[f - f0] = offs[f] - offs[f0];
+        q.rows = q.h_off.back();
+        q.padded_rows = region[p + 1] - region[p];
+        q.d_off = c->tq_off.as<int64_t>() + f0 + p;
+        q.d_desc = c->tq_desc.as<uint8_t>() + (size_t)region[p] * 128;
+        q.d_norm = c->tq_norm.as<int32_t>() + region[p];
+        q.d_frame = c->tq_frame.as<int32_t>() + region[p];
+        if (q.n_queries == 0) continue;
+        CU(cudaMemcpyAsync(q.d_off, q.h_off.data(), (size_t)(q.n_queries + 1) * 8, cudaMemcpyHostToDevice, cs));
+        rc = ingest_rows128(c, cs, (const uint8_t*)q_desc + (size_t)offs[f0] * row_b, q_dtype, q.rows, q.n_queries, q.d_off,
+                            q.d_off, q.padded_rows, (uint8_t*)q.d_desc, q.d_norm, q.d_frame,
+                            c->stage.as<uint8_t>() + (size_t)offs[f0] * row_b, false);
+        if (rc) break;
+        CU(cudaEventRecord(c->part_events[p], cs));
+        CU(cudaStreamWaitEvent(st, c->part_events[p], 0));
+        rc = match_device(m, &q, mode, ratio, d_mask ? d_mask + (size_t)f0 * ni : nullptr, fill_value, algo,
+                          c->tmp_counts.as<int32_t>() + (size_t)f0 * ni, st);
+    }
+    if (rc == MCL_OK) {
+        cudaError_t e = cudaMemcpyAsync(out_counts, c->tmp_counts.p, n_out * 4, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) rc = fail(MCL_ECUDA, "D2H of counts failed: %s", cudaGetErrorString(e));
+    }
+    int h_bad = 0;
+    cudaStreamSynchronize(cs);
+    cudaError_t e1 = cudaStreamSynchronize(st);
+    if (rc == MCL_OK && e1 != cudaSuccess) rc = fail(MCL_ECUDA, "stream sync failed: %s", cudaGetErrorString(e1));
+    if (rc == MCL_OK && q_dtype == MCL_F32) {
+        CU(cudaMemcpy(&h_bad, bad, 4, cudaMemcpyDeviceToHost));
+        if (h_bad) rc = fail(MCL_EDATA, "SIFT descriptors must be integer valued in [0,255]");
+    }
+    return rc;
+}
+}  // namespace
+
 extern "C" int mcl_match_counts(mcl_map* m, int n_queries, const int64_t* q_row_offsets, const void* q_desc, int q_dtype,
                                 int mode, double ratio, const uint8_t* mask, int32_t fill_value, int algo,
                                 int32_t* out_counts) {
     if (!m || !out_counts) return fail(MCL_EINVAL, "mcl_match_counts: NULL argument");
     if (!(ratio > 0.0) || !(ratio <= 1.0)) return fail(MCL_EINVAL, "ratio must be in (0,1]");
     mcl_ctx* c = m->ctx;
+    if (m->kind == MCL_SIFT && n_queries > 1 && q_row_offsets && q_desc && (q_dtype == MCL_U8 || q_dtype == MCL_F32) &&
+        check_offsets(q_row_offsets, n_queries, "mcl_match_counts") == MCL_OK && n_queries <= 65535) {
+        const int r = match_counts_sift_pipelined(m, n_queries, q_row_offsets, q_desc, q_dtype, mode, ratio, mask, fill_value,
+                                                  algo, out_counts);
+        if (r != 1) return r;
+    }
     mcl_queries* q = nullptr;
     int rc = queries_build(c, m->kind, n_queries, q_row_offsets, q_desc, q_dtype, true, &q);
     if (rc) return rc;
@@ -915,7 +1022,7 @@ extern "C" int mcl_bow_create(mcl_ctx* c, int n_locations, const int64_t* voc_ro
     if (!c || !out || !voc || !idf || !im_features) return fail(MCL_EINVAL, "mcl_bow_create: NULL argument");
     *out = nullptr;
     if (n_locations <= 0 || W <= 0) return fail(MCL_EINVAL, "mcl_bow_create: n_locations and W must be positive");
-    if ((size_t)W * 4 > 200 * 1024) return fail(MCL_EINVAL, "mcl_bow_create: W=%d does not fit the shared-memory histogram", W);
+    if ((size_t)W * 12 > 200 * 1024) return fail(MCL_EINVAL, "mcl_bow_create: W=%d does not fit the shared-memory histogram + word list", W);
     int rc = check_offsets(voc_row_offsets, n_locations, "mcl_bow_create(voc)");
     if (rc) return rc;
     rc = check_offsets(img_offsets, n_locations, "mcl_bow_create(images)");
@@ -956,7 +1063,7 @@ extern "C" int mcl_bow_create(mcl_ctx* c, int n_locations, const int64_t* voc_ro
         BCU(cudaMemcpyAsync(b->d_imf, im_features, (size_t)b->total_images * W * 4, cudaMemcpyHostToDevice, st));
     BCU(cudaMemcpyAsync(b->d_voc_off, b->h_voc_off.data(), (size_t)(n_locations + 1) * 8, cudaMemcpyHostToDevice, st));
     BCU(cudaMemcpyAsync(b->d_img_off, b->h_img_off.data(), (size_t)(n_locations + 1) * 8, cudaMemcpyHostToDevice, st));
-    BCU(cudaFuncSetAttribute(mcl::bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W * 4));
+    BCU(cudaFuncSetAttribute(mcl::bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W * 12));
     BCU(cudaStreamSynchronize(st));
 #undef BCU
     *out = b;
@@ -987,10 +1094,13 @@ extern "C" int mcl_bow_score_device(mcl_bow* b, mcl_queries* q, int32_t* d_words
     CU(cudaGetLastError());
     {
         dim3 grid(b->n_loc, nf);
+        int64_t max_rows = 1;
+        for (int f = 0; f < nf; ++f) max_rows = std::max(max_rows, q->h_off[f + 1] - q->h_off[f]);
+        const int list_cap = (int)std::min<int64_t>(b->W, max_rows);   // distinct words of a frame <= its rows
         ProfScope ps(c, PROF_SCORE, st);
-        mcl::bow_score_kernel<<<grid, 256, (size_t)b->W * 4, st>>>(c->bow_best.as<unsigned long long>(), n_q, q->d_off, b->d_idf,
-                                                                   b->d_imf, b->d_img_off, b->W, (int)b->total_images,
-                                                                   d_words, d_scores);
+        mcl::bow_score_kernel<<<grid, 256, (size_t)b->W * 4 + (size_t)list_cap * 8, st>>>(
+            c->bow_best.as<unsigned long long>(), n_q, q->d_off, b->d_idf, b->d_imf, b->d_img_off, b->W,
+            (int)b->total_images, list_cap, d_words, d_scores);
     }
     CU(cudaGetLastError());
     return MCL_OK;
@@ -1038,34 +1148,38 @@ int laplacian_common(mcl_ctx* c, int n, const uint8_t* const* imgs, const int* h
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     std::vector<int64_t> off(n + 1, 0);
+    std::vector<int> pitch(n);
     int max_h = 0, max_w = 0;
     for (int i = 0; i < n; ++i) {
         if (h[i] <= 0 || w[i] <= 0 || !imgs[i]) return fail(MCL_EINVAL, "image %d: bad size or NULL pointer", i);
         if (stride && stride[i] < w[i]) return fail(MCL_EINVAL, "image %d: stride < width", i);
-        off[i + 1] = off[i] + (((int64_t)h[i] * w[i] + 15) & ~(int64_t)15);
+        pitch[i] = (w[i] + 15) & ~15;   // rows start on 16-byte boundaries: one aligned 128-bit load per 16 pixels
+        off[i + 1] = off[i] + (int64_t)h[i] * pitch[i];
         max_h = std::max(max_h, h[i]);
         max_w = std::max(max_w, w[i]);
     }
-    CU(c->lap_pix.ensure((size_t)off[n]));
-    // meta: off (n+1 int64) | h (n int) | w (n int) | sums (2n int64) | var (n double)
-    const size_t o_h = (size_t)(n + 1) * 8, o_w = o_h + (size_t)n * 4, o_s = (o_w + (size_t)n * 4 + 7) & ~(size_t)7,
-                 o_v = o_s + (size_t)n * 16, total = o_v + (size_t)n * 8;
+    CU(c->lap_pix.ensure((size_t)off[n] + 32));
+    // meta: off (n+1 int64) | h (n int) | w (n int) | pitch (n int) | sums (2n int64) | var (n double)
+    const size_t o_h = (size_t)(n + 1) * 8, o_w = o_h + (size_t)n * 4, o_p = o_w + (size_t)n * 4,
+                 o_s = (o_p + (size_t)n * 4 + 7) & ~(size_t)7, o_v = o_s + (size_t)n * 16, total = o_v + (size_t)n * 8;
     CU(c->lap_meta.ensure(total));
     uint8_t* mb = c->lap_meta.as<uint8_t>();
     for (int i = 0; i < n; ++i) {
         const int s = stride ? stride[i] : w[i];
-        CU(cudaMemcpy2DAsync(c->lap_pix.as<uint8_t>() + off[i], (size_t)w[i], imgs[i], (size_t)s, (size_t)w[i], (size_t)h[i],
+        CU(cudaMemcpy2DAsync(c->lap_pix.as<uint8_t>() + off[i], (size_t)pitch[i], imgs[i], (size_t)s, (size_t)w[i], (size_t)h[i],
                              cudaMemcpyHostToDevice, st));
     }
     CU(cudaMemcpyAsync(mb, off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(mb + o_h, h, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(mb + o_w, w, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(mb + o_p, pitch.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(mb + o_s, 0, (size_t)n * 16, st));
     {
-        dim3 grid((max_w + mcl::LAP_TW - 1) / mcl::LAP_TW, (max_h + mcl::LAP_TH - 1) / mcl::LAP_TH, n);
+        dim3 grid((max_w + 1023) / 1024, (max_h + 4 * mcl::LAP_RY - 1) / (4 * mcl::LAP_RY), n);
         ProfScope ps(c, PROF_LAP, st);
-        mcl::laplacian_sums_kernel<<<grid, 256, 0, st>>>(c->lap_pix.as<uint8_t>(), (const int64_t*)mb, (const int*)(mb + o_h),
-                                                         (const int*)(mb + o_w), (long long*)(mb + o_s));
+        mcl::laplacian_sums_kernel<<<grid, dim3(64, 4), 0, st>>>(c->lap_pix.as<uint8_t>(), (const int64_t*)mb,
+                                                                 (const int*)(mb + o_p), (const int*)(mb + o_h),
+                                                                 (const int*)(mb + o_w), (long long*)(mb + o_s));
     }
     CU(cudaGetLastError());
     if (var_out) {

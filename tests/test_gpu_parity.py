@@ -140,6 +140,37 @@ def test_sift_full_size_properties(ctx):
     assert np.array_equal(tc2, tc[:, perm])
 
 
+def test_sift_host_batch_pipelined_equals_resident(ctx):
+    """Host batches above 64 k rows are cut into parts (H2D + ingest of part p+1 overlaps the matching of part p):
+    same counts as the resident-query path and as the oracle on a sample; ragged frames, a mask, float32 input."""
+    import torch
+    rng = np.random.default_rng(12)
+    map_des = [synth.sift_like(rng, n) for n in (700, 64, 1500, 333)]
+    sizes = [2048] * 30 + [0, 1, 777, 4000, 2048, 2048, 5, 2048, 3000, 2048]
+    frames = [synth.sift_like(rng, n) if n else None for n in sizes]
+    frames[3][:300] = synth.sift_noisy_copy(rng, map_des[2][:300], 4.0)
+    frames[33][:200] = synth.sift_noisy_copy(rng, map_des[0][:200], 4.0)
+    assert sum(sizes) > 2 * 32768
+    m = _lib.MapIndex(ctx, "SIFT", map_des)
+    got = m.match_counts(frames, algo=_lib.ALGO_TENSOR)
+    q = _lib.QueryBatch(ctx, "SIFT", frames)
+    out = torch.zeros((len(frames), len(map_des)), dtype=torch.int32, device="cuda")
+    m.match_counts_device(q, out.data_ptr(), algo=_lib.ALGO_TENSOR)
+    ctx.sync()
+    assert np.array_equal(got, out.cpu().numpy())
+    for f in (3, 30, 31, 32, 33, 39):
+        assert np.array_equal(got[f], [oracle.sift_pair_count(frames[f], d) for d in map_des])
+    assert got[3, 2] >= 250 and got[33, 0] >= 150
+    mask = (rng.random(got.shape) < 0.5).astype(np.uint8)
+    assert np.array_equal(m.match_counts(frames, mask=mask, fill_value=1, algo=_lib.ALGO_TENSOR), np.where(mask > 0, got, 1))
+    bad = [f.copy() if f is not None else None for f in frames]
+    bad[20][5, 5] = 0.25
+    with pytest.raises(_lib.MclError):
+        m.match_counts(bad, algo=_lib.ALGO_TENSOR)
+    q.close()
+    m.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # ORB
 # ------------------------------------------------------------------------------------------------
