@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--images", type=int, default=LOC_PER_GPU * IMG_PER_LOC, help="map images per GPU")
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="0 = auto (about 10-20 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--algo", type=int, default=1, help="1 = sift_tc3 (product), 4 = sift_tc2, 3 = sift_tc, 2 = SIMT")
+    ap.add_argument("--opt1", type=int, default=0, help="libmcl diagnostic option 1")
     return ap.parse_args()
 
 
@@ -210,6 +212,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.Context(local_rank)  # fails loudly without libmcl.so / an sm_100 GPU
     info = ctx.info()
+    if args.opt1:
+        ctx.set_option(1, args.opt1)
 
     n_images, n_frames = args.images, args.frames
     map_des, frames = make_workload(rank, n_images, n_frames)
@@ -227,12 +231,12 @@ def main():
     d_all = torch.zeros((world, n_frames, n_images), dtype=torch.int32, device="cuda") if world > 1 else None
 
     def step_resident():
-        resident.match_counts_device(queries, d_counts.data_ptr(), algo=_lib.ALGO_TENSOR, stream=stream.cuda_stream)
+        resident.match_counts_device(queries, d_counts.data_ptr(), algo=args.algo, stream=stream.cuda_stream)
         if world > 1:
             dist.all_gather_into_tensor(d_all, d_counts)
 
     def step_e2e():
-        c = resident.match_counts(None, algo=_lib.ALGO_TENSOR, packed=packed_pinned)
+        c = resident.match_counts(None, algo=args.algo, packed=packed_pinned)
         if world > 1:
             t = torch.from_numpy(c).cuda(non_blocking=True)
             dist.all_gather_into_tensor(d_all, t)

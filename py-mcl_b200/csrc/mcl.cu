@@ -17,6 +17,7 @@
 #include "prep.cuh"
 #include "sift_tc.cuh"
 #include "sift_tc2.cuh"
+#include "sift_tc3.cuh"
 #include "simt_match.cuh"
 #include "bow_lap_filter.cuh"
 #include "microbench.cuh"
@@ -124,6 +125,8 @@ struct mcl_map {
     int n_tiles2 = 0;
     int key_c = 0;                       // sift_tc2: true key = 2*acc - key_c (+ parity)
     bool ext_ok = false;                 // the norms' range fits the extension encoding
+    mcl::sifttc3::TileMeta* d_meta3 = nullptr;   // sift_tc3: per 64-row tile
+    bool tc3_attr = false;
     int max_rows_per_image = 0;
 };
 
@@ -190,7 +193,7 @@ size_t row_bytes(int kind, int dtype) {
 int ingest_rows128(mcl_ctx* c, cudaStream_t st, const void* h_src, int dtype, int64_t n_rows, int n_seg,
                    const int64_t* d_src_off, const int64_t* d_dst_off, int64_t padded_rows, uint8_t* d_desc,
                    int32_t* d_norm, int32_t* d_seg, uint8_t* d_stage = nullptr /* null: the context's staging buffer */,
-                   bool check_now = true) {
+                   bool check_now = true, const int32_t* d_perm = nullptr) {
     CU(cudaMemsetAsync(d_desc, 0, (size_t)padded_rows * 128, st));
     CU(cudaMemsetAsync(d_norm, 0xFF, (size_t)padded_rows * 4, st));
     CU(cudaMemsetAsync(d_seg, 0xFF, (size_t)padded_rows * 4, st));
@@ -207,9 +210,9 @@ int ingest_rows128(mcl_ctx* c, cudaStream_t st, const void* h_src, int dtype, in
         ProfScope ps(c, PROF_PREP, st);
         const int grid = grid_for(n_rows * 32, 256, c->sm_count * 8);
         if (dtype == MCL_F32)
-            mcl::prep_rows128_kernel<true><<<grid, 256, 0, st>>>(d_stage, n_rows, d_src_off, d_dst_off, n_seg, d_desc, d_norm, d_seg, bad);
+            mcl::prep_rows128_kernel<true><<<grid, 256, 0, st>>>(d_stage, n_rows, d_src_off, d_dst_off, n_seg, d_desc, d_norm, d_seg, bad, d_perm);
         else
-            mcl::prep_rows128_kernel<false><<<grid, 256, 0, st>>>(d_stage, n_rows, d_src_off, d_dst_off, n_seg, d_desc, d_norm, d_seg, bad);
+            mcl::prep_rows128_kernel<false><<<grid, 256, 0, st>>>(d_stage, n_rows, d_src_off, d_dst_off, n_seg, d_desc, d_norm, d_seg, bad, d_perm);
     }
     CU(cudaGetLastError());
     if (dtype == MCL_F32 && check_now) {
@@ -386,6 +389,7 @@ extern "C" void mcl_map_destroy(mcl_map* m) {
     for (auto& cs : m->chunk_sets) cudaFree(cs.d);
     for (auto& cs : m->chunk_sets2) cudaFree(cs.d);
     cudaFree(m->d_ext2);
+    cudaFree(m->d_meta3);
     delete m;
 }
 
@@ -442,8 +446,37 @@ extern "C" int mcl_map_create(mcl_ctx* c, int kind, int n_images, const int64_t*
         MCU(cudaMalloc(&m->d_norm, (size_t)m->padded_rows * 4));
         MCU(cudaMalloc(&m->d_img_of, (size_t)m->padded_rows * 4));
         MCU(cudaMalloc(&m->d_meta, (size_t)m->n_tiles * sizeof(TileMeta)));
+        // rows of every image are stored sorted by |m|^2 (sift_tc3: a 32-row group then has one norm, up to a few units)
+        int32_t* d_perm = nullptr;
+        if (rows > 0) {
+            std::vector<int64_t> nrm((size_t)rows);
+            if (desc_dtype == MCL_U8) {
+                const uint8_t* p8 = (const uint8_t*)desc;
+                for (int64_t r = 0; r < rows; ++r) {
+                    int64_t a = 0;
+                    for (int k = 0; k < 128; ++k) a += (int64_t)p8[r * 128 + k] * p8[r * 128 + k];
+                    nrm[r] = a;
+                }
+            } else {
+                const float* pf = (const float*)desc;
+                for (int64_t r = 0; r < rows; ++r) {
+                    double a = 0;
+                    for (int k = 0; k < 128; ++k) a += (double)pf[r * 128 + k] * pf[r * 128 + k];
+                    nrm[r] = (int64_t)a;
+                }
+            }
+            std::vector<int32_t> perm((size_t)rows);
+            for (int64_t r = 0; r < rows; ++r) perm[r] = (int32_t)r;
+            for (int i = 0; i < n_images; ++i)
+                std::stable_sort(perm.begin() + row_offsets[i], perm.begin() + row_offsets[i + 1],
+                                 [&](int32_t a, int32_t b) { return nrm[a] < nrm[b]; });
+            MCU(cudaMalloc(&d_perm, (size_t)rows * 4));
+            MCU(cudaMemcpy(d_perm, perm.data(), (size_t)rows * 4, cudaMemcpyHostToDevice));
+        }
         rc = ingest_rows128(c, st, desc, desc_dtype, rows, n_images, m->d_src_off, m->d_dst_off, m->padded_rows,
-                            (uint8_t*)m->d_desc, m->d_norm, m->d_img_of);
+                            (uint8_t*)m->d_desc, m->d_norm, m->d_img_of, nullptr, true, d_perm);
+        cudaStreamSynchronize(st);
+        cudaFree(d_perm);
         if (rc) { mcl_map_destroy(m); return rc; }
         {
             ProfScope ps(c, PROF_PREP, st);
@@ -495,6 +528,14 @@ extern "C" int mcl_map_create(mcl_ctx* c, int kind, int n_images, const int64_t*
             }
             MCU(cudaGetLastError());
         }
+        // ---- third-generation kernel: per 64-row tile metadata with the groups' norm brackets
+        MCU(cudaMalloc(&m->d_meta3, (size_t)m->n_tiles2 * sizeof(mcl::sifttc3::TileMeta)));
+        {
+            ProfScope ps(c, PROF_PREP, st);
+            mcl::sifttc3::build_meta_kernel<<<(m->n_tiles2 + 127) / 128, 128, 0, st>>>(m->d_norm, m->d_img_of, m->d_src_off,
+                                                                                   m->n_tiles2, m->d_meta3);
+        }
+        MCU(cudaGetLastError());
         m->resident_bytes = (size_t)m->padded_rows * (128 + 8) + (size_t)m->n_tiles * sizeof(TileMeta) +
                             (m->d_ext2 ? (size_t)m->n_tiles2 * mcl::sifttc2::EXT_META_BYTES : 0);
     } else {
@@ -779,6 +820,90 @@ int launch_sift_tc2(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
     return MCL_OK;
 }
 
+int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, cudaStream_t st) {
+    using namespace mcl::sifttc3;
+    mcl_ctx* c = m->ctx;
+    const size_t smem = sizeof(Smem);
+    if (!m->tc3_attr) {
+        CU(cudaFuncSetAttribute(sift_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc3_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        m->tc3_attr = true;
+    }
+    const int n_qblocks_total = (int)(q->padded_rows / QBLK);
+    const int64_t pairs_total = q->padded_rows * (int64_t)std::max(1, m->n_images);
+    const int64_t want = std::min<int64_t>(std::max<int64_t>(pairs_total / 4, 1 << 16), (int64_t)48 << 20);
+    if ((size_t)want > c->cand_cap_entries) {
+        CU(c->cand.ensure((size_t)want * sizeof(int4)));
+        c->cand_cap_entries = (size_t)want;
+    }
+    const int64_t cap = (int64_t)c->cand_cap_entries;
+    int batch_qblocks = (int)std::max<int64_t>(1, cap * 4 / ((int64_t)std::max(1, m->n_images) * QBLK));
+    batch_qblocks = std::min(batch_qblocks, n_qblocks_total);
+    unsigned int* d_cand_count = c->flags.as<unsigned int>();
+    int* d_overflow = c->flags.as<int>() + 1;
+    unsigned int* d_rescans = c->flags.as<unsigned int>() + 3;
+    CU(cudaMemsetAsync(d_overflow, 0, 4, st));
+    for (int qb0 = 0; qb0 < n_qblocks_total; qb0 += batch_qblocks) {
+        const int nqb = std::min(batch_qblocks, n_qblocks_total - qb0);
+        const mcl_map::ChunkSet* cs = pick_chunks(m->chunk_sets2, nqb, c->sm_count);
+        if (cs->n == 0) break;
+        CU(cudaMemsetAsync(d_cand_count, 0, 4, st));
+        Params p;
+        p.q_desc = (const uint8_t*)q->d_desc + (size_t)qb0 * QBLK * 128;
+        p.q_norm = q->d_norm + (size_t)qb0 * QBLK;
+        p.m_desc = (const uint8_t*)m->d_desc;
+        p.m_meta = m->d_meta3;
+        p.chunks = cs->d;
+        p.n_qblocks = nqb;
+        p.n_chunks = cs->n;
+        p.ratio = ratio;
+        p.cand = c->cand.as<int4>();
+        p.cand_count = d_cand_count;
+        p.cand_cap = (unsigned)cap;
+        p.overflow = d_overflow;
+        p.q_row_base = qb0 * QBLK;
+        p.meta_cap = c->opt[1] == 1 ? 0 : META_CAP;   // option 1 = 1: always read the tile metadata from global memory
+        const int64_t n_items = (int64_t)nqb * cs->n;
+        const int grid = (int)std::min<int64_t>(n_items, c->sm_count);
+        {
+            ProfScope ps(c, PROF_SIFT_TC, st);
+            if (c->opt[0] == 3) sift_tc3_kernel<3><<<grid, THREADS, smem, st>>>(p);
+            else if (c->opt[0] == 4) sift_tc3_kernel<4><<<grid, THREADS, smem, st>>>(p);
+            else if (c->opt[0] == 5) {
+                sift_tc3_kernel<5><<<grid, THREADS, smem, st>>>(p);
+                long long tl[64 * 5];
+                cudaStreamSynchronize(st);
+                cudaMemcpy(tl, reinterpret_cast<long long*>(c->cand.p) + (size_t)(1 << 20), sizeof tl, cudaMemcpyDeviceToHost);
+                for (int i = 0; i < 64; ++i)
+                    fprintf(stderr, "tile %2d: wait_full %5lld  ldtm %5lld  release %5lld  compute %5lld  | period %5lld\n", i, tl[i * 5 + 1] - tl[i * 5],
+                            tl[i * 5 + 2] - tl[i * 5 + 1], tl[i * 5 + 3] - tl[i * 5 + 2], tl[i * 5 + 4] - tl[i * 5 + 3],
+                            i ? tl[i * 5] - tl[i * 5 - 5] : 0);
+            }
+            else sift_tc3_kernel<0><<<grid, THREADS, smem, st>>>(p);
+        }
+        CU(cudaGetLastError());
+        {
+            ProfScope ps(c, PROF_SIFT_FIX, st);
+            sift_fixup3_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->cand.as<int4>(), d_cand_count, (unsigned)cap,
+                                                               (const uint8_t*)q->d_desc, q->d_norm, q->d_frame,
+                                                               (const uint8_t*)m->d_desc, m->d_norm, m->d_img_of, m->d_dst_off,
+                                                               ratio, m->n_images, d_counts, d_rescans);
+        }
+        CU(cudaGetLastError());
+    }
+    {
+        ProfScope ps(c, PROF_SIFT_SIMT, st);
+        dim3 grid(std::max(1, m->n_images), std::max(1, q->n_queries));
+        mcl::sift_simt_kernel<<<grid, 128, 0, st>>>((const uint8_t*)q->d_desc, q->d_norm, q->d_off, (const uint8_t*)m->d_desc,
+                                                    m->d_norm, m->d_dst_off, m->d_src_off, m->n_images, ratio, nullptr,
+                                                    d_overflow, d_counts);
+    }
+    CU(cudaGetLastError());
+    return MCL_OK;
+}
+
 int match_device(mcl_map* m, mcl_queries* q, int mode, double ratio, const uint8_t* d_mask, int32_t fill, int algo,
                  int32_t* d_counts, cudaStream_t st) {
     mcl_ctx* c = m->ctx;
@@ -797,8 +922,11 @@ int match_device(mcl_map* m, mcl_queries* q, int mode, double ratio, const uint8
                 const double macs = (double)q->rows * (double)m->rows;
                 use = (d_mask || macs < 4.0e6) ? MCL_ALGO_SIMT : MCL_ALGO_TENSOR;
             }
-            if (use == MCL_ALGO_TENSOR && !m->ext_ok) use = MCL_ALGO_TENSOR_V1;  // norm range too wide for the K extension
+            if (use == MCL_ALGO_TENSOR_V2 && !m->ext_ok) use = MCL_ALGO_TENSOR_V1;  // norm range too wide for the K extension
             if (use == MCL_ALGO_TENSOR) {
+                int rc = launch_sift_tc3(m, q, ratio, d_counts, st);
+                if (rc) return rc;
+            } else if (use == MCL_ALGO_TENSOR_V2) {
                 int rc = launch_sift_tc2(m, q, ratio, d_counts, st);
                 if (rc) return rc;
             } else if (use == MCL_ALGO_TENSOR_V1) {
@@ -872,14 +1000,16 @@ extern "C" int mcl_match_counts_device(mcl_map* m, mcl_queries* q, int mode, dou
 }
 
 namespace {
-// Host batch of SIFT frames, large enough to be worth pipelining: the frames are cut into up to 8 parts; part p+1 is
+// Host batch of SIFT frames, large enough to be worth pipelining: the frames are cut into 2-3 parts of growing size; part p+1 is
 // copied (H2D) and ingested on the copy stream while part p is matched on the main stream.  Returns 1 if the batch is
 // too small (caller takes the plain path).
 int match_counts_sift_pipelined(mcl_map* m, int n_queries, const int64_t* offs, const void* q_desc, int q_dtype, int mode,
                                 double ratio, const uint8_t* mask, int32_t fill_value, int algo, int32_t* out_counts) {
     mcl_ctx* c = m->ctx;
     const int64_t total_rows = offs[n_queries];
-    int P = (int)std::min<int64_t>(8, total_rows / 32768);
+    // Two or three parts with growing sizes (1/16, 3/16, 3/4 of the rows): only the first, small part's copy is exposed;
+    // the later, large parts keep the tensor-core launches long (short launches lose a few % to tails and A reloads).
+    int P = total_rows >= 8 * 32768 ? 3 : (total_rows >= 2 * 32768 ? 2 : 1);
     P = std::min(P, n_queries);
     if (P <= 1 || m->n_images == 0) return 1;
     CU(cudaSetDevice(c->device));
@@ -889,13 +1019,15 @@ int match_counts_sift_pipelined(mcl_map* m, int n_queries, const int64_t* offs, 
         CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         c->part_events.push_back(e);
     }
-    // frame ranges with about equal rows
     std::vector<int> fb(P + 1, n_queries);
     fb[0] = 0;
-    for (int p = 1, f = 0; p < P; ++p) {
-        const int64_t target = total_rows * p / P;
-        while (f < n_queries && offs[f] < target) ++f;
-        fb[p] = std::max(f, fb[p - 1]);
+    {
+        const double cut3[2] = {1.0 / 16, 4.0 / 16}, cut2[1] = {1.0 / 8};
+        for (int p = 1, f = 0; p < P; ++p) {
+            const int64_t target = (int64_t)((P == 3 ? cut3[p - 1] : cut2[p - 1]) * (double)total_rows);
+            while (f < n_queries && offs[f] < target) ++f;
+            fb[p] = std::max(f, fb[p - 1]);
+        }
     }
     const size_t row_b = q_dtype == MCL_F32 ? 512 : 128;
     const int ni = m->n_images;
@@ -1261,6 +1393,23 @@ extern "C" int mcl_microbench(mcl_ctx* c, int which, int iters, double* out /* [
         mcl::popc_peak_kernel<<<c->sm_count * 8, 256, 0, st>>>(iters, c->stage.as<int>());
         CU(cudaEventRecord(b, st));
         ops = 16.0 * (double)iters * 256.0 * c->sm_count * 8;  // popc32 results
+    } else if (which >= 50 && which < 60) {  // development probe: integer-pipe issue rates, which = 50 + OP
+        void (*k)(int, int*) = nullptr;
+        switch (which - 50) {
+            case 0: k = mcl::alu_probe_kernel<0>; break;
+            case 1: k = mcl::alu_probe_kernel<1>; break;
+            case 2: k = mcl::alu_probe_kernel<2>; break;
+            case 3: k = mcl::alu_probe_kernel<3>; break;
+            case 4: k = mcl::alu_probe_kernel<4>; break;
+            case 5: k = mcl::alu_probe_kernel<5>; break;
+            case 6: k = mcl::alu_probe_kernel<6>; break;
+            default: return fail(MCL_EINVAL, "mcl_microbench: unknown probe variant");
+        }
+        k<<<c->sm_count * 8, 256, 0, st>>>(iters / 8 + 1, c->stage.as<int>());
+        CU(cudaEventRecord(a, st));
+        k<<<c->sm_count * 8, 256, 0, st>>>(iters, c->stage.as<int>());
+        CU(cudaEventRecord(b, st));
+        ops = 16.0 * (double)iters * 256.0 * c->sm_count * 8;
     } else if (which >= 100) {  // development probe: which = 100 + n/64 (1,2,4) + 10*ts + 100*ext
         const int w = which - 100;
         const int n = (w % 10) * 64, ts = (w / 10) % 10, ext = (w / 100) % 10;

@@ -105,6 +105,41 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int iters, int* __res
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// integer-pipe issue-rate probe: 16 independent chains per thread, one op of the selected kind per chain per iteration.
+// OP: 0 = max3 (VIMNMX3), 1 = max (VIMNMX), 2 = add3 (IADD3), 3 = mad (IMAD), 4 = fmaxf (FMNMX), 5 = max3 + mad interleaved,
+// 6 = 16-bit packed max (VIMNMX.S16x2 via __vmaxs2)
+template <int OP>
+__global__ void __launch_bounds__(256) alu_probe_kernel(int iters, int* __restrict__ sink) {
+    int x[16], y[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        x[i] = threadIdx.x * 2654435 + i * 40503 + blockIdx.x;
+        y[i] = x[i] ^ 0x5bd1e995;
+    }
+    int z = threadIdx.x ^ 0x9e3779b9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (OP == 0) x[i] = max3(x[i], y[i], z);
+            if (OP == 1) x[i] = max(x[i], y[i] + 0 * z);
+            if (OP == 2) x[i] = x[i] + y[i] + z;
+            if (OP == 3) x[i] = x[i] * z + y[i];
+            if (OP == 4) x[i] = __float_as_int(fmaxf(__int_as_float(x[i]), __int_as_float(y[i])));
+            if (OP == 5) { x[i] = max3(x[i], y[i], z); y[i] = y[i] * z + x[(i + 1) & 15]; }
+            if (OP == 6) x[i] = (int)__vmaxs2((unsigned)x[i], (unsigned)y[i]);
+        }
+        z += 0x7f4a7c15;
+        if (OP == 1 || OP == 4 || OP == 6) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] ^= z;   // keeps the max from being hoisted; one extra LOP3 per op
+        }
+    }
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i] ^ y[i];
+    if (s == 0x7fffffff) sink[0] = s;
+}
+
 // XOR + popc.b32: 16 independent results per iteration per thread
 __global__ void __launch_bounds__(256) popc_peak_kernel(int iters, int* __restrict__ sink) {
     unsigned x[16];

@@ -22,25 +22,29 @@ __device__ __forceinline__ int find_segment(const int64_t* __restrict__ off, int
 //   norm     : |d|^2 per destination row (pad rows stay -1)
 //   seg_of   : segment id per destination row (pad rows stay -1)
 //   bad      : set to 1 if a float value is not an integer in [0,255]
+//   perm     : optional; position k of the concatenated rows takes source row perm[k] (rows of a map image are
+//              stored sorted by norm, see sift_tc3.cuh; a permutation inside each segment)
 template <bool SRC_F32>
 __global__ void prep_rows128_kernel(const void* __restrict__ src, int64_t n_rows, const int64_t* __restrict__ src_off,
                                     const int64_t* __restrict__ dst_off, int n_seg, uint8_t* __restrict__ dst,
-                                    int32_t* __restrict__ norm, int32_t* __restrict__ seg_of, int* __restrict__ bad) {
+                                    int32_t* __restrict__ norm, int32_t* __restrict__ seg_of, int* __restrict__ bad,
+                                    const int32_t* __restrict__ perm) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t row = warp; row < n_rows; row += n_warps) {
         uint32_t b0, b1, b2, b3;
         bool ok = true;
+        const int64_t srow = perm ? (int64_t)perm[row] : row;
         if (SRC_F32) {
-            const float4 f = reinterpret_cast<const float4*>(src)[row * 32 + lane];
+            const float4 f = reinterpret_cast<const float4*>(src)[srow * 32 + lane];
             const float r0 = rintf(f.x), r1 = rintf(f.y), r2 = rintf(f.z), r3 = rintf(f.w);
             ok = (r0 == f.x) && (r1 == f.y) && (r2 == f.z) && (r3 == f.w) && f.x >= 0.f && f.x <= 255.f &&
                  f.y >= 0.f && f.y <= 255.f && f.z >= 0.f && f.z <= 255.f && f.w >= 0.f && f.w <= 255.f;
             b0 = (uint32_t)(int)r0 & 255u; b1 = (uint32_t)(int)r1 & 255u;
             b2 = (uint32_t)(int)r2 & 255u; b3 = (uint32_t)(int)r3 & 255u;
         } else {
-            const uchar4 u = reinterpret_cast<const uchar4*>(src)[row * 32 + lane];
+            const uchar4 u = reinterpret_cast<const uchar4*>(src)[srow * 32 + lane];
             b0 = u.x; b1 = u.y; b2 = u.z; b3 = u.w;
         }
         if (!ok) *bad = 1;
