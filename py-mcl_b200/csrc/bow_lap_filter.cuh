@@ -14,7 +14,9 @@ constexpr int VQ_WORDS = 64;
 
 __global__ void __launch_bounds__(128) bow_vq_kernel(
     const float4* __restrict__ q_desc /* (n_q,128) f32 */, int n_q, const float4* __restrict__ voc,
-    const int64_t* __restrict__ voc_off /* rows, n_loc+1 */, unsigned long long* __restrict__ best /* [n_loc][n_q] */) {
+    const int64_t* __restrict__ voc_off /* rows, n_loc+1 */, const int* __restrict__ only_if /* optional device flag */,
+    unsigned long long* __restrict__ best /* [n_loc][n_q] */) {
+    if (only_if && *only_if == 0) return;
     const int loc = blockIdx.z;
     const int64_t v0 = voc_off[loc];
     const int n_words = (int)(voc_off[loc + 1] - v0);

@@ -1,0 +1,347 @@
+// BOW visual-word assignment on tensor cores.
+//
+//   replaces: words, distance = vq(query_descriptors, voc)   (Matcher.py:250, scipy.cluster.vq.vq)
+//
+// words[i] = argmin_j ||o_i - c_j||^2 = argmax_j (2 o_i.c_j - |c_j|^2), o = SIFT rows (integer valued 0..255), c = k-means
+// centroids (float32, NOT integer valued).  The codebook is quantised to 16-bit fixed point g = rint(256 c)
+// and split into two u8 planes, g = 256 hi + lo, so that o.g = 256 (o.hi) + (o.lo) is two u8 x u8 -> s32 tensor-core
+// contractions (tcgen05.mma kind::i8) into two accumulators.  The epilogue forms T = 2 (256 P_hi + P_lo) - rint(256 |c|^2)
+// (the key in units of 1/256), and keeps per query row the best T, its word and the second-best T.
+// |256 key - T| <= sum_k o_k + 1/2, so when best - second > 2 (sum_k o_k + 1) the approximate argmax IS the exact argmin
+// (and is far from any float32 tie); otherwise (about a percent of the rows, and every exact tie) bow_resolve_kernel
+// rescans that row over the whole codebook in float32 direct-difference form with lowest-index tie-breaking, exactly
+// like the SIMT kernel.  Words are therefore identical to the SIMT path's.
+//
+// Work item = (location, block of 128 query rows); one CTA per item, persistent grid.  Warps 0-3 epilogue (TMEM lane
+// quadrants), warp 4 TMA producer, warp 5 MMA issuer.  TMEM: 2 stages x (hi, lo) x 128 columns.
+#pragma once
+#include "common.cuh"
+
+namespace mcl {
+namespace bowtc {
+
+constexpr int TILE_N = 128;                 // words per tile
+constexpr int QTILE = 128;                  // query rows per item
+constexpr int PLANE_BYTES = TILE_N * 128;   // 16 KB
+constexpr int TILE_BYTES = 2 * PLANE_BYTES + TILE_N * 4;   // hi plane | lo plane | nb[128]
+constexpr int STAGE_BYTES = 33792;          // 32 KB + 512 B, rounded to 1 KB
+constexpr int B_STAGES = 4;
+constexpr int ACC_STAGES = 2;
+constexpr int EPI_WARPS = 4;
+constexpr int THREADS = (EPI_WARPS + 2) * 32;
+constexpr int TMEM_COLS = 512;
+constexpr int NB_PAD = 1 << 30;             // nb of a padding word: its key can never win
+
+struct Smem {
+    alignas(1024) uint8_t a[QTILE * 128];
+    alignas(1024) uint8_t stage[B_STAGES][STAGE_BYTES];
+    alignas(8) uint64_t a_full, a_empty;
+    uint64_t b_full[B_STAGES], b_empty[B_STAGES];
+    uint64_t acc_full[ACC_STAGES], acc_empty[ACC_STAGES];
+    uint32_t tmem_base;
+};
+
+struct Params {
+    const uint8_t* q_desc;      // SW128 atoms, n_qtiles*128 rows
+    const uint8_t* tiles;       // per tile: TILE_BYTES (hi | lo | nb), 16-byte aligned records of STAGE_BYTES stride
+    const int32_t* tile_off;    // n_loc+1: first tile of each location
+    int n_loc, n_qtiles, n_q;
+    int n_splits;               // each location's tiles are cut into n_splits contiguous ranges (more work items)
+    int4* out;                  // [n_splits][n_loc][n_q]: {best word, best T, second T, -}
+};
+
+// codebook -> planes (built once per index).  One warp per word row; lane l owns dims 4l..4l+3.
+__global__ void build_planes_kernel(const float* __restrict__ voc, const int64_t* __restrict__ voc_off, int n_loc,
+                                    const int32_t* __restrict__ tile_off, uint8_t* __restrict__ tiles, int* __restrict__ bad) {
+    const int lane = threadIdx.x & 31;
+    const int wtile = blockIdx.x;           // global tile index
+    // find the location of this tile
+    int loc = 0;
+    while (loc + 1 < n_loc && tile_off[loc + 1] <= wtile) ++loc;
+    const int64_t v0 = voc_off[loc];
+    const int n_words = (int)(voc_off[loc + 1] - v0);
+    const int w0 = (wtile - tile_off[loc]) * TILE_N;
+    uint8_t* rec = tiles + (size_t)wtile * STAGE_BYTES;
+    for (int r = threadIdx.x >> 5; r < TILE_N; r += blockDim.x >> 5) {
+        const int w = w0 + r;
+        uint32_t hi = 0, lo = 0;
+        double nn = 0.0;
+        bool ok = true;
+        if (w < n_words) {
+            const float4 c = reinterpret_cast<const float4*>(voc + (v0 + w) * 128)[lane];
+            const float cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float g = rintf(cc[k] * 256.0f);
+                ok = ok && (g >= 0.0f) && (g <= 65535.0f);
+                const uint32_t gi = (uint32_t)(int)fminf(fmaxf(g, 0.0f), 65535.0f);
+                hi |= (gi >> 8) << (8 * k);
+                lo |= (gi & 255u) << (8 * k);
+                nn += (double)cc[k] * (double)cc[k];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+        if (!ok) *bad = 1;
+        *reinterpret_cast<uint32_t*>(rec + sw128_chunk_offset(r, lane >> 2) + (lane & 3) * 4) = hi;
+        *reinterpret_cast<uint32_t*>(rec + PLANE_BYTES + sw128_chunk_offset(r, lane >> 2) + (lane & 3) * 4) = lo;
+        if (lane == 0) {
+            int nb = NB_PAD;
+            if (w < n_words) {
+                const double x = rint(nn * 256.0);
+                if (x >= (double)(1 << 28)) { *bad = 1; } else { nb = (int)x; }
+            }
+            reinterpret_cast<int32_t*>(rec + 2 * PLANE_BYTES)[r] = nb;
+        }
+    }
+}
+
+// keys of 32 columns: T = 512 P_hi + 2 P_lo - nb
+__device__ __forceinline__ void keys32(const uint32_t (&h)[32], const uint32_t (&l)[32], const int32_t* __restrict__ nb, int (&k)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        const int4 c = *reinterpret_cast<const int4*>(nb + i);
+        k[i] = (int)h[i] * 512 + ((int)l[i] * 2 - c.x);
+        k[i + 1] = (int)h[i + 1] * 512 + ((int)l[i + 1] * 2 - c.y);
+        k[i + 2] = (int)h[i + 2] * 512 + ((int)l[i + 2] * 2 - c.z);
+        k[i + 3] = (int)h[i + 3] * 512 + ((int)l[i + 3] * 2 - c.w);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+    const int warp = warp_id_uniform();
+    const int lane = threadIdx.x & 31;
+    const uint32_t leader = lane == 0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&s.a_full, 1);
+        mbar_init(&s.a_empty, 1);
+        for (int i = 0; i < B_STAGES; ++i) { mbar_init(&s.b_full[i], 1); mbar_init(&s.b_empty[i], 1 + EPI_WARPS); }
+        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&s.acc_full[i], 1); mbar_init(&s.acc_empty[i], EPI_WARPS); }
+        mbar_fence_init();
+    }
+    if (warp == EPI_WARPS + 1) tmem_alloc<TMEM_COLS>(&s.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_base;
+    const int n_items = p.n_splits * p.n_loc * p.n_qtiles;
+    // item -> (split, location, query tile) and the split's tile range
+    auto decode = [&](int item, int& sp, int& loc, int& qt, int& tb, int& te, int& t0) {
+        qt = item % p.n_qtiles;
+        loc = (item / p.n_qtiles) % p.n_loc;
+        sp = item / (p.n_qtiles * p.n_loc);
+        t0 = p.tile_off[loc];
+        const int nt = p.tile_off[loc + 1] - t0;
+        const int per = (nt + p.n_splits - 1) / p.n_splits;
+        tb = t0 + min(nt, sp * per);
+        te = t0 + min(nt, (sp + 1) * per);
+    };
+
+    if (warp == EPI_WARPS) {
+        // ================= TMA producer =================
+        uint32_t bn = 0, item_n = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+            int sp, loc, qt, tb, te, t0;
+            decode(item, sp, loc, qt, tb, te, t0);
+            mbar_wait(&s.a_empty, (item_n & 1) ^ 1);
+            mbar_arrive_expect_tx_if(leader, &s.a_full, QTILE * 128);
+            bulk_g2s_if(leader, s.a, p.q_desc + (size_t)qt * QTILE * 128, QTILE * 128, &s.a_full);
+            for (int t = tb; t < te; ++t, ++bn) {
+                const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
+                mbar_wait(&s.b_empty[bs], bph ^ 1);
+                mbar_arrive_expect_tx_if(leader, &s.b_full[bs], TILE_BYTES);
+                bulk_g2s_if(leader, s.stage[bs], p.tiles + (size_t)t * STAGE_BYTES, TILE_BYTES, &s.b_full[bs]);
+            }
+        }
+    } else if (warp == EPI_WARPS + 1) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = umma_idesc(/*c=S32*/ 2, /*a=u8*/ 0, /*b=u8*/ 0, QTILE, TILE_N);
+        const uint64_t a_desc = umma_desc_sw128(smem_u32(s.a));
+        uint32_t bn = 0, item_n = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+            int sp, loc, qt, tb, te, t0;
+            decode(item, sp, loc, qt, tb, te, t0);
+            mbar_wait(&s.a_full, item_n & 1);
+            for (int t = tb; t < te; ++t, ++bn) {
+                const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
+                const uint32_t as = bn % ACC_STAGES, aph = (bn / ACC_STAGES) & 1;
+                mbar_wait(&s.b_full[bs], bph);
+                mbar_wait(&s.acc_empty[as], aph ^ 1);
+                tc_fence_after();
+                const uint64_t hi_desc = umma_desc_sw128(smem_u32(s.stage[bs]));
+                const uint64_t lo_desc = umma_desc_sw128(smem_u32(s.stage[bs] + PLANE_BYTES));
+                const uint32_t d = tmem_base + as * (2 * TILE_N);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_i8_if(leader, d, a_desc + 2 * k, hi_desc + 2 * k, idesc, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_i8_if(leader, d + TILE_N, a_desc + 2 * k, lo_desc + 2 * k, idesc, k > 0);
+                tc_commit_if(leader, &s.b_empty[bs]);
+                tc_commit_if(leader, &s.acc_full[as]);
+                __syncwarp();
+            }
+            tc_commit_if(leader, &s.a_empty);
+            __syncwarp();
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int lane_base = warp * 32;
+        const uint32_t t_lane = tmem_base + ((uint32_t)lane_base << 16);
+        uint32_t bn = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int sp, loc, qt, tb, te, t0;
+            decode(item, sp, loc, qt, tb, te, t0);
+            const int row = qt * QTILE + lane_base + lane;
+            int b1 = INT_MIN, b2 = INT_MIN, idx = 0;
+            for (int t = tb; t < te; ++t, ++bn) {
+                const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
+                const uint32_t as = bn % ACC_STAGES, aph = (bn / ACC_STAGES) & 1;
+                mbar_wait(&s.acc_full[as], aph);
+                tc_fence_after();
+                mbar_wait(&s.b_full[bs], bph);   // complete already; orders the read of nb[]
+                const int32_t* nb = reinterpret_cast<const int32_t*>(s.stage[bs] + 2 * PLANE_BYTES);
+                const uint32_t tcol = t_lane + as * (2 * TILE_N);
+#pragma unroll 1
+                for (int g = 0; g < TILE_N / 32; ++g) {
+                    uint32_t h[32], l[32];
+                    tmem_ld32(tcol + g * 32, h);
+                    tmem_ld32(tcol + TILE_N + g * 32, l);
+                    tmem_wait_all();
+                    tmem_fence_regs(h);
+                    tmem_fence_regs(l);
+                    int k[32];
+                    keys32(h, l, nb + g * 32, k);
+                    int m[11];
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) m[i] = max3(k[3 * i], k[3 * i + 1], k[3 * i + 2]);
+                    m[10] = max(k[30], k[31]);
+                    const int gm = max3(max3(max3(m[0], m[1], m[2]), max3(m[3], m[4], m[5]), max3(m[6], m[7], m[8])), m[9], m[10]);
+                    if (gm > b1) {
+                        // new best inside this group: find its (first) column and the group's second best
+                        int gi = 0, sec = INT_MIN;
+                        bool seen = false;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const bool is = (k[i] == gm) && !seen;
+                            gi = is ? i : gi;
+                            sec = is ? sec : max(sec, k[i]);
+                            seen = seen || is;
+                        }
+                        b2 = max(b1, sec);
+                        b1 = gm;
+                        idx = (t - t0) * TILE_N + g * 32 + gi;
+                    } else {
+                        b2 = max(b2, gm);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&s.acc_empty[as]);
+                    mbar_arrive(&s.b_empty[bs]);
+                }
+            }
+            if (row < p.n_q) p.out[((size_t)sp * p.n_loc + loc) * p.n_q + row] = make_int4(idx, b1, b2, 0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == EPI_WARPS + 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---- resolve ---------------------------------------------------------------------------------------------------
+// Pass 1 (one warp per (location, row)): merge the splits' (best, second), accept the tensor-core argmax when its lead
+// exceeds the quantisation bound 2 (sum_k o_k + 1), else queue the row for an exact float32 rescan.
+// state: [0] = queued rows, [1] = run-the-SIMT-kernel flag (written by bow_decide_kernel), [2] = rows rescanned (statistics)
+__global__ void __launch_bounds__(256) bow_accept_kernel(const int4* __restrict__ tc, int n_splits, const float* __restrict__ q_desc,
+                                                         int n_q, int n_loc, const int* __restrict__ bad,
+                                                         unsigned long long* __restrict__ best, int* __restrict__ queue,
+                                                         unsigned int* __restrict__ state) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_w = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_jobs = (int64_t)n_loc * n_q;
+    const bool all_bad = *bad != 0;   // non-integer query rows: nothing from the tensor-core pass can be trusted
+    for (int64_t job = wid; job < n_jobs; job += n_w) {
+        const int row = (int)(job % n_q);
+        const float4 o = reinterpret_cast<const float4*>(q_desc + (size_t)row * 128)[lane];
+        float sum = o.x + o.y + o.z + o.w;   // integer valued: exact
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, k);
+        int b1 = INT_MIN, b2 = INT_MIN, idx = 0;
+        for (int sp = 0; sp < n_splits; ++sp) {
+            const int4 r = tc[(size_t)sp * n_jobs + job];
+            if (r.y > b1) { b2 = max(b1, r.z); b1 = r.y; idx = r.x; }
+            else { b2 = max(b2, r.y); }
+        }
+        const long long lead = (long long)b1 - (long long)b2;
+        const bool accept = !all_bad && (b2 == INT_MIN || lead > 2LL * ((long long)sum + 1));   // a single word cannot tie
+        if (lane == 0) {
+            if (accept) best[job] = (unsigned long long)(unsigned)idx;
+            else queue[atomicAdd(&state[0], 1u)] = (int)job;
+        }
+    }
+}
+
+// many ambiguous rows (random-like data) -> one pass of the float32 SIMT kernel is cheaper than row-by-row rescans
+__global__ void bow_decide_kernel(const int* __restrict__ bad, int64_t n_jobs, unsigned int* __restrict__ state) {
+    const unsigned int thr = (unsigned int)max((int64_t)64, n_jobs / 16);
+    state[1] = (*bad != 0 || state[0] > thr) ? 1u : 0u;
+}
+
+// Pass 2 (one CTA per queued row, 8 warps striding over the words, 4 words in flight per warp): exact float32
+// direct-difference scan of the location's codebook, lowest index on ties.
+// best[] gets (distance bits << 32 | word) like bow_vq_kernel's atomicMin key.
+__global__ void __launch_bounds__(256) bow_rescan_kernel(const int* __restrict__ queue, const float* __restrict__ q_desc, int n_q,
+                                                         const float* __restrict__ voc, const int64_t* __restrict__ voc_off,
+                                                         unsigned long long* __restrict__ best, unsigned int* __restrict__ state) {
+    if (state[1] != 0) return;
+    __shared__ unsigned long long part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned n = state[0];
+    for (unsigned c = blockIdx.x; c < n; c += gridDim.x) {
+        const int job = queue[c];
+        const int loc = job / n_q, row = job % n_q;
+        const float4 o = reinterpret_cast<const float4*>(q_desc + (size_t)row * 128)[lane];
+        const int64_t v0 = voc_off[loc];
+        const int n_words = (int)(voc_off[loc + 1] - v0);
+        unsigned long long bk = ~0ULL;
+        for (int w0 = warp * 4; w0 < n_words; w0 += 32) {
+            float d[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int w = min(w0 + j, n_words - 1);
+                const float4 cc = reinterpret_cast<const float4*>(voc + (v0 + w) * 128)[lane];
+                const float dx = o.x - cc.x, dy = o.y - cc.y, dz = o.z - cc.z, dw = o.w - cc.w;
+                d[j] = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+            }
+#pragma unroll
+            for (int k = 16; k > 0; k >>= 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[j] += __shfl_xor_sync(0xffffffffu, d[j], k);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (w0 + j < n_words) {
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(d[j]) << 32) | (unsigned)(w0 + j);
+                    bk = key < bk ? key : bk;
+                }
+            }
+        }
+        if (lane == 0) part[warp] = bk;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long m = part[0];
+            for (int k = 1; k < 8; ++k) m = part[k] < m ? part[k] : m;
+            best[job] = m;
+            atomicAdd(&state[2], 1u);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace bowtc
+}  // namespace mcl

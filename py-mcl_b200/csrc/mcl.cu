@@ -20,6 +20,7 @@
 #include "sift_tc3.cuh"
 #include "simt_match.cuh"
 #include "bow_lap_filter.cuh"
+#include "bow_tc.cuh"
 #include "microbench.cuh"
 
 namespace {
@@ -43,7 +44,7 @@ int fail(int code, const char* fmt, ...) {
             return fail(MCL_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-enum { PROF_SIFT_TC = 0, PROF_SIFT_FIX, PROF_ORB, PROF_SURF, PROF_VQ, PROF_SCORE, PROF_LAP, PROF_PREP, PROF_SIFT_SIMT, PROF_N };
+enum { PROF_SIFT_TC = 0, PROF_SIFT_FIX, PROF_ORB, PROF_SURF, PROF_VQ, PROF_SCORE, PROF_LAP, PROF_PREP, PROF_SIFT_SIMT, PROF_VQ_TC, PROF_VQ_RESOLVE, PROF_N };
 constexpr int QROW_PAD = 768;  // lcm of the two tensor-core kernels' query blocks (256, 384)
 
 // growable device scratch buffer (never shrinks; avoids cudaMalloc on the per-frame path)
@@ -84,7 +85,8 @@ struct mcl_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[PROF_N];
     // scratch
     DevBuf stage, cand, flags /* [0]=cand_count [1]=overflow [2]=bad [3]=rescans [4]=norm min [5]=norm max */, row_arg, bow_best, lap_pix, lap_meta, filt, tmp_counts,
-        tmp_mask, tmp_words, tmp_scores, tq_off, tq_desc, tq_norm, tq_frame;
+        tmp_mask, tmp_words, tmp_scores, tq_off, tq_desc, tq_norm, tq_frame, bow_q8, bow_qaux, bow_tc_out;
+    bool bowtc_attr = false;
     size_t cand_cap_entries = 0;
     bool tc_attr_set = false, tc2_attr_set = false;
     int opt[8] = {0};  // mcl_set_option: [0] = sift_tc diagnostic mode
@@ -136,6 +138,11 @@ struct mcl_bow {
     int64_t total_images = 0, voc_rows = 0;
     int max_words = 0;
     std::vector<int64_t> h_voc_off, h_img_off;
+    // tensor-core word assignment (bow_tc.cuh): codebook planes per 128-word tile
+    std::vector<int32_t> h_tile_off;
+    int32_t* d_tile_off = nullptr;
+    uint8_t* d_tiles = nullptr;
+    bool tc_ok = false;
     float* d_voc = nullptr;
     float* d_idf = nullptr;
     float* d_imf = nullptr;
@@ -302,7 +309,7 @@ extern "C" void mcl_shutdown(mcl_ctx* c) {
         for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     DevBuf* bufs[] = {&c->stage, &c->cand, &c->flags, &c->row_arg, &c->bow_best, &c->lap_pix, &c->lap_meta, &c->filt,
                       &c->tmp_counts, &c->tmp_mask, &c->tmp_words, &c->tmp_scores, &c->tq_off, &c->tq_desc, &c->tq_norm,
-                      &c->tq_frame};
+                      &c->tq_frame, &c->bow_q8, &c->bow_qaux, &c->bow_tc_out};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->part_events) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -1145,6 +1152,8 @@ extern "C" void mcl_bow_destroy(mcl_bow* b) {
     cudaFree(b->d_imf);
     cudaFree(b->d_voc_off);
     cudaFree(b->d_img_off);
+    cudaFree(b->d_tile_off);
+    cudaFree(b->d_tiles);
     delete b;
 }
 
@@ -1196,6 +1205,30 @@ extern "C" int mcl_bow_create(mcl_ctx* c, int n_locations, const int64_t* voc_ro
     BCU(cudaMemcpyAsync(b->d_voc_off, b->h_voc_off.data(), (size_t)(n_locations + 1) * 8, cudaMemcpyHostToDevice, st));
     BCU(cudaMemcpyAsync(b->d_img_off, b->h_img_off.data(), (size_t)(n_locations + 1) * 8, cudaMemcpyHostToDevice, st));
     BCU(cudaFuncSetAttribute(mcl::bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W * 12));
+    // codebook planes for the tensor-core word assignment
+    {
+        b->h_tile_off.resize(n_locations + 1);
+        int32_t acc = 0;
+        for (int l = 0; l < n_locations; ++l) {
+            b->h_tile_off[l] = acc;
+            acc += (int32_t)((voc_row_offsets[l + 1] - voc_row_offsets[l] + mcl::bowtc::TILE_N - 1) / mcl::bowtc::TILE_N);
+        }
+        b->h_tile_off[n_locations] = acc;
+        BCU(cudaMalloc(&b->d_tile_off, (size_t)(n_locations + 1) * 4));
+        BCU(cudaMemcpyAsync(b->d_tile_off, b->h_tile_off.data(), (size_t)(n_locations + 1) * 4, cudaMemcpyHostToDevice, st));
+        BCU(cudaMalloc(&b->d_tiles, (size_t)acc * mcl::bowtc::STAGE_BYTES));
+        int* bad = c->flags.as<int>() + 6;
+        BCU(cudaMemsetAsync(bad, 0, 4, st));
+        {
+            ProfScope ps(c, PROF_PREP, st);
+            mcl::bowtc::build_planes_kernel<<<acc, 256, 0, st>>>(b->d_voc, b->d_voc_off, n_locations, b->d_tile_off, b->d_tiles, bad);
+        }
+        BCU(cudaGetLastError());
+        int h_bad = 0;
+        BCU(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
+        BCU(cudaStreamSynchronize(st));
+        b->tc_ok = h_bad == 0;   // centroids outside [0, 256) or huge norms: the SIMT kernel is used instead
+    }
     BCU(cudaStreamSynchronize(st));
 #undef BCU
     *out = b;
@@ -1217,10 +1250,71 @@ extern "C" int mcl_bow_score_device(mcl_bow* b, mcl_queries* q, int32_t* d_words
     CU(c->bow_best.ensure(nbest * 8));
     CU(cudaMemsetAsync(c->bow_best.p, 0xFF, nbest * 8, st));
     if (n_q > 0) {
+        const int* only_if = nullptr;
+        if (b->tc_ok && c->opt[2] != 1) {
+            // ---- tensor cores: u8 copy of the query rows in the SW128 image, two-plane contraction, float32 resolve
+            using namespace mcl::bowtc;
+            const int n_qtiles = (n_q + QTILE - 1) / QTILE;
+            const int64_t padded = (int64_t)n_qtiles * QTILE;
+            CU(c->bow_q8.ensure((size_t)padded * 128));
+            CU(c->bow_qaux.ensure((size_t)padded * 8 + 64));
+            const int n_qt = n_qtiles;
+            int n_splits = (2 * c->sm_count + b->n_loc * n_qt - 1) / (b->n_loc * n_qt);
+            n_splits = std::max(1, std::min(n_splits, 8));
+            CU(c->bow_tc_out.ensure((size_t)n_splits * nbest * sizeof(int4) + nbest * 4));
+            int* queue = reinterpret_cast<int*>(c->bow_tc_out.as<int4>() + (size_t)n_splits * nbest);
+            int32_t* q_norm = c->bow_qaux.as<int32_t>();
+            int32_t* q_seg = q_norm + padded;
+            int64_t* q_off = reinterpret_cast<int64_t*>(q_seg + padded);
+            const int64_t h_off[2] = {0, n_q};
+            CU(cudaMemcpyAsync(q_off, h_off, 16, cudaMemcpyHostToDevice, st));
+            CU(cudaMemsetAsync(c->bow_q8.p, 0, (size_t)padded * 128, st));
+            int* bad = c->flags.as<int>() + 6;
+            unsigned int* state = c->flags.as<unsigned int>() + 8;   // [8] queued rows, [9] SIMT flag, [10] rescans
+            CU(cudaMemsetAsync(bad, 0, 4, st));
+            CU(cudaMemsetAsync(state, 0, 8, st));
+            {
+                ProfScope ps(c, PROF_PREP, st);
+                mcl::prep_rows128_kernel<true><<<grid_for((int64_t)n_q * 32, 256, c->sm_count * 8), 256, 0, st>>>(
+                    q->d_desc, n_q, q_off, q_off, 1, c->bow_q8.as<uint8_t>(), q_norm, q_seg, bad, nullptr);
+            }
+            CU(cudaGetLastError());
+            const size_t smem = sizeof(Smem);
+            if (!c->bowtc_attr) {
+                CU(cudaFuncSetAttribute(bow_vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                c->bowtc_attr = true;
+            }
+            Params p;
+            p.q_desc = c->bow_q8.as<uint8_t>();
+            p.tiles = b->d_tiles;
+            p.tile_off = b->d_tile_off;
+            p.n_loc = b->n_loc;
+            p.n_qtiles = n_qtiles;
+            p.n_q = n_q;
+            p.n_splits = n_splits;
+            p.out = c->bow_tc_out.as<int4>();
+            const int n_items = n_splits * b->n_loc * n_qtiles;
+            {
+                ProfScope ps(c, PROF_VQ_TC, st);
+                bow_vq_tc_kernel<<<std::min(n_items, c->sm_count), THREADS, smem, st>>>(p);
+            }
+            CU(cudaGetLastError());
+            {
+                ProfScope ps(c, PROF_VQ_RESOLVE, st);
+                bow_accept_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->bow_tc_out.as<int4>(), n_splits, (const float*)q->d_desc, n_q,
+                                                                  b->n_loc, bad, c->bow_best.as<unsigned long long>(), queue, state);
+                bow_decide_kernel<<<1, 1, 0, st>>>(bad, (int64_t)nbest, state);
+                bow_rescan_kernel<<<c->sm_count * 8, 256, 0, st>>>(queue, (const float*)q->d_desc, n_q, b->d_voc, b->d_voc_off,
+                                                                  c->bow_best.as<unsigned long long>(), state);
+            }
+            c->launches += 2;
+            CU(cudaGetLastError());
+            only_if = reinterpret_cast<const int*>(state + 1);   // many ambiguous rows or non-integer queries: float32 SIMT pass
+        }
         dim3 grid((b->max_words + mcl::VQ_WORDS - 1) / mcl::VQ_WORDS, (n_q + 127) / 128, b->n_loc);
         if (grid.y > 65535 || grid.z > 65535) return fail(MCL_EINVAL, "bow batch too large");
         ProfScope ps(c, PROF_VQ, st);
-        mcl::bow_vq_kernel<<<grid, 128, 0, st>>>((const float4*)q->d_desc, n_q, (const float4*)b->d_voc, b->d_voc_off,
+        mcl::bow_vq_kernel<<<grid, 128, 0, st>>>((const float4*)q->d_desc, n_q, (const float4*)b->d_voc, b->d_voc_off, only_if,
                                                  c->bow_best.as<unsigned long long>());
     }
     CU(cudaGetLastError());

@@ -109,23 +109,49 @@ if "bow" in names:   # cfg5 scaled: 16 locations x 100 images, W = 10000, Nq = 3
     locs = []
     for l in range(L):
         rng = np.random.default_rng(500 + l)
-        voc = (synth.sift_like(rng, 10000) + rng.normal(0, 0.3, size=(10000, 128))).astype(np.float32)
+        voc = np.clip(synth.sift_like(rng, 10000) + rng.normal(0, 0.3, size=(10000, 128)), 0, 255).astype(np.float32)
         im = rng.random((100, 10000), dtype=np.float32) * (rng.random((100, 10000)) < 0.03)
         im /= np.maximum(np.linalg.norm(im, axis=1, keepdims=True), 1e-9)
         idf = rng.random(10000, dtype=np.float32) + 0.5
         locs.append((im.astype(np.float32), idf, voc))
     bow = _lib.BowIndex(ctx, locs, 10000)
     rng = np.random.default_rng(9)
-    q = synth.sift_like(rng, 300)
-    e2e = timeit(lambda: bow.score([q]), reps=5, warm=2)
-    vq_ms = prof(lambda: bow.score([q]), "bow_vq", reps=5, warm=2)
-    sc_ms = prof(lambda: bow.score([q]), "bow_score", reps=5, warm=2)
+    slots = ("bow_vq_tc", "bow_resolve", "bow_vq", "bow_score")
+
+    def run(q, reps=5, warm=2):
+        for _ in range(warm):
+            bow.score([q])
+        for k in slots:
+            ctx.profile_read(k)
+        ctx.profile_enable(True)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            bow.score([q])
+        ctx.sync()
+        dt = (time.perf_counter() - t0) / reps
+        r = {k: ctx.profile_read(k)[0] / reps for k in slots}
+        ctx.profile_enable(False)
+        r["e2e_ms"] = dt * 1e3
+        return r
+
+    # (a) clustered queries: re-observed codebook-like points (what BoW is used on); (b) random queries (adversarial:
+    # best and second-best distances nearly tie, so most rows take the exact float32 route)
+    q_clu = np.clip(np.rint(locs[3][2][rng.choice(10000, 300)] + rng.normal(0, 6.0, size=(300, 128))), 0, 255).astype(np.float32)
+    q_rnd = synth.sift_like(rng, 300)
     from scipy.cluster.vq import vq
-    cpu = cpu_rate(lambda: oracle.scipy_bow_score(q, locs[0][2], locs[0][1], locs[0][0], 10000), 3.0)
-    out.append({"config": "cfg5 BOW 1 frame x %d locations x 100 images (W=10000, Nq=300)" % L, "e2e_ms": e2e * 1e3,
-                "vq_ms": vq_ms, "score_ms": sc_ms, "vq_tflops_fp32": 3.0 * 300 * 10000 * 128 * L / (vq_ms * 1e-3) / 1e12,
-                "score_GBps": L * 100 * 10000 * 4 / (sc_ms * 1e-3) / 1e9, "locations_per_s_e2e": L / e2e,
-                "cpu_locations_per_s": cpu})
+    cpu = cpu_rate(lambda: oracle.scipy_bow_score(q_clu, locs[0][2], locs[0][1], locs[0][0], 10000), 3.0)
+    for tag, q in (("clustered", q_clu), ("random", q_rnd)):
+        r = run(q)
+        ctx.set_option(2, 1)
+        r_simt = run(q)
+        ctx.set_option(2, 0)
+        out.append({"config": "cfg5 BOW 1 frame x %d locations x 100 images (W=10000, Nq=300), %s queries" % (L, tag),
+                    "e2e_ms": r["e2e_ms"], "vq_tc_ms": r["bow_vq_tc"], "vq_resolve_ms": r["bow_resolve"],
+                    "vq_simt_fallback_ms": r["bow_vq"], "score_ms": r["bow_score"],
+                    "vq_tc_TOPs": 2.0 * 2 * 300 * 10000 * 128 * L / (max(r["bow_vq_tc"], 1e-9) * 1e-3) / 1e12,
+                    "locations_per_s_e2e": L / (r["e2e_ms"] * 1e-3),
+                    "simt_only_e2e_ms": r_simt["e2e_ms"], "simt_only_vq_ms": r_simt["bow_vq"],
+                    "cpu_locations_per_s": cpu})
     bow.close()
 if "laplacian" in names:
     import cv2
