@@ -285,6 +285,63 @@ def test_bow_multi_location_vs_oracle(ctx):
     assert int(np.argmax(scores[0, off1:off1 + len(locs[1][0])])) == 2
 
 
+def test_bow_tensor_core_path_equals_simt_and_oracle(ctx):
+    """Word assignment on tensor cores (two u8 planes of the 16-bit fixed-point codebook + float32 resolve) gives the
+    same words as the float32 SIMT kernel and as the oracle (up to float32 near-ties); non-integer query rows and
+    out-of-range centroids take the SIMT kernel on the device."""
+    W = 640
+    rng = np.random.default_rng(21)
+    locs = []
+    for rows in (640, 500, 129):
+        voc = np.clip(synth.sift_like(rng, rows) + rng.normal(0, 0.4, size=(rows, 128)), 0, 255).astype(np.float32)
+        voc[5] = voc[4]                      # an exact tie between two words: lowest index must win
+        im = rng.random((7, W), dtype=np.float32)
+        im /= np.linalg.norm(im, axis=1, keepdims=True)
+        locs.append((im, (rng.random(W, dtype=np.float32) + 0.5), voc))
+    clustered = np.clip(np.rint(locs[0][2][rng.choice(640, 300)] + rng.normal(0, 5.0, size=(300, 128))), 0, 255).astype(np.float32)
+    clustered[:3] = np.rint(locs[0][2][4])   # rows sitting on the tied pair
+    frames = [clustered, synth.sift_like(rng, 50), synth.sift_like(rng, 1), None]
+    bow = _lib.BowIndex(ctx, locs, W)
+    ctx.profile_enable(True)
+    scores, words = bow.score(frames, want_words=True)
+    _, n_tc = ctx.profile_read("bow_vq_tc")
+    ctx.profile_enable(False)
+    assert n_tc == 1, "the tensor-core kernel did not run"
+    ctx.set_option(2, 1)
+    scores_simt, words_simt = bow.score(frames, want_words=True)
+    ctx.set_option(2, 0)
+    allq = np.vstack([f for f in frames if f is not None])
+    for l, (_, _, voc) in enumerate(locs):
+        ow, gap = oracle.bow_words(allq, voc)
+        for got in (words[l], words_simt[l]):
+            differ = got != ow
+            assert np.all(gap[differ] < 1e-5)
+        same = words[l] == words_simt[l]
+        assert np.all(gap[~same] < 1e-5)
+    assert np.array_equal(words[0][:3], [4, 4, 4])
+    if np.array_equal(words, words_simt):
+        assert np.allclose(scores, scores_simt, rtol=0, atol=1e-7)
+    # non-integer query rows: rejected by the u8 ingest on the device, the SIMT kernel assigns the words
+    frac = [f + 0.25 if f is not None else None for f in frames]
+    s_frac, w_frac = bow.score(frac, want_words=True)
+    ctx.set_option(2, 1)
+    s_ref, w_ref = bow.score(frac, want_words=True)
+    ctx.set_option(2, 0)
+    assert np.array_equal(w_frac, w_ref) and np.array_equal(s_frac, s_ref)
+    bow.close()
+    # a centroid outside [0, 256): no planes are built for this index, SIMT only
+    bad_locs = [(locs[0][0], locs[0][1], locs[0][2] - 3.0)]
+    bow2 = _lib.BowIndex(ctx, bad_locs, W)
+    ctx.profile_enable(True)
+    s2, w2 = bow2.score(frames[:2], want_words=True)
+    _, n_tc = ctx.profile_read("bow_vq_tc")
+    ctx.profile_enable(False)
+    assert n_tc == 0
+    ow, gap = oracle.bow_words(np.vstack(frames[:2]), bad_locs[0][2])
+    assert np.all(gap[w2[0] != ow] < 1e-5)
+    bow2.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # Laplacian variance
 # ------------------------------------------------------------------------------------------------
