@@ -175,11 +175,26 @@ class Matcher(object):
         Creates a dictionary with keys as image paths and values as keypoints and descriptors
         (reference Matcher.py:147-163; extraction stays on cv2 so the descriptors are identical).
         '''
-        desc = _make_extractor(self.alg if self.alg in ('SURF', 'SIFT') else 'ORB')
-        index = {}
-        for imagePath in glob.glob(self.data + '/*' + extension):
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        alg = self.alg if self.alg in ('SURF', 'SIFT') else 'ORB'
+        _make_extractor(alg)  # raise here (not in a worker) if the extractor is unavailable
+        paths = glob.glob(self.data + '/*' + extension)
+
+        def one(imagePath):
+            # a fresh extractor per image: cv2 extractors are deterministic across instances and threads (SURVEY D5),
+            # and cv2 releases the GIL, so the map images are extracted in parallel; dict order = glob order
             image = cv2.imread(imagePath)
-            kp, des = desc.detectAndCompute(image, None)
+            return _make_extractor(alg).detectAndCompute(image, None)
+
+        workers = max(1, min(len(paths), int(os.environ.get("MCL_EXTRACT_THREADS", os.cpu_count() or 1))))
+        if workers == 1:
+            results = [one(p) for p in paths]
+        else:
+            with ThreadPoolExecutor(max_workers=workers) as pool:
+                results = list(pool.map(one, paths))
+        index = {}
+        for imagePath, (kp, des) in zip(paths, results):
             index[imagePath] = (kp, des)
         return index
 

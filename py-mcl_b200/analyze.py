@@ -91,6 +91,26 @@ class analyzer(object):
         matcher.setQuery(imagePath)
         return matcher._query_descriptors(self._kind())
 
+    def _extract_many(self, imagePaths, kind=None):
+        """Query descriptors of many frames.  setQuery + detectAndCompute per frame exactly as the reference does them
+        (Matcher.py:48-51 + the extractor call of *Match), on a thread pool: cv2 releases the GIL, extraction is
+        deterministic and independent per frame, and it is the end-to-end bottleneck once matching runs on the GPU
+        (SURVEY D5 / hard part 7).  Order is preserved."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        kind = kind or self._kind()
+
+        def one(path):
+            m = Matcher(self.method, width=self.w, height=self.h)
+            m.setQuery(path)
+            return m._query_descriptors(kind)
+
+        workers = max(1, min(len(imagePaths), int(os.environ.get("MCL_EXTRACT_THREADS", os.cpu_count() or 1))))
+        if workers == 1:
+            return [one(p) for p in imagePaths]
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            return list(pool.map(one, imagePaths))
+
     @staticmethod
     def _run_result(counts):
         numbers = [int(c) for c in counts]
@@ -115,7 +135,7 @@ class analyzer(object):
         frames = glob.glob('cam1_img' + '/*' + extension)
 
         if self.method != 'BOW':
-            qdes = [self._extract(matcher, imagePath) for imagePath in frames]
+            qdes = self._extract_many(frames)
             counts = self._resident_map().match_counts(qdes, mode=self._mode())
             for f, imagePath in enumerate(frames):
                 for i in range(self.numLocations):
@@ -128,10 +148,7 @@ class analyzer(object):
                 im_features, image_paths, idf, numWords, voc = joblib.load('map/' + str(i) + '.pkl')
                 locs.append((im_features, idf, voc))
             bow = _lib.BowIndex(self._context(), locs, int(np.asarray(locs[0][0]).shape[1]))
-            qdes = []
-            for imagePath in frames:
-                matcher.setQuery(imagePath)
-                qdes.append(matcher._query_descriptors('SIFT'))
+            qdes = self._extract_many(frames, 'SIFT')
             scores, _ = bow.score(qdes)
             for f, imagePath in enumerate(frames):
                 for i in range(self.numLocations):
