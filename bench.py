@@ -316,21 +316,21 @@ def main():
         i8_rate, _ = ctx.microbench(0, 4000)
         peak = i8_rate / 1e12
         roofline = {
-            "bound": "tensor", "kernel": "sift_tc2_kernel (tcgen05.mma kind::i8 u8xu8->s32, A in TMEM, K extended 128->160 for the norm term, fused top-2 epilogue)",
+            "bound": "tensor", "kernel": "sift_tc3_kernel (tcgen05.mma kind::i8 u8xu8->s32, queries in TMEM, norm-sorted map tiles, fused bracketed top-2 epilogue)",
             "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
             "peak_source": "int8 tensor pipe measured live in this run (mcl_microbench: back-to-back tcgen05.mma kind::i8 "
                            "128x128x32 on all SMs); MEASURED_PEAKS.json (%s) carries no int8 figure" % pk["src"],
             "peak_2x_bf16_sustained": 2.0 * pk["bf16_sustained"], "frac_of_2x_bf16_sustained": achieved / (2.0 * pk["bf16_sustained"]),
             "peak_2x_bf16_burst": 2.0 * pk["bf16_burst"], "frac_of_2x_bf16_burst": achieved / (2.0 * pk["bf16_burst"]),
             "peak_nominal": 4500.0, "frac_of_nominal": achieved / 4500.0,
-            "tensor_pipe_busy_frac": achieved * 1.25 / peak,
-            "note": "achieved counts only the algorithmic 2*Nq*Nm*128 int-ops; the kernel issues 25% more MMA work (K 128->160) "
-                    "so the tensor pipe itself is tensor_pipe_busy_frac busy",
             "kernel_ms_per_step": tc_ms_step, "kernel_launches_per_step": tc_n / steps_prof,
             "kernel_share_of_step": tc_ms_step / (ms / args.steps),
             "fixup_ms_per_step": fix_ms / steps_prof, "repair_ms_per_step": simt_ms / steps_prof,
             "algorithmic_ops_per_unit": OPS_PER_UNIT, "units_per_step_per_gpu": n_frames * n_images,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default configuration, from the ncu --set full
+            # capture summarised in profiles/r1_sift_tc3_fullcfg_ncu.md (tensor-bound kernel: 0.15 % of the HBM peak)
+            "traffic": 241.6e6 if (n_frames == FRAMES and n_images == LOC_PER_GPU * IMG_PER_LOC and args.algo == 1) else None,
+            "traffic_unit": "bytes per launch (ncu, profiles/r1_sift_tc3_fullcfg_ncu.md)",
         }
         cpu = None
         if not args.no_cpu_baseline:
