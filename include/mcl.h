@@ -107,6 +107,13 @@ int mcl_bow_score(mcl_bow* bow, int n_queries, const int64_t* q_row_offsets, con
                   int32_t* out_words, float* out_scores);
 int mcl_bow_score_device(mcl_bow* bow, mcl_queries* q, int32_t* d_words, float* d_scores, void* stream);
 
+/* mcl_kmeans: the code book training of Matcher.createIndex (Matcher.py:124, `kmeans(descriptors, numWords, 1)`), i.e.
+ * scipy.cluster.vq._kmeans(obs, guess, thresh): Lloyd iterations from the initial code book `guess` (k x 128 float32) over
+ * n observations (n x 128, uint8 or integer-valued float32) until the average distortion changes by <= thresh; empty
+ * clusters are dropped.  out_voc must hold k x 128 floats; *out_k = rows kept.  The assignment step is mcl_bow_score's. */
+int mcl_kmeans(mcl_ctx* ctx, int64_t n, const void* obs, int obs_dtype, int k, const float* guess, double thresh,
+               int max_iter, float* out_voc, int* out_k, double* out_distortion, int* out_iters);
+
 /* ---- small stages --------------------------------------------------------------------------------------
  * mcl_laplacian_var: analyzer.Laplacian (analyze.py:441-445) for n grayscale u8 images (host pointers,
  * row stride in bytes): out[i] = cv2.Laplacian(img, CV_64F).var().

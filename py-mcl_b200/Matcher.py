@@ -133,10 +133,11 @@ class Matcher(object):
     #############################
 
     def createIndex(self, trainingPath):
-        """Reference Matcher.py:106-141.  k-means training stays on scipy (unseeded in the reference, offline);
-        the visual-word assignment of the training descriptors runs on the GPU vq kernel."""
+        """Reference Matcher.py:106-141.  kmeans(train_descriptors, numWords, 1) = one run of Lloyd iterations from numWords
+        observations drawn with numpy's global RandomState (scipy's _kpoints, unseeded unless the caller seeds
+        np.random); the iterations (assignment on tensor cores, means, empty clusters dropped, distortion threshold 1e-5)
+        run on the GPU (mcl_kmeans), as does the visual-word assignment of the training descriptors."""
         import joblib
-        from scipy.cluster.vq import kmeans
         from sklearn import preprocessing
         desc = _make_extractor('SIFT')
         train_des_list = []
@@ -148,9 +149,10 @@ class Matcher(object):
             kp, des = desc.detectAndCompute(image, None)
             train_des_list.append((imagePath, des))
         train_descriptors = np.vstack([d for _, d in train_des_list if d is not None])
-        voc, variance = kmeans(train_descriptors, numWords, 1)
-        voc = np.ascontiguousarray(voc, dtype=np.float32)
         ctx = self._context()
+        idx = np.random.mtrand._rand.choice(train_descriptors.shape[0], size=int(numWords), replace=False)
+        voc, variance, _ = ctx.kmeans(train_descriptors, np.take(train_descriptors, idx, axis=0))
+        voc = np.ascontiguousarray(voc, dtype=np.float32)
         tmp = _lib.BowIndex(ctx, [(np.zeros((0, numWords), 'float32'), np.ones(numWords, 'float32'), voc)], numWords)
         _, words = tmp.score([d for _, d in train_des_list], want_words=True)
         tmp.close()

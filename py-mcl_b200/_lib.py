@@ -59,6 +59,8 @@ SIGNATURES = {
     "mcl_bow_destroy": (None, [_p]),
     "mcl_bow_score": (C.c_int, [_p, C.c_int, _i64p, _p, C.c_int, _p, _p]),
     "mcl_bow_score_device": (C.c_int, [_p, _p, _p, _p, _p]),
+    "mcl_kmeans": (C.c_int, [_p, C.c_int64, _p, C.c_int, C.c_int, _p, C.c_double, C.c_int, _p, C.POINTER(C.c_int),
+                            C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "mcl_laplacian_var": (C.c_int, [_p, C.c_int, C.POINTER(_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _p]),
     "mcl_laplacian_sums": (C.c_int, [_p, C.c_int, C.POINTER(_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _p]),
     "mcl_filter_step": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_char, C.c_double, _p, _p, _p, _p]),
@@ -188,6 +190,24 @@ class Context:
         out = (C.c_double * 2)()
         _check(self._lib.mcl_microbench(self._h, which, iters, out), "mcl_microbench")
         return out[0], out[1]
+
+    def kmeans(self, obs, guess, thresh=1e-5, max_iter=0):
+        """scipy.cluster.vq._kmeans(obs, guess, thresh) on the GPU -> (code_book (k', 128) float32, avg distortion, iterations)."""
+        obs = np.asarray(obs)
+        if obs.ndim != 2 or obs.shape[1] != 128:
+            raise MclError("kmeans: observations must be (n, 128)")
+        if obs.dtype == np.uint8:
+            o, code = np.ascontiguousarray(obs), U8
+        else:
+            o, code = np.ascontiguousarray(obs, dtype=np.float32), F32
+        g = np.ascontiguousarray(guess, dtype=np.float32)
+        if g.ndim != 2 or g.shape[1] != 128:
+            raise MclError("kmeans: guess must be (k, 128)")
+        out = np.zeros_like(g)
+        k_out, dist, iters = C.c_int(), C.c_double(), C.c_int()
+        _check(self._lib.mcl_kmeans(self._h, len(o), _ptr(o), code, len(g), _ptr(g), float(thresh), int(max_iter), _ptr(out),
+                                    C.byref(k_out), C.byref(dist), C.byref(iters)), "mcl_kmeans")
+        return out[:k_out.value].copy(), dist.value, iters.value
 
     # ---- small stages -------------------------------------------------------------------
     def laplacian_var(self, images):

@@ -21,6 +21,7 @@
 #include "simt_match.cuh"
 #include "bow_lap_filter.cuh"
 #include "bow_tc.cuh"
+#include "kmeans.cuh"
 #include "microbench.cuh"
 
 namespace {
@@ -1235,17 +1236,11 @@ extern "C" int mcl_bow_create(mcl_ctx* c, int n_locations, const int64_t* voc_ro
     return MCL_OK;
 }
 
-extern "C" int mcl_bow_score_device(mcl_bow* b, mcl_queries* q, int32_t* d_words, float* d_scores, void* stream) {
-    if (!b || !q || !d_scores) return fail(MCL_EINVAL, "mcl_bow_score_device: NULL argument");
-    if (q->kind != MCL_BOWQ) return fail(MCL_EINVAL, "mcl_bow_score_device: queries must be of kind MCL_BOWQ");
-    if (b->ctx != q->ctx) return fail(MCL_EINVAL, "bow index and queries belong to different contexts");
+namespace {
+// Visual-word assignment of n_q query rows (float32, (n_q,128) on the device) against every location of `b`:
+// fills ctx->bow_best[loc * n_q + row] with (float32 distance bits << 32 | word) or (0 << 32 | word).
+int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
     mcl_ctx* c = b->ctx;
-    CU(cudaSetDevice(c->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    const int n_q = (int)q->rows;
-    const int nf = q->n_queries;
-    if (nf == 0) return MCL_OK;
-    if (nf > 65535) return fail(MCL_EINVAL, "at most 65535 query frames per call");
     const size_t nbest = (size_t)b->n_loc * std::max(1, n_q);
     CU(c->bow_best.ensure(nbest * 8));
     CU(cudaMemsetAsync(c->bow_best.p, 0xFF, nbest * 8, st));
@@ -1276,7 +1271,7 @@ extern "C" int mcl_bow_score_device(mcl_bow* b, mcl_queries* q, int32_t* d_words
             {
                 ProfScope ps(c, PROF_PREP, st);
                 mcl::prep_rows128_kernel<true><<<grid_for((int64_t)n_q * 32, 256, c->sm_count * 8), 256, 0, st>>>(
-                    q->d_desc, n_q, q_off, q_off, 1, c->bow_q8.as<uint8_t>(), q_norm, q_seg, bad, nullptr);
+                    d_q, n_q, q_off, q_off, 1, c->bow_q8.as<uint8_t>(), q_norm, q_seg, bad, nullptr);
             }
             CU(cudaGetLastError());
             const size_t smem = sizeof(Smem);
@@ -1301,10 +1296,10 @@ extern "C" int mcl_bow_score_device(mcl_bow* b, mcl_queries* q, int32_t* d_words
             CU(cudaGetLastError());
             {
                 ProfScope ps(c, PROF_VQ_RESOLVE, st);
-                bow_accept_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->bow_tc_out.as<int4>(), n_splits, (const float*)q->d_desc, n_q,
+                bow_accept_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->bow_tc_out.as<int4>(), n_splits, d_q, n_q,
                                                                   b->n_loc, bad, c->bow_best.as<unsigned long long>(), queue, state);
                 bow_decide_kernel<<<1, 1, 0, st>>>(bad, (int64_t)nbest, state);
-                bow_rescan_kernel<<<c->sm_count * 8, 256, 0, st>>>(queue, (const float*)q->d_desc, n_q, b->d_voc, b->d_voc_off,
+                bow_rescan_kernel<<<c->sm_count * 8, 256, 0, st>>>(queue, d_q, n_q, b->d_voc, b->d_voc_off,
                                                                   c->bow_best.as<unsigned long long>(), state);
             }
             c->launches += 2;
@@ -1314,10 +1309,29 @@ extern "C" int mcl_bow_score_device(mcl_bow* b, mcl_queries* q, int32_t* d_words
         dim3 grid((b->max_words + mcl::VQ_WORDS - 1) / mcl::VQ_WORDS, (n_q + 127) / 128, b->n_loc);
         if (grid.y > 65535 || grid.z > 65535) return fail(MCL_EINVAL, "bow batch too large");
         ProfScope ps(c, PROF_VQ, st);
-        mcl::bow_vq_kernel<<<grid, 128, 0, st>>>((const float4*)q->d_desc, n_q, (const float4*)b->d_voc, b->d_voc_off, only_if,
+        mcl::bow_vq_kernel<<<grid, 128, 0, st>>>((const float4*)d_q, n_q, (const float4*)b->d_voc, b->d_voc_off, only_if,
                                                  c->bow_best.as<unsigned long long>());
     }
     CU(cudaGetLastError());
+    return MCL_OK;
+}
+}  // namespace
+
+extern "C" int mcl_bow_score_device(mcl_bow* b, mcl_queries* q, int32_t* d_words, float* d_scores, void* stream) {
+    if (!b || !q || !d_scores) return fail(MCL_EINVAL, "mcl_bow_score_device: NULL argument");
+    if (q->kind != MCL_BOWQ) return fail(MCL_EINVAL, "mcl_bow_score_device: queries must be of kind MCL_BOWQ");
+    if (b->ctx != q->ctx) return fail(MCL_EINVAL, "bow index and queries belong to different contexts");
+    mcl_ctx* c = b->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const int n_q = (int)q->rows;
+    const int nf = q->n_queries;
+    if (nf == 0) return MCL_OK;
+    if (nf > 65535) return fail(MCL_EINVAL, "at most 65535 query frames per call");
+    {
+        const int r = bow_assign(b, (const float*)q->d_desc, n_q, st);
+        if (r) return r;
+    }
     {
         dim3 grid(b->n_loc, nf);
         int64_t max_rows = 1;
@@ -1359,6 +1373,130 @@ extern "C" int mcl_bow_score(mcl_bow* b, int n_queries, const int64_t* q_row_off
     };
     rc = body();
     mcl_queries_destroy(q);
+    return rc;
+}
+
+// ================================================================================================
+// k-means code book training (BOW index build)
+// ================================================================================================
+extern "C" int mcl_kmeans(mcl_ctx* c, int64_t n, const void* obs, int obs_dtype, int k, const float* guess, double thresh,
+                          int max_iter, float* out_voc, int* out_k, double* out_distortion, int* out_iters) {
+    if (!c || !obs || !guess || !out_voc || !out_k) return fail(MCL_EINVAL, "mcl_kmeans: NULL argument");
+    if (n <= 0 || k <= 0 || n > ((int64_t)1 << 30)) return fail(MCL_EINVAL, "mcl_kmeans: bad n or k");
+    if (obs_dtype != MCL_U8 && obs_dtype != MCL_F32) return fail(MCL_EINVAL, "mcl_kmeans: bad dtype");
+    if (max_iter <= 0) max_iter = 1000;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    using namespace mcl::bowtc;
+    const int max_tiles = (k + TILE_N - 1) / TILE_N;
+    float* d_obs = nullptr;
+    float* d_voc[2] = {nullptr, nullptr};
+    float* d_sums = nullptr;
+    int* d_counts = nullptr;
+    int64_t* d_voc_off = nullptr;
+    int32_t* d_tile_off = nullptr;
+    uint8_t* d_tiles = nullptr;
+    double* d_sum = nullptr;   // [0] distortion sum; the following int is k_new
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(st);
+        cudaFree(d_obs); cudaFree(d_voc[0]); cudaFree(d_voc[1]); cudaFree(d_sums); cudaFree(d_counts);
+        cudaFree(d_voc_off); cudaFree(d_tile_off); cudaFree(d_tiles); cudaFree(d_sum);
+    };
+#define KCU(expr)                                                                                                \
+    do {                                                                                                          \
+        cudaError_t e_ = (expr);                                                                                  \
+        if (e_ != cudaSuccess) {                                                                                  \
+            cleanup();                                                                                            \
+            return fail(MCL_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+        }                                                                                                         \
+    } while (0)
+    KCU(cudaMalloc(&d_obs, (size_t)n * 512));
+    KCU(cudaMalloc(&d_voc[0], (size_t)k * 512));
+    KCU(cudaMalloc(&d_voc[1], (size_t)k * 512));
+    KCU(cudaMalloc(&d_sums, (size_t)k * 512));
+    KCU(cudaMalloc(&d_counts, (size_t)k * 4));
+    KCU(cudaMalloc(&d_voc_off, 16));
+    KCU(cudaMalloc(&d_tile_off, 8));
+    KCU(cudaMalloc(&d_tiles, (size_t)max_tiles * STAGE_BYTES));
+    KCU(cudaMalloc(&d_sum, 16));
+    if (obs_dtype == MCL_F32) {
+        KCU(cudaMemcpyAsync(d_obs, obs, (size_t)n * 512, cudaMemcpyHostToDevice, st));
+    } else {
+        KCU(c->stage.ensure((size_t)n * 128));
+        KCU(cudaMemcpyAsync(c->stage.p, obs, (size_t)n * 128, cudaMemcpyHostToDevice, st));
+        c->launches++;
+        mcl::u8_to_f32_kernel<<<grid_for(n * 128, 256, c->sm_count * 8), 256, 0, st>>>(c->stage.as<uint8_t>(), d_obs, n * 128);
+    }
+    KCU(cudaMemcpyAsync(d_voc[0], guess, (size_t)k * 512, cudaMemcpyHostToDevice, st));
+    mcl_bow tmp;   // a one-location "index" over the current code book, for bow_assign
+    tmp.ctx = c;
+    tmp.n_loc = 1;
+    tmp.W = k;
+    tmp.d_voc_off = d_voc_off;
+    tmp.d_tile_off = d_tile_off;
+    tmp.d_tiles = d_tiles;
+    int cur = 0, k_cur = k, iters = 0;
+    double prev = INFINITY, avg = 0.0;
+    int rc = MCL_OK;
+    auto assign_and_distort = [&]() -> int {
+        const int64_t h_off[2] = {0, k_cur};
+        const int32_t h_toff[2] = {0, (k_cur + TILE_N - 1) / TILE_N};
+        KCU(cudaMemcpyAsync(d_voc_off, h_off, 16, cudaMemcpyHostToDevice, st));
+        KCU(cudaMemcpyAsync(d_tile_off, h_toff, 8, cudaMemcpyHostToDevice, st));
+        int* bad = c->flags.as<int>() + 6;
+        KCU(cudaMemsetAsync(bad, 0, 4, st));
+        c->launches++;
+        build_planes_kernel<<<h_toff[1], 256, 0, st>>>(d_voc[cur], d_voc_off, 1, d_tile_off, d_tiles, bad);
+        int h_bad = 0;
+        KCU(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
+        KCU(cudaStreamSynchronize(st));
+        tmp.d_voc = d_voc[cur];
+        tmp.max_words = k_cur;
+        tmp.voc_rows = k_cur;
+        tmp.tc_ok = h_bad == 0;
+        const int r = bow_assign(&tmp, d_obs, (int)n, st);
+        if (r) return r;
+        KCU(cudaMemsetAsync(d_sum, 0, 16, st));
+        c->launches++;
+        mcl::kmeans_distort_kernel<<<c->sm_count * 8, 256, 0, st>>>(d_obs, n, d_voc[cur], c->bow_best.as<unsigned long long>(), d_sum);
+        double h_sum = 0.0;
+        KCU(cudaMemcpyAsync(&h_sum, d_sum, 8, cudaMemcpyDeviceToHost, st));
+        KCU(cudaStreamSynchronize(st));
+        avg = h_sum / (double)n;
+        return MCL_OK;
+    };
+    // scipy _kmeans: while diff > thresh: assign, avg distortion, update, diff = |previous avg - avg|
+    double diff = INFINITY;
+    while (diff > thresh && iters < max_iter) {
+        rc = assign_and_distort();
+        if (rc) break;
+        KCU(cudaMemsetAsync(d_sums, 0, (size_t)k_cur * 512, st));
+        KCU(cudaMemsetAsync(d_counts, 0, (size_t)k_cur * 4, st));
+        c->launches += 2;
+        mcl::kmeans_accum_kernel<<<c->sm_count * 8, 256, 0, st>>>(d_obs, n, c->bow_best.as<unsigned long long>(), d_sums, d_counts);
+        int* d_knew = reinterpret_cast<int*>(d_sum + 1);
+        mcl::kmeans_update_kernel<<<1, 1024, 0, st>>>(k_cur, d_sums, d_counts, d_voc[cur ^ 1], d_knew);
+        int h_knew = 0;
+        KCU(cudaMemcpyAsync(&h_knew, d_knew, 4, cudaMemcpyDeviceToHost, st));
+        KCU(cudaStreamSynchronize(st));
+        diff = std::fabs(prev - avg);
+        prev = avg;
+        cur ^= 1;
+        k_cur = h_knew;
+        ++iters;
+        if (k_cur <= 0) { rc = fail(MCL_EDATA, "mcl_kmeans: every cluster became empty"); break; }
+    }
+    if (rc == MCL_OK) rc = assign_and_distort();   // final distortion of the returned code book
+    if (rc == MCL_OK) {
+        KCU(cudaMemcpyAsync(out_voc, d_voc[cur], (size_t)k_cur * 512, cudaMemcpyDeviceToHost, st));
+        KCU(cudaStreamSynchronize(st));
+        *out_k = k_cur;
+        if (out_distortion) *out_distortion = avg;
+        if (out_iters) *out_iters = iters;
+    }
+    tmp.d_voc = nullptr; tmp.d_voc_off = nullptr; tmp.d_tile_off = nullptr; tmp.d_tiles = nullptr;
+    cleanup();
+#undef KCU
     return rc;
 }
 

@@ -9,7 +9,7 @@ from pymcl_b200 import _lib, synth
 import oracle
 
 ctx = _lib.Context(0)
-names = sys.argv[1:] or ["orb", "orb_batch", "sift_cfg2", "surf", "bow", "laplacian"]
+names = sys.argv[1:] or ["orb", "orb_batch", "sift_cfg2", "surf", "bow", "kmeans", "laplacian"]
 POPC_PEAK = None
 
 
@@ -153,6 +153,20 @@ if "bow" in names:   # cfg5 scaled: 16 locations x 100 images, W = 10000, Nq = 3
                     "simt_only_e2e_ms": r_simt["e2e_ms"], "simt_only_vq_ms": r_simt["bow_vq"],
                     "cpu_locations_per_s": cpu})
     bow.close()
+if "kmeans" in names:   # createIndex's code book training: 25 images x 2000 descriptors, k = 10000 (Matcher.py:46,124)
+    from scipy.cluster.vq import kmeans as sp_kmeans
+    rng = np.random.default_rng(8)
+    centers = synth.sift_like(rng, 12000)
+    obs = np.clip(np.rint(centers[rng.integers(0, 12000, size=50000)] + rng.normal(0, 7.0, size=(50000, 128))), 0, 255).astype(np.float32)
+    guess = obs[rng.choice(50000, size=10000, replace=False)]
+    ctx.kmeans(obs[:2000], guess[:100])
+    t0 = time.perf_counter(); book, dist, iters = ctx.kmeans(obs, guess); t1 = time.perf_counter()
+    sub = 4
+    t2 = time.perf_counter(); rb, rd = sp_kmeans(obs[::sub], guess[::sub], thresh=1e-5); t3 = time.perf_counter()
+    out.append({"config": "k-means code book, 50000 x 128 observations, k = 10000 (createIndex)", "gpu_s": t1 - t0, "iterations": iters,
+                "words_kept": int(book.shape[0]), "distortion": dist,
+                "scipy_s_on_1/%d of obs and 1/%d of k" % (sub, sub): t3 - t2,
+                "scipy_extrapolated_s": (t3 - t2) * sub * sub})
 if "laplacian" in names:
     import cv2
     rng = np.random.default_rng(6)

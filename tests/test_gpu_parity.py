@@ -71,6 +71,31 @@ def test_sift_ragged_and_edge_cases(ctx, algo):
     assert got[1].sum() == 0 and got[:, 0].sum() == 0 and got[:, 1].sum() == 0
 
 
+@pytest.mark.parametrize("algo", [_lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V2, _lib.ALGO_TENSOR_V1])
+def test_sift_many_tiny_images_and_one_huge_image(ctx, algo):
+    """Shapes at the edges of the tiling: hundreds of images of a few rows each (every 32-row group is another image) and
+    one image longer than the shared-memory metadata window of a chunk (> 352 tiles of 64 rows)."""
+    rng = np.random.default_rng(31)
+    tiny = [synth.sift_like(rng, int(n)) for n in rng.integers(2, 40, size=300)]
+    frames = [synth.sift_like(rng, 500), synth.sift_like(rng, 130)]
+    src = np.vstack(tiny[:40])
+    frames[0][:200] = synth.sift_noisy_copy(rng, src[:200], 3.0)
+    want = oracle_counts(oracle.sift_pair_count, frames, tiny)
+    m = _lib.MapIndex(ctx, "SIFT", tiny)
+    got = m.match_counts(frames, algo=algo)
+    m.close()
+    assert want.sum() > 100
+    assert np.array_equal(got, want)
+    huge = [synth.sift_like(rng, 23000), synth.sift_like(rng, 70), synth.sift_like(rng, 2050)]
+    frames[1][:60] = synth.sift_noisy_copy(rng, huge[0][22000:22060], 3.0)
+    want = oracle_counts(oracle.sift_pair_count, frames, huge)
+    m = _lib.MapIndex(ctx, "SIFT", huge)
+    got = m.match_counts(frames, algo=algo)
+    m.close()
+    assert want[1, 0] >= 50
+    assert np.array_equal(got, want)
+
+
 def test_sift_ratio_known_answers(ctx, golden_dir):
     """The cv2 ratio semantics float(sqrtf(d0^2)) < 0.7*float(sqrtf(d1^2)) on the survey's integer pairs:
     build 1 query row and 2 map rows with exactly those squared distances."""
@@ -340,6 +365,26 @@ def test_bow_tensor_core_path_equals_simt_and_oracle(ctx):
     ow, gap = oracle.bow_words(np.vstack(frames[:2]), bad_locs[0][2])
     assert np.all(gap[w2[0] != ow] < 1e-5)
     bow2.close()
+
+
+def test_kmeans_matches_scipy_lloyd(ctx):
+    """mcl_kmeans = scipy.cluster.vq._kmeans(obs, guess, thresh): same iterations from the same initial code book.
+    Observations are integer valued, so member sums are exact and the centroids agree to float32 rounding unless an
+    assignment sat on a float32 near-tie (none on this data)."""
+    from scipy.cluster.vq import kmeans
+    rng = np.random.default_rng(77)
+    centers = synth.sift_like(rng, 60)
+    obs = np.clip(np.rint(centers[rng.integers(0, 60, size=5000)] + rng.normal(0, 9.0, size=(5000, 128))), 0, 255).astype(np.float32)
+    guess = obs[rng.choice(5000, size=48, replace=False)].copy()
+    guess[7] = guess[3]     # duplicate initial centroid -> an empty cluster that must be dropped (lowest index wins ties)
+    ref_book, ref_dist = kmeans(obs, guess, thresh=1e-5)
+    book, dist, iters = ctx.kmeans(obs, guess, thresh=1e-5)
+    assert book.shape == ref_book.shape and book.shape[0] < 48
+    assert iters >= 2
+    assert np.allclose(book, ref_book, rtol=0, atol=1e-3)
+    assert abs(dist - float(ref_dist)) <= 1e-4 * float(ref_dist)
+    book8, dist8, _ = ctx.kmeans(obs.astype(np.uint8), guess, thresh=1e-5)
+    assert np.array_equal(book8, book) and dist8 == dist
 
 
 # ------------------------------------------------------------------------------------------------
