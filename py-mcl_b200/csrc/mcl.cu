@@ -837,6 +837,7 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         CU(cudaFuncSetAttribute(sift_tc3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaFuncSetAttribute(sift_tc3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaFuncSetAttribute(sift_tc3_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc3_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         m->tc3_attr = true;
     }
     const int n_qblocks_total = (int)(q->padded_rows / QBLK);
@@ -879,6 +880,7 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
             ProfScope ps(c, PROF_SIFT_TC, st);
             if (c->opt[0] == 3) sift_tc3_kernel<3><<<grid, THREADS, smem, st>>>(p);
             else if (c->opt[0] == 4) sift_tc3_kernel<4><<<grid, THREADS, smem, st>>>(p);
+            else if (c->opt[0] == 6) sift_tc3_kernel<6><<<grid, THREADS, smem, st>>>(p);
             else if (c->opt[0] == 5) {
                 sift_tc3_kernel<5><<<grid, THREADS, smem, st>>>(p);
                 long long tl[64 * 5];

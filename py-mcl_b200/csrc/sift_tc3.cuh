@@ -206,15 +206,23 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc3_kernel(const __grid_const
                 if (as != my_stage) continue;
                 mbar_wait(&s.b_full[bs], bph);
                 const uint64_t b_desc = umma_desc_sw128(smem_u32(s.stage[bs]));
+                // The three accumulators of this stage are independent: issue each A tile's MMAs as soon as ITS accumulator
+                // has been handed back, in whatever order that happens (in-order issue lets the slowest of the 12 epilogue
+                // warps hold up the other two A tiles: a convoy).
+                uint32_t pending = (1u << ATILES) - 1u;
+                while (pending) {
 #pragma unroll
-                for (int a = 0; a < ATILES; ++a) {
-                    mbar_wait(&s.acc_empty[as][a], aph ^ 1);
-                    tc_fence_after();
-                    const uint32_t d = tmem_base + ACC_COL0 + (as * ATILES + a) * TILE_N;
-                    const uint32_t ta = tmem_base + a * A_COLS;
+                    for (int a = 0; a < ATILES; ++a) {
+                        if (!(pending & (1u << a))) continue;
+                        if (!mbar_test_wait(&s.acc_empty[as][a], aph ^ 1)) continue;
+                        pending &= ~(1u << a);
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + ACC_COL0 + (as * ATILES + a) * TILE_N;
+                        const uint32_t ta = tmem_base + a * A_COLS;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_i8_ts_if(leader, d, ta + 8 * k, b_desc + 2 * k, idesc, k > 0);
-                    tc_commit_if(leader, &s.acc_full[as][a]);
+                        for (int k = 0; k < 4; ++k) umma_i8_ts_if(leader, d, ta + 8 * k, b_desc + 2 * k, idesc, k > 0);
+                        tc_commit_if(leader, &s.acc_full[as][a]);
+                    }
                 }
                 tc_commit_if(leader, &s.b_empty[bs]);
                 __syncwarp();
@@ -288,7 +296,13 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc3_kernel(const __grid_const
                 if (MODE == 5) tk1 = clock64();
                 const uint32_t tcol = t_lane + ACC_COL0 + (as * ATILES + atile) * TILE_N;
                 uint32_t v[GROUPS][32];
-                if (MODE != 4) {
+                if (MODE == 6) {   // diagnostic: half of the TMEM read volume (results meaningless)
+                    tmem_ld32(tcol, v[0]);
+                    tmem_wait_all();
+                    tmem_fence_regs(v[0]);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[1][i] = v[0][i];
+                } else if (MODE != 4) {
                     tmem_ld64(tcol, reinterpret_cast<uint32_t(&)[64]>(v));
                     tmem_wait_all();
 #pragma unroll
