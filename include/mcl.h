@@ -37,9 +37,10 @@ enum { MCL_U8 = 0, MCL_F32 = 1 };
 enum { MCL_KNN2_RATIO = 0 /* knnMatch(k=2) + ratio lambda, Matcher.py:218-219,279-280 */,
        MCL_CROSSCHECK = 1 /* ORB only: BFMatcher(NORM_HAMMING, crossCheck=True).match, Matcher.py:180-182 */ };
 /* algorithm selector for SIFT (testing / profiling) */
-enum { MCL_ALGO_AUTO = 0, MCL_ALGO_TENSOR = 1 /* tcgen05, A in tensor memory, norm-sorted groups (sift_tc3): the product path */,
+enum { MCL_ALGO_AUTO = 0, MCL_ALGO_TENSOR = 1 /* tcgen05, A in tensor memory, norm-sorted groups, N = 128 (sift_tc4): the product path */,
        MCL_ALGO_SIMT = 2 /* dp4a, exact top-2 */, MCL_ALGO_TENSOR_V1 = 3 /* tcgen05, operands in shared memory (sift_tc) */,
-       MCL_ALGO_TENSOR_V2 = 4 /* tcgen05, A in tensor memory + K extension 128->160 (sift_tc2) */ };
+       MCL_ALGO_TENSOR_V2 = 4 /* tcgen05, A in tensor memory + K extension 128->160 (sift_tc2) */,
+       MCL_ALGO_TENSOR_V3 = 5 /* as the product path with N = 64 tiles and double-buffered accumulators (sift_tc3) */ };
 
 /* ---- context ---------------------------------------------------------------------------------------- */
 int mcl_init(int device_id, mcl_ctx** out);

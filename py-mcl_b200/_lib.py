@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libmcl.so")
 SIFT, ORB, SURF, BOWQ = 0, 1, 2, 3
 U8, F32 = 0, 1
 KNN2_RATIO, CROSSCHECK = 0, 1
-ALGO_AUTO, ALGO_TENSOR, ALGO_SIMT, ALGO_TENSOR_V1, ALGO_TENSOR_V2 = 0, 1, 2, 3, 4
+ALGO_AUTO, ALGO_TENSOR, ALGO_SIMT, ALGO_TENSOR_V1, ALGO_TENSOR_V2, ALGO_TENSOR_V3 = 0, 1, 2, 3, 4, 5
 F_COMMAND, F_PREV, F_BLUR, F_BEST, F_ALL = 1, 2, 4, 8, 15
 KIND_BY_NAME = {"SIFT": SIFT, "ORB": ORB, "SURF": SURF}
 ROW_DIM = {SIFT: 128, ORB: 32, SURF: 64, BOWQ: 128}

@@ -18,6 +18,7 @@
 #include "sift_tc.cuh"
 #include "sift_tc2.cuh"
 #include "sift_tc3.cuh"
+#include "sift_tc4.cuh"
 #include "simt_match.cuh"
 #include "bow_lap_filter.cuh"
 #include "bow_tc.cuh"
@@ -129,7 +130,7 @@ struct mcl_map {
     int key_c = 0;                       // sift_tc2: true key = 2*acc - key_c (+ parity)
     bool ext_ok = false;                 // the norms' range fits the extension encoding
     mcl::sifttc3::TileMeta* d_meta3 = nullptr;   // sift_tc3: per 64-row tile
-    bool tc3_attr = false;
+    bool tc3_attr = false, tc4_attr = false;
     int max_rows_per_image = 0;
 };
 
@@ -828,7 +829,7 @@ int launch_sift_tc2(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
     return MCL_OK;
 }
 
-int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, cudaStream_t st) {
+int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, cudaStream_t st, bool gen4 = false) {
     using namespace mcl::sifttc3;
     mcl_ctx* c = m->ctx;
     const size_t smem = sizeof(Smem);
@@ -839,6 +840,13 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         CU(cudaFuncSetAttribute(sift_tc3_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaFuncSetAttribute(sift_tc3_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         m->tc3_attr = true;
+    }
+    const size_t smem4 = sizeof(mcl::sifttc4::Smem);
+    if (gen4 && !m->tc4_attr) {
+        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        m->tc4_attr = true;
     }
     const int n_qblocks_total = (int)(q->padded_rows / QBLK);
     const int64_t pairs_total = q->padded_rows * (int64_t)std::max(1, m->n_images);
@@ -856,7 +864,7 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
     CU(cudaMemsetAsync(d_overflow, 0, 4, st));
     for (int qb0 = 0; qb0 < n_qblocks_total; qb0 += batch_qblocks) {
         const int nqb = std::min(batch_qblocks, n_qblocks_total - qb0);
-        const mcl_map::ChunkSet* cs = pick_chunks(m->chunk_sets2, nqb, c->sm_count);
+        const mcl_map::ChunkSet* cs = pick_chunks(gen4 ? m->chunk_sets : m->chunk_sets2, nqb, c->sm_count);   // 128- / 64-row tiles
         if (cs->n == 0) break;
         CU(cudaMemsetAsync(d_cand_count, 0, 4, st));
         Params p;
@@ -878,7 +886,12 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         const int grid = (int)std::min<int64_t>(n_items, c->sm_count);
         {
             ProfScope ps(c, PROF_SIFT_TC, st);
-            if (c->opt[0] == 3) sift_tc3_kernel<3><<<grid, THREADS, smem, st>>>(p);
+            if (gen4) {
+                using namespace mcl::sifttc4;
+                if (c->opt[0] == 3) sift_tc4_kernel<3><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
+                else if (c->opt[0] == 4) sift_tc4_kernel<4><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
+                else sift_tc4_kernel<0><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
+            } else if (c->opt[0] == 3) sift_tc3_kernel<3><<<grid, THREADS, smem, st>>>(p);
             else if (c->opt[0] == 4) sift_tc3_kernel<4><<<grid, THREADS, smem, st>>>(p);
             else if (c->opt[0] == 6) sift_tc3_kernel<6><<<grid, THREADS, smem, st>>>(p);
             else if (c->opt[0] == 5) {
@@ -934,7 +947,10 @@ int match_device(mcl_map* m, mcl_queries* q, int mode, double ratio, const uint8
             }
             if (use == MCL_ALGO_TENSOR_V2 && !m->ext_ok) use = MCL_ALGO_TENSOR_V1;  // norm range too wide for the K extension
             if (use == MCL_ALGO_TENSOR) {
-                int rc = launch_sift_tc3(m, q, ratio, d_counts, st);
+                int rc = launch_sift_tc3(m, q, ratio, d_counts, st, true);
+                if (rc) return rc;
+            } else if (use == MCL_ALGO_TENSOR_V3) {
+                int rc = launch_sift_tc3(m, q, ratio, d_counts, st, false);
                 if (rc) return rc;
             } else if (use == MCL_ALGO_TENSOR_V2) {
                 int rc = launch_sift_tc2(m, q, ratio, d_counts, st);

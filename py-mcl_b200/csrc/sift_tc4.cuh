@@ -1,0 +1,222 @@
+// SIFT / integer-L2 matching on 5th-gen tensor cores, fourth generation.
+//
+// sift_tc3 is bound by TENSOR-MEMORY READ BANDWIDTH, not by the tensor pipe or the ALUs: halving the tcgen05.ld volume
+// (diagnostic mode 6) lifts it from 76 % to 90 % of the int8 peak.  Per 64 map rows and 384 query rows it reads 96 KB of
+// accumulators (inherent: 4 bytes per 128 MACs) plus 48 KB of A operand, because with the query block in tensor memory
+// every MMA re-reads its 128 x 32-byte A slice and N = 64 needs 24 MMAs per 128 map rows.
+// This generation issues N = 128 MMAs (12 per 128 map rows): the A-operand reads halve (144 -> 120 KB per 64 rows).
+// Tensor memory then has room for one accumulator per A tile only (96 + 3 x 128 columns), so accumulators are single
+// buffered and the three A tiles form the pipeline: while the epilogue warps of A tile a drain its accumulator, the
+// tensor pipe works on the other two (2 x 268 cycles), which covers the drain (two 64-column loads + hand-back).
+// Everything else (norm-sorted rows, bracketed pre-filter, candidate list, exact fix-up, metadata records per 64 rows)
+// is sift_tc3's; the candidate format and sift_fixup3_kernel are shared.
+#pragma once
+#include "common.cuh"
+#include "sift_tc3.cuh"
+
+namespace mcl {
+namespace sifttc4 {
+
+using sifttc::Chunk;
+using sifttc3::Params;          // chunks / tile indices are in units of TILE_N = 128 rows here; m_meta stays per 64 rows
+using sifttc3::NONE;
+
+constexpr int TILE_N = 128;
+constexpr int HALF = 64;
+constexpr int GROUP = 32;
+constexpr int QTILE = 128;
+constexpr int ATILES = 3;
+constexpr int QBLK = ATILES * QTILE;
+constexpr int A_COLS = 32;
+constexpr int ACC_COL0 = 128;
+constexpr int B_TILE_BYTES = TILE_N * 128;   // 16 KB
+constexpr int B_STAGES = 8;
+constexpr int EPI_WARPS = ATILES * 4;
+constexpr int THREADS = (EPI_WARPS + 2) * 32;
+constexpr int TMEM_COLS = 512;
+constexpr int META_CAP = sifttc3::META_CAP;  // 64-row records staged per chunk
+
+struct Smem {
+    alignas(1024) uint8_t stage[B_STAGES][B_TILE_BYTES];
+    alignas(16) int4 meta[META_CAP * 3];
+    alignas(8) uint64_t b_full[B_STAGES];
+    uint64_t b_empty[B_STAGES];
+    uint64_t acc_full[ATILES], acc_empty[ATILES];
+    uint64_t a_full, a_free;
+    uint32_t tmem_base;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+    const int warp = warp_id_uniform();
+    const int lane = threadIdx.x & 31;
+    const uint32_t leader = lane == 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < B_STAGES; ++i) { mbar_init(&s.b_full[i], 1); mbar_init(&s.b_empty[i], 1); }
+        for (int a = 0; a < ATILES; ++a) { mbar_init(&s.acc_full[a], 1); mbar_init(&s.acc_empty[a], 4); }
+        mbar_init(&s.a_full, EPI_WARPS);
+        mbar_init(&s.a_free, 1);
+        mbar_fence_init();
+    }
+    if (warp == EPI_WARPS + 1) tmem_alloc<TMEM_COLS>(&s.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_base;
+    const int n_items = p.n_qblocks * p.n_chunks;
+
+    if (warp == EPI_WARPS) {
+        // ================= TMA producer: one 128-row map tile (16 KB) per stage ========================================
+        uint32_t bn = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const Chunk ch = p.chunks[item / p.n_qblocks];
+            for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
+                const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
+                mbar_wait(&s.b_empty[bs], bph ^ 1);
+                mbar_arrive_expect_tx_if(leader, &s.b_full[bs], B_TILE_BYTES);
+                bulk_g2s_if(leader, s.stage[bs], p.m_desc + (size_t)t * B_TILE_BYTES, B_TILE_BYTES, &s.b_full[bs]);
+            }
+        }
+    } else if (warp == EPI_WARPS + 1) {
+        // ================= MMA issuer: A from tensor memory, B from shared memory, N = 128 ==============================
+        constexpr uint32_t idesc = umma_idesc(/*c=S32*/ 2, /*a=u8*/ 0, /*b=u8*/ 0, QTILE, TILE_N);
+        uint32_t bn = 0, item_n = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+            const Chunk ch = p.chunks[item / p.n_qblocks];
+            mbar_wait(&s.a_full, item_n & 1);
+            tc_fence_after();
+            for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
+                const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
+                mbar_wait(&s.b_full[bs], bph);
+                const uint64_t b_desc = umma_desc_sw128(smem_u32(s.stage[bs]));
+                // round robin over the A tiles: accumulator a was filled first last time, so it is drained first; a blocking
+                // try_wait wakes ~60 cycles after the arrive, a polling loop over three barriers costs ~150 per probe
+#pragma unroll
+                for (int a = 0; a < ATILES; ++a) {
+                    mbar_wait(&s.acc_empty[a], (bn & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + ACC_COL0 + a * TILE_N;
+                    const uint32_t ta = tmem_base + a * A_COLS;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_i8_ts_if(leader, d, ta + 8 * k, b_desc + 2 * k, idesc, k > 0);
+                    tc_commit_if(leader, &s.acc_full[a]);
+                }
+                tc_commit_if(leader, &s.b_empty[bs]);
+                __syncwarp();
+            }
+            tc_commit_if(leader, &s.a_free);
+            __syncwarp();
+        }
+    } else {
+        // ================= epilogue warps ===========================================================================
+        const int atile = warp >> 2;
+        const int lane_base = (warp & 3) * 32;
+        const int row_in_blk = atile * QTILE + lane_base + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)lane_base << 16);
+        uint32_t bn = 0, item_n = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+            const int qb = item % p.n_qblocks;
+            const Chunk ch = p.chunks[item / p.n_qblocks];
+            const int64_t qrow = (int64_t)qb * QBLK + row_in_blk;
+            {   // this thread's query row -> tensor memory (row = TMEM lane, 4 K-bytes per column)
+                uint32_t w[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 x = *reinterpret_cast<const uint4*>(p.q_desc + sw128_chunk_offset(qrow, c));
+                    w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
+                }
+                mbar_wait(&s.a_free, (item_n & 1) ^ 1);
+                tc_fence_after();
+                tmem_st32(t_lane + atile * A_COLS, w);
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.a_full);
+            }
+            const int Q = p.q_norm[qrow];
+            const bool row_valid = Q >= 0;
+            int H1 = NONE, L1 = NONE, H2 = NONE, L2 = NONE, pos = 0;
+            auto join = [&](int gm, int nmin, int nmax, int id) {
+                const int hi = 2 * gm - nmin, lo = 2 * gm - nmax;
+                const bool better = hi > H1;
+                H2 = max(H2, better ? H1 : hi);
+                L2 = max(L2, better ? L1 : lo);
+                pos = better ? id : pos;
+                L1 = better ? lo : L1;
+                H1 = max(H1, hi);
+            };
+            // the chunk's 64-row metadata records, staged once per work item (named barrier 1 among the epilogue warps)
+            const int n_rec = 2 * (ch.tile_end - ch.tile_begin);
+            const int4* mp = reinterpret_cast<const int4*>(p.m_meta + 2 * (int64_t)ch.tile_begin);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            if (n_rec <= p.meta_cap) {
+                for (int i = threadIdx.x; i < n_rec * 3; i += EPI_WARPS * 32) s.meta[i] = __ldg(mp + i);
+                mp = s.meta;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            // one 64-row half: maxima of its two 32-row groups, bracket update, end-of-image test
+            auto half = [&](int g0, int g1, const int4* rec, int unit /* 64-row unit index */) {
+                const int4 c2 = rec[2];     // {end_mask, tnmin, tnmax, -}
+                const int end_mask = c2.x;
+                if ((end_mask & 1) == 0) {
+                    join(max(g0, g1), c2.y, c2.z, unit * 2);
+                    if (end_mask & 2) {
+                        const int4 c0 = rec[0];   // {img0, img1, nval0, nval1}
+                        sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, H2, L2, pos, c0.y, c0.w, ch);
+                        H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
+                    }
+                } else {
+                    const int4 c0 = rec[0], c1 = rec[1];   // c1 = {nmin0, nmin1, nmax0, nmax1}
+                    join(g0, c1.x, c1.z, unit * 2);
+                    sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, H2, L2, pos, c0.x, c0.z, ch);
+                    H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
+                    if (c0.y >= 0) {
+                        join(g1, c1.y, c1.w, unit * 2 + 1);
+                        if (end_mask & 2) {
+                            sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, H2, L2, pos, c0.y, c0.w, ch);
+                            H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
+                        }
+                    }
+                }
+            };
+#pragma unroll 1
+            for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
+                mbar_wait(&s.acc_full[atile], bn & 1);
+                tc_fence_after();
+                const uint32_t tcol = t_lane + ACC_COL0 + atile * TILE_N;
+                const int4* rec = mp + (size_t)(t - ch.tile_begin) * 6;
+                uint32_t v[2][32];
+                if (MODE != 4) {
+                    tmem_ld64(tcol, reinterpret_cast<uint32_t(&)[64]>(v));
+                    tmem_wait_all();
+                    tmem_fence_regs(v[0]);
+                    tmem_fence_regs(v[1]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { v[0][i] = 0; v[1][i] = 0; }
+                }
+                // first half: only the two max trees run before the second load is issued; the brackets follow the release
+                const int e0 = sifttc3::group_max<MODE>(v[0]), e1 = sifttc3::group_max<MODE>(v[1]);
+                if (MODE != 4) {
+                    tmem_ld64(tcol + HALF, reinterpret_cast<uint32_t(&)[64]>(v));
+                    tmem_wait_all();
+                    tmem_fence_regs(v[0]);
+                    tmem_fence_regs(v[1]);
+                }
+                if (lane == 0) mbar_arrive(&s.acc_empty[atile]);   // both halves are out of tensor memory: the accumulator is free
+                half(e0, e1, rec, 2 * t);
+                half(sifttc3::group_max<MODE>(v[0]), sifttc3::group_max<MODE>(v[1]), rec + 3, 2 * t + 1);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == EPI_WARPS + 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+}  // namespace sifttc4
+}  // namespace mcl

@@ -25,7 +25,7 @@ def oracle_counts(fn, qs, ms):
 # ------------------------------------------------------------------------------------------------
 # SIFT
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("algo", [_lib.ALGO_SIMT, _lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V1, _lib.ALGO_TENSOR_V2, _lib.ALGO_AUTO])
+@pytest.mark.parametrize("algo", [_lib.ALGO_SIMT, _lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V1, _lib.ALGO_TENSOR_V2, _lib.ALGO_TENSOR_V3, _lib.ALGO_AUTO])
 def test_sift_golden_reference_counts(ctx, golden_dir, algo):
     """Descriptors extracted by the reference run + the reference's own SIFTMatch counts (exact search)."""
     z = np.load(os.path.join(golden_dir, "sift_desc_case.npz"))
@@ -39,7 +39,7 @@ def test_sift_golden_reference_counts(ctx, golden_dir, algo):
     m.close()
 
 
-@pytest.mark.parametrize("algo", [_lib.ALGO_SIMT, _lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V1, _lib.ALGO_TENSOR_V2])
+@pytest.mark.parametrize("algo", [_lib.ALGO_SIMT, _lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V1, _lib.ALGO_TENSOR_V2, _lib.ALGO_TENSOR_V3])
 @pytest.mark.parametrize("nm,nq,n_images,n_frames", [(256, 256, 12, 5), (300, 150, 9, 3), (37, 61, 20, 4),
                                                      (1000, 700, 3, 2)])
 def test_sift_synthetic_vs_oracle(ctx, algo, nm, nq, n_images, n_frames):
@@ -52,7 +52,7 @@ def test_sift_synthetic_vs_oracle(ctx, algo, nm, nq, n_images, n_frames):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("algo", [_lib.ALGO_SIMT, _lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V1, _lib.ALGO_TENSOR_V2])
+@pytest.mark.parametrize("algo", [_lib.ALGO_SIMT, _lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V1, _lib.ALGO_TENSOR_V2, _lib.ALGO_TENSOR_V3])
 def test_sift_ragged_and_edge_cases(ctx, algo):
     """Variable descriptors per image incl. 0, 1, 2, 15, 16, 17, 128, 129 rows; empty frames; duplicates."""
     rng = np.random.default_rng(5)
@@ -71,7 +71,7 @@ def test_sift_ragged_and_edge_cases(ctx, algo):
     assert got[1].sum() == 0 and got[:, 0].sum() == 0 and got[:, 1].sum() == 0
 
 
-@pytest.mark.parametrize("algo", [_lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V2, _lib.ALGO_TENSOR_V1])
+@pytest.mark.parametrize("algo", [_lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V3, _lib.ALGO_TENSOR_V2, _lib.ALGO_TENSOR_V1])
 def test_sift_many_tiny_images_and_one_huge_image(ctx, algo):
     """Shapes at the edges of the tiling: hundreds of images of a few rows each (every 32-row group is another image) and
     one image longer than the shared-memory metadata window of a chunk (> 352 tiles of 64 rows)."""
@@ -114,7 +114,7 @@ def test_sift_ratio_known_answers(ctx, golden_dir):
         assert i <= 128
         return v
 
-    for algo in (_lib.ALGO_SIMT, _lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V1, _lib.ALGO_TENSOR_V2):
+    for algo in (_lib.ALGO_SIMT, _lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V1, _lib.ALGO_TENSOR_V2, _lib.ALGO_TENSOR_V3):
         for d0, d1, expect in kat:
             q = np.zeros((1, 128), np.uint8)
             m = np.stack([rows_with_d2(d0), rows_with_d2(d1)]).astype(np.uint8)
@@ -131,7 +131,7 @@ def test_sift_mask_fill(ctx):
     rng = np.random.default_rng(0)
     mask = (rng.random((4, 10)) < 0.4).astype(np.uint8)
     m = _lib.MapIndex(ctx, "SIFT", map_des)
-    for algo in (_lib.ALGO_AUTO, _lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V1, _lib.ALGO_TENSOR_V2, _lib.ALGO_SIMT):
+    for algo in (_lib.ALGO_AUTO, _lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V1, _lib.ALGO_TENSOR_V2, _lib.ALGO_TENSOR_V3, _lib.ALGO_SIMT):
         got = m.match_counts(frames, mask=mask, fill_value=1, algo=algo)
         assert np.array_equal(got, np.where(mask > 0, want, 1))
     m.close()
@@ -152,9 +152,10 @@ def test_sift_full_size_properties(ctx):
     tc = m.match_counts(frames, algo=_lib.ALGO_TENSOR)
     tc1 = m.match_counts(frames, algo=_lib.ALGO_TENSOR_V1)
     tc2 = m.match_counts(frames, algo=_lib.ALGO_TENSOR_V2)
+    tc3 = m.match_counts(frames, algo=_lib.ALGO_TENSOR_V3)
     simt = m.match_counts(frames, algo=_lib.ALGO_SIMT)
     m.close()
-    assert np.array_equal(tc, simt) and np.array_equal(tc1, simt) and np.array_equal(tc2, simt)
+    assert np.array_equal(tc, simt) and np.array_equal(tc1, simt) and np.array_equal(tc2, simt) and np.array_equal(tc3, simt)
     for f in range(2):
         planted = (f * 7) % 6
         assert tc[f, planted] >= 0.9 * 512
