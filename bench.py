@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--images", type=int, default=LOC_PER_GPU * IMG_PER_LOC, help="map images per GPU")
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="0 = auto (about 10-20 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--algo", type=int, default=1, help="1 = sift_tc3 (product), 4 = sift_tc2, 3 = sift_tc, 2 = SIMT")
+    ap.add_argument("--algo", type=int, default=1, help="1 = sift_tc4 (product), 5 = sift_tc3, 4 = sift_tc2, 3 = sift_tc, 2 = SIMT")
     ap.add_argument("--opt1", type=int, default=0, help="libmcl diagnostic option 1")
     return ap.parse_args()
 
@@ -316,7 +316,7 @@ def main():
         i8_rate, _ = ctx.microbench(0, 4000)
         peak = i8_rate / 1e12
         roofline = {
-            "bound": "tensor", "kernel": "sift_tc3_kernel (tcgen05.mma kind::i8 u8xu8->s32, queries in TMEM, norm-sorted map tiles, fused bracketed top-2 epilogue)",
+            "bound": "tensor", "kernel": "sift_tc4_kernel (tcgen05.mma kind::i8 u8xu8->s32 128x128x32, queries in TMEM, norm-sorted map tiles, fused bracketed top-2 epilogue)",
             "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak,
             "peak_source": "int8 tensor pipe measured live in this run (mcl_microbench: back-to-back tcgen05.mma kind::i8 "
                            "128x128x32 on all SMs); MEASURED_PEAKS.json (%s) carries no int8 figure" % pk["src"],
@@ -328,9 +328,9 @@ def main():
             "fixup_ms_per_step": fix_ms / steps_prof, "repair_ms_per_step": simt_ms / steps_prof,
             "algorithmic_ops_per_unit": OPS_PER_UNIT, "units_per_step_per_gpu": n_frames * n_images,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default configuration, from the ncu --set full
-            # capture summarised in profiles/r1_sift_tc3_fullcfg_ncu.md (tensor-bound kernel: 0.15 % of the HBM peak)
-            "traffic": 241.6e6 if (n_frames == FRAMES and n_images == LOC_PER_GPU * IMG_PER_LOC and args.algo == 1) else None,
-            "traffic_unit": "bytes per launch (ncu, profiles/r1_sift_tc3_fullcfg_ncu.md)",
+            # capture summarised in profiles/r1_sift_tc4_ncu_full.md (tensor-bound kernel: 0.2 % of the HBM peak)
+            "traffic": 310.4e6 if (n_frames == FRAMES and n_images == LOC_PER_GPU * IMG_PER_LOC and args.algo == 1) else None,
+            "traffic_unit": "bytes per launch (ncu, profiles/r1_sift_tc4_ncu_full.md)",
         }
         cpu = None
         if not args.no_cpu_baseline:

@@ -37,7 +37,7 @@ keep = re.compile(r"^(gpu__time_duration.sum|dram__bytes_(read|write).sum$|dram_
                   r"sm__throughput.avg.pct|l1tex__throughput.avg.pct|lts__throughput.avg.pct)")
 with open("profiles/%s_ncu_full.md" % tag, "w") as f:
     f.write("# ncu --set full --clock-control none, one launch of the dominant kernel (%s)\n\n" % tag)
-    f.write("command: `python bench.py --steps 1 --warmup 1 --frames 48 --images 200 --no-cpu-baseline` (-k regex:sift_tc3 -s 1 -c 1)\n\n")
+    f.write("command: `python bench.py --steps 1 --warmup 1 --steps 1 --warmup 3 --no-cpu-baseline` at the default configuration (-k regex:sift_tc4 -s 1 -c 1)\n\n")
     f.write("| metric | unit | value |\n|---|---|---:|\n")
     for h, u, v in sorted(zip(hdr, units, vals)):
         if keep.match(h):
