@@ -105,11 +105,25 @@ class analyzer(object):
             m.setQuery(path)
             return m._query_descriptors(kind)
 
-        workers = max(1, min(len(imagePaths), int(os.environ.get("MCL_EXTRACT_THREADS", os.cpu_count() or 1))))
-        if workers == 1:
-            return [one(p) for p in imagePaths]
-        with ThreadPoolExecutor(max_workers=workers) as pool:
-            return list(pool.map(one, imagePaths))
+        def many(paths):
+            workers = max(1, min(len(paths), int(os.environ.get("MCL_EXTRACT_THREADS", os.cpu_count() or 1))))
+            if workers <= 1:
+                return [one(p) for p in paths]
+            with ThreadPoolExecutor(max_workers=workers) as pool:
+                return list(pool.map(one, paths))
+
+        # one process per GPU: the frames are dealt to the ranks, each extracts its share, descriptors are all-gathered
+        from .engine import _dist
+        d = _dist()
+        if d is None or d.get_world_size() == 1:
+            return many(imagePaths)
+        world, rank = d.get_world_size(), d.get_rank()
+        parts = [None] * world
+        d.all_gather_object(parts, many(imagePaths[rank::world]))
+        out = [None] * len(imagePaths)
+        for r in range(world):
+            out[r::world] = parts[r]
+        return out
 
     @staticmethod
     def _run_result(counts):
@@ -310,6 +324,10 @@ class analyzer(object):
 
     def writeProb(self, prob, filename, mode):
         ''' write out the probabilistic values to a txt file (reference analyze.py:351-356) '''
+        from .engine import _dist
+        d = _dist()
+        if d is not None and d.get_rank() != 0:
+            return   # one process per GPU: every rank holds the same lists, rank 0 writes the files
         file = open(filename, mode)
         for index in prob:
             file.write(str(index[0]) + '\n')

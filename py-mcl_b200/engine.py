@@ -39,6 +39,23 @@ def _dist():
     return None
 
 
+def sharded_apply(fn, items, group=None):
+    """[fn(x) for x in items], with the calls dealt round-robin to the ranks and the results all-gathered in order.
+    Used for cv2 extraction of the query frames, which is deterministic and the end-to-end bottleneck once matching runs
+    on the GPU: N ranks extract N times faster and every rank ends up with every frame's descriptors."""
+    d = _dist()
+    if d is None or d.get_world_size(group) == 1:
+        return [fn(x) for x in items]
+    world, rank = d.get_world_size(group), d.get_rank(group)
+    mine = [fn(x) for x in items[rank::world]]
+    parts = [None] * world
+    d.all_gather_object(parts, mine, group=group)
+    out = [None] * len(items)
+    for r in range(world):
+        out[r::world] = parts[r]
+    return out
+
+
 class ShardedMap(object):
     """All map images of all locations, flattened, with this rank's slice resident on its GPU."""
 

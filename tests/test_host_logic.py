@@ -120,6 +120,10 @@ assert np.array_equal(got_m, np.where(mask > 0, want, 1))
 assert want[0, 6] >= 20 and want[1, 2] >= 10
 # every rank holds a strict subset and only the counts travelled
 assert sm.hi - sm.lo < len(sizes)
+# extraction-style work dealt round-robin to the ranks, results gathered in order on every rank
+items = list(range(11))
+res = engine.sharded_apply(lambda i: (np.full((i % 3, 4), i, np.uint8) if i % 4 else None), items)
+assert len(res) == 11 and res[4] is None and res[5].shape == (2, 4) and int(res[10][0, 0]) == 10
 dist.barrier()
 if rank == 0:
     print("SHARD_OK", sm.bounds)
