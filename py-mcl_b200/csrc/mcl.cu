@@ -940,10 +940,11 @@ int match_device(mcl_map* m, mcl_queries* q, int mode, double ratio, const uint8
             if (mode != MCL_KNN2_RATIO) return fail(MCL_EINVAL, "SIFT supports mode MCL_KNN2_RATIO only");
             int use = algo;
             if (use == MCL_ALGO_AUTO) {
-                // tensor cores pay off once the tile pipeline has work for every SM; DOR masks (<= 30 of the images per
-                // frame) and single small frames go to the SIMT kernel, which skips masked pairs entirely
-                const double macs = (double)q->rows * (double)m->rows;
-                use = (d_mask || macs < 4.0e6) ? MCL_ALGO_SIMT : MCL_ALGO_TENSOR;
+                // measured (scripts/latency_probe.py): the tensor-core path wins even for one 150-row frame against 25 small
+                // images (93 us vs 122 us).  Only DOR-masked calls on small problems go to the SIMT kernel, which skips the
+                // masked pairs (<= 30 of 175 images per frame) instead of matching everything and masking afterwards.
+                const double pairs = (double)q->rows * (double)m->rows;
+                use = (d_mask && pairs < 2.0e7) ? MCL_ALGO_SIMT : MCL_ALGO_TENSOR;
             }
             if (use == MCL_ALGO_TENSOR_V2 && !m->ext_ok) use = MCL_ALGO_TENSOR_V1;  // norm range too wide for the K extension
             if (use == MCL_ALGO_TENSOR) {
