@@ -46,7 +46,8 @@ enum { MCL_ALGO_AUTO = 0, MCL_ALGO_TENSOR = 1 /* tcgen05, A in tensor memory, no
 int mcl_init(int device_id, mcl_ctx** out);
 void mcl_shutdown(mcl_ctx* ctx);
 const char* mcl_last_error(void);
-/* info[0]=SM count, [1]=cc major, [2]=cc minor, [3]=HBM MiB, [4]=max SM clock kHz, [5]=L2 bytes */
+/* info[0]=SM count, [1]=cc major, [2]=cc minor, [3]=HBM MiB, [4]=max SM clock kHz, [5]=L2 bytes, [6]=opt-in smem bytes,
+ * [7]=whole-image exact rescans done by the SIFT fix-up kernels so far (statistics) */
 int mcl_device_info(mcl_ctx* ctx, int64_t info[8]);
 int mcl_sync(mcl_ctx* ctx);
 /* pinned host memory for the end-to-end path (cudaHostAlloc) */

@@ -166,7 +166,7 @@ class Context:
         a = (C.c_int64 * 8)()
         _check(self._lib.mcl_device_info(self._h, a), "mcl_device_info")
         return {"sm_count": a[0], "cc": (a[1], a[2]), "hbm_mib": a[3], "sm_clock_khz": a[4], "l2_bytes": a[5],
-                "smem_optin": a[6]}
+                "smem_optin": a[6], "sift_rescans": a[7]}
 
     def sync(self):
         _check(self._lib.mcl_sync(self._h), "mcl_sync")

@@ -330,7 +330,12 @@ extern "C" int mcl_device_info(mcl_ctx* c, int64_t info[8]) {
     info[4] = clk;
     info[5] = c->prop.l2CacheSize;
     info[6] = (int64_t)c->prop.sharedMemPerBlockOptin;
-    info[7] = 0;
+    {   // statistics: exact whole-image rescans done by the SIFT fix-up kernels since mcl_init
+        unsigned int r = 0;
+        cudaStreamSynchronize(c->stream);
+        cudaMemcpy(&r, c->flags.as<unsigned int>() + 3, 4, cudaMemcpyDeviceToHost);
+        info[7] = r;
+    }
     return MCL_OK;
 }
 

@@ -401,7 +401,7 @@ __global__ void sift_fixup2_kernel(const int4* __restrict__ cand, const unsigned
         if (cd.z < 0) {  // the image has no other group
             verdict = k2 > INT_MIN && ratio_pass(Q - k1, Q - k2, ratio);
         } else {
-            const int lo = 2 * cd.z - key_c, hi = lo + 1;  // the best key of the other groups is lo or hi
+            const int lo = min(2 * cd.z - key_c, Q), hi = min(lo + 1, Q);  // the best key of the other groups is lo or hi (no key exceeds Q)
             if (hi <= k2) {
                 verdict = ratio_pass(Q - k1, Q - k2, ratio);
             } else {

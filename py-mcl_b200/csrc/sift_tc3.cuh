@@ -121,12 +121,14 @@ __global__ void build_meta_kernel(const int32_t* __restrict__ m_norm, const int3
 // ------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void finalize_image(const Params& p, int lane, bool row_valid, int Q, int64_t qrow, int H1, int H2,
-                                            int L2, int pos, int img, int nval, const Chunk& ch) {
+__device__ __noinline__ void finalize_image(const Params& p, int lane, bool row_valid, int Q, int64_t qrow, int H1, int L1,
+                                            int H2, int L2, int pos, int img, int nval, const Chunk& ch) {
     bool pass = false;
     if (row_valid && nval >= 2 && img >= ch.img_begin && img < ch.img_end) {
         const int d0lo = max(0, Q - H1);                       // smallest possible best distance^2
-        const int d1hi = L2 <= NONE ? (1 << 30) : Q - L2;      // largest possible second-best distance^2
+        // G1 holds a row with key >= L1 and some other tile a row with key >= L2, so the second-best key of the image is
+        // at least min(L1, L2) (G1 is the tile with the largest UPPER bound; with wide brackets its own rows may be poor)
+        const int d1hi = L2 <= NONE ? (1 << 30) : Q - min(L1, L2);   // largest possible second-best distance^2
         pass = ratio_pass(d0lo, d1hi, p.ratio);
     }
     const unsigned bal = __ballot_sync(0xffffffffu, pass);
@@ -324,17 +326,17 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc3_kernel(const __grid_const
                     // both groups belong to one image (the common case): one 64-row bracket
                     join(max(g0, g1), c2.y, c2.z, t * GROUPS);
                     if (end_mask & 2) {
-                        finalize_image(p, lane, row_valid, Q, qrow, H1, H2, L2, pos, c0.y, c0.w, ch);
+                        finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.y, c0.w, ch);
                         H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
                     }
                 } else {
                     join(g0, c1.x, c1.z, t * GROUPS);
-                    finalize_image(p, lane, row_valid, Q, qrow, H1, H2, L2, pos, c0.x, c0.z, ch);
+                    finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.x, c0.z, ch);
                     H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
                     if (c0.y >= 0) {
                         join(g1, c1.y, c1.w, t * GROUPS + 1);
                         if (end_mask & 2) {
-                            finalize_image(p, lane, row_valid, Q, qrow, H1, H2, L2, pos, c0.y, c0.w, ch);
+                            finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.y, c0.w, ch);
                             H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
                         }
                     }
@@ -406,7 +408,9 @@ __global__ void sift_fixup3_kernel(const int4* __restrict__ cand, const unsigned
         }
         int k1, k2;
         warp_top2(max(va, vb), min(va, vb), k1, k2);
-        const int hi = cd.z, lo = cd.w;   // the best key of the other groups lies in [lo, hi]
+        // the best key of the other groups lies in [lo, hi]; no key exceeds Q (d^2 >= 0), and an unclamped upper bound
+        // would turn into a negative d^2 (NaN under sqrtf: the reading would silently count as a failed test)
+        const int hi = min(cd.z, Q), lo = min(cd.w, Q);
         bool verdict, decided = true;
         if (hi <= NONE) {                 // the image has no other group
             verdict = k2 > INT_MIN && ratio_pass(Q - k1, Q - k2, ratio);

@@ -166,18 +166,18 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
                     join(max(g0, g1), c2.y, c2.z, unit * 2);
                     if (end_mask & 2) {
                         const int4 c0 = rec[0];   // {img0, img1, nval0, nval1}
-                        sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, H2, L2, pos, c0.y, c0.w, ch);
+                        sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.y, c0.w, ch);
                         H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
                     }
                 } else {
                     const int4 c0 = rec[0], c1 = rec[1];   // c1 = {nmin0, nmin1, nmax0, nmax1}
                     join(g0, c1.x, c1.z, unit * 2);
-                    sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, H2, L2, pos, c0.x, c0.z, ch);
+                    sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.x, c0.z, ch);
                     H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
                     if (c0.y >= 0) {
                         join(g1, c1.y, c1.w, unit * 2 + 1);
                         if (end_mask & 2) {
-                            sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, H2, L2, pos, c0.y, c0.w, ch);
+                            sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.y, c0.w, ch);
                             H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
                         }
                     }

@@ -96,6 +96,36 @@ def test_sift_many_tiny_images_and_one_huge_image(ctx, algo):
     assert np.array_equal(got, want)
 
 
+def test_sift_adversarial_norm_spread_forces_exact_rescans(ctx):
+    """Rows whose norms vary by orders of magnitude inside every tile (so the tile brackets are useless) and many
+    near-threshold best/second pairs: the bracketed pre-filter cannot decide, the fix-up kernel must fall back to exact
+    whole-image rescans -- and the counts must still equal the exact SIMT kernel's and the oracle's."""
+    rng = np.random.default_rng(41)
+
+    def wild(n):
+        base = synth.sift_like(rng, n)
+        scale = rng.choice([0.05, 0.2, 0.5, 1.0], size=(n, 1))
+        return np.clip(np.rint(base * scale), 0, 255).astype(np.float32)
+
+    map_des = [wild(n) for n in (700, 90, 333, 64, 1500)]
+    frames = [wild(600), wild(257)]
+    # near-threshold structure: query rows that are convex mixtures of two map rows
+    for f, (i, n) in enumerate(((0, 300), (4, 200))):
+        a = map_des[i][rng.integers(0, len(map_des[i]), size=n)]
+        b = map_des[i][rng.integers(0, len(map_des[i]), size=n)]
+        w = rng.uniform(0.55, 0.75, size=(n, 1))
+        frames[f][:n] = np.clip(np.rint(w * a + (1 - w) * b), 0, 255)
+    before = ctx.info()["sift_rescans"]
+    m = _lib.MapIndex(ctx, "SIFT", map_des)
+    simt = m.match_counts(frames, algo=_lib.ALGO_SIMT)
+    for algo in (_lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V3, _lib.ALGO_TENSOR_V2, _lib.ALGO_TENSOR_V1):
+        assert np.array_equal(m.match_counts(frames, algo=algo), simt), algo
+    m.close()
+    assert np.array_equal(simt, oracle_counts(oracle.sift_pair_count, frames, map_des))
+    assert simt.sum() > 50
+    assert ctx.info()["sift_rescans"] > before, "the exact-rescan path was not exercised"
+
+
 def test_sift_ratio_known_answers(ctx, golden_dir):
     """The cv2 ratio semantics float(sqrtf(d0^2)) < 0.7*float(sqrtf(d1^2)) on the survey's integer pairs:
     build 1 query row and 2 map rows with exactly those squared distances."""
