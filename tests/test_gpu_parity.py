@@ -126,6 +126,45 @@ def test_sift_adversarial_norm_spread_forces_exact_rescans(ctx):
     assert ctx.info()["sift_rescans"] > before, "the exact-rescan path was not exercised"
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_sift_fuzz_all_generations_equal_exact_kernel(ctx, seed):
+    """Random shapes and data styles (SIFT-like, wildly scaled norms, low-entropy rows with many exact ties, copies,
+    mixtures near the ratio threshold): every tensor-core generation must equal the exact SIMT kernel, which itself is
+    checked against the oracle on a sample."""
+    rng = np.random.default_rng(1000 + seed)
+
+    def rows(n, style):
+        if style == 0:
+            return synth.sift_like(rng, n)
+        if style == 1:
+            return np.clip(np.rint(synth.sift_like(rng, n) * rng.choice([0.03, 0.1, 0.4, 1.0], size=(n, 1))), 0, 255).astype(np.float32)
+        if style == 2:
+            return (rng.integers(0, 3, size=(n, 128)) * rng.choice([1, 60, 127], size=(n, 1))).astype(np.float32)
+        return rng.integers(0, 256, size=(n, 128)).astype(np.float32)
+
+    n_img = int(rng.integers(1, 9))
+    map_des = [rows(int(rng.integers(0, 900)), int(rng.integers(0, 4))) for _ in range(n_img)]
+    map_des = [m if len(m) else None for m in map_des]
+    frames = [rows(int(rng.integers(1, 700)), int(rng.integers(0, 4))) for _ in range(int(rng.integers(1, 4)))]
+    for f in frames:   # plant copies / noisy copies / mixtures
+        src = [m for m in map_des if m is not None and len(m) >= 2]
+        if not src:
+            break
+        m = src[int(rng.integers(0, len(src)))]
+        n = min(len(f), len(m)) // 2
+        if n:
+            a, b = m[rng.integers(0, len(m), size=n)], m[rng.integers(0, len(m), size=n)]
+            w = rng.choice([1.0, 0.9, 0.7, 0.6, 0.5], size=(n, 1))
+            f[:n] = np.clip(np.rint(w * a + (1 - w) * b + rng.normal(0, rng.choice([0, 1, 4]), size=a.shape)), 0, 255)
+    mi = _lib.MapIndex(ctx, "SIFT", map_des)
+    exact = mi.match_counts(frames, algo=_lib.ALGO_SIMT)
+    for algo in (_lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V3, _lib.ALGO_TENSOR_V2, _lib.ALGO_TENSOR_V1):
+        assert np.array_equal(mi.match_counts(frames, algo=algo), exact), (seed, algo)
+    mi.close()
+    f0 = frames[0]
+    assert np.array_equal(exact[0], [oracle.sift_pair_count(f0, m) for m in map_des])
+
+
 def test_sift_ratio_known_answers(ctx, golden_dir):
     """The cv2 ratio semantics float(sqrtf(d0^2)) < 0.7*float(sqrtf(d1^2)) on the survey's integer pairs:
     build 1 query row and 2 map rows with exactly those squared distances."""
