@@ -54,7 +54,9 @@ int mcl_sync(mcl_ctx* ctx);
 int mcl_host_alloc(size_t bytes, void** out);
 void mcl_host_free(void* p);
 /* tuning / diagnostic switches (development aid, no reference counterpart).  option 0: SIFT tensor-core kernel
- * epilogue variant, 0 = product, 1 = TMEM-read-only, 2 = max-only (1 and 2 give meaningless counts; profiling only). */
+ * epilogue variant, 0 = product, other values = profiling variants with meaningless counts; option 1 = 1: tile metadata from
+ * global memory; option 2 = 1: BOW word assignment on the float32 SIMT kernel only; option 3 = n > 0: cap the SIFT candidate
+ * list at n entries (tests: forces the overflow -> exact SIMT repair path). */
 int mcl_set_option(mcl_ctx* ctx, int option, int value);
 /* number of kernels this library launched since mcl_init (bench.py's gpu_launches) */
 int64_t mcl_launch_count(mcl_ctx* ctx);

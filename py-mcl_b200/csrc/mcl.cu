@@ -704,7 +704,8 @@ int launch_sift_tc(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, 
         CU(c->cand.ensure((size_t)want * sizeof(int4)));
         c->cand_cap_entries = (size_t)want;
     }
-    const int64_t cap = (int64_t)c->cand_cap_entries;
+    // option 3 (tests): cap the candidate list to force the overflow -> exact SIMT repair path
+    const int64_t cap = c->opt[3] > 0 ? std::min<int64_t>(c->opt[3], (int64_t)c->cand_cap_entries) : (int64_t)c->cand_cap_entries;
     int batch_qblocks = (int)std::max<int64_t>(1, cap * 4 / ((int64_t)std::max(1, m->n_images) * QBLK));
     batch_qblocks = std::min(batch_qblocks, n_qblocks_total);
     unsigned int* d_cand_count = c->flags.as<unsigned int>();
@@ -778,7 +779,8 @@ int launch_sift_tc2(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         CU(c->cand.ensure((size_t)want * sizeof(int4)));
         c->cand_cap_entries = (size_t)want;
     }
-    const int64_t cap = (int64_t)c->cand_cap_entries;
+    // option 3 (tests): cap the candidate list to force the overflow -> exact SIMT repair path
+    const int64_t cap = c->opt[3] > 0 ? std::min<int64_t>(c->opt[3], (int64_t)c->cand_cap_entries) : (int64_t)c->cand_cap_entries;
     int batch_qblocks = (int)std::max<int64_t>(1, cap * 4 / ((int64_t)std::max(1, m->n_images) * QBLK));
     batch_qblocks = std::min(batch_qblocks, n_qblocks_total);
     unsigned int* d_cand_count = c->flags.as<unsigned int>();
@@ -860,7 +862,8 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         CU(c->cand.ensure((size_t)want * sizeof(int4)));
         c->cand_cap_entries = (size_t)want;
     }
-    const int64_t cap = (int64_t)c->cand_cap_entries;
+    // option 3 (tests): cap the candidate list to force the overflow -> exact SIMT repair path
+    const int64_t cap = c->opt[3] > 0 ? std::min<int64_t>(c->opt[3], (int64_t)c->cand_cap_entries) : (int64_t)c->cand_cap_entries;
     int batch_qblocks = (int)std::max<int64_t>(1, cap * 4 / ((int64_t)std::max(1, m->n_images) * QBLK));
     batch_qblocks = std::min(batch_qblocks, n_qblocks_total);
     unsigned int* d_cand_count = c->flags.as<unsigned int>();

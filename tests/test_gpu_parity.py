@@ -165,6 +165,22 @@ def test_sift_fuzz_all_generations_equal_exact_kernel(ctx, seed):
     assert np.array_equal(exact[0], [oracle.sift_pair_count(f0, m) for m in map_des])
 
 
+def test_sift_candidate_overflow_is_repaired_on_the_device(ctx):
+    """A candidate list that is too small sets a device flag; the exact SIMT kernel then recomputes every count in the
+    same call (no host round trip, no error): results are unchanged."""
+    map_des, frames = synth.sift_map_and_frames(5, 6, 400, 3, 300)
+    m = _lib.MapIndex(ctx, "SIFT", map_des)
+    want = m.match_counts(frames, algo=_lib.ALGO_SIMT)
+    assert want.sum() > 200
+    ctx.set_option(3, 16)
+    try:
+        for algo in (_lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V3, _lib.ALGO_TENSOR_V2, _lib.ALGO_TENSOR_V1):
+            assert np.array_equal(m.match_counts(frames, algo=algo), want), algo
+    finally:
+        ctx.set_option(3, 0)
+    m.close()
+
+
 def test_sift_ratio_known_answers(ctx, golden_dir):
     """The cv2 ratio semantics float(sqrtf(d0^2)) < 0.7*float(sqrtf(d1^2)) on the survey's integer pairs:
     build 1 query row and 2 map rows with exactly those squared distances."""
