@@ -62,7 +62,7 @@ int mcl_set_option(mcl_ctx* ctx, int option, int value);
 int64_t mcl_launch_count(mcl_ctx* ctx);
 /* per-kernel device timing with CUDA events on the launching stream.  which: 0 = SIFT tensor-core kernel,
  * 1 = SIFT fix-up, 2 = ORB, 3 = SURF, 4 = BOW vq, 5 = BOW score, 6 = Laplacian, 7 = ingest (prep),
- * 8 = SIFT SIMT (dp4a) kernel, 9 = BOW vq tensor-core kernel, 10 = BOW float32 resolve kernel.
+ * 8 = SIFT SIMT (dp4a) kernel, 9 = BOW vq tensor-core kernel, 10 = BOW float32 resolve kernel, 11 = chi-squared kernel.
  * mcl_profile_read synchronises, returns accumulated milliseconds and launch count, and resets them. */
 int mcl_profile_enable(mcl_ctx* ctx, int on);
 int mcl_profile_read(mcl_ctx* ctx, int which, double* ms, int64_t* launches);
@@ -138,6 +138,26 @@ int mcl_laplacian_sums(mcl_ctx* ctx, int n, const uint8_t* const* imgs, const in
 enum { MCL_F_COMMAND = 1, MCL_F_PREV = 2, MCL_F_BLUR = 4, MCL_F_BEST = 8, MCL_F_ALL = 15 };
 int mcl_filter_step(mcl_ctx* ctx, int L, int I, int stages, char cmd, double blur, double* prev, const double* cur,
                     double* out, int* best);
+
+/* mcl_filter_step_typed: the same step when the lists hold numpy scalars as well as Python numbers, which is what the
+ * colour method produces (np.float32 from the float32 histograms; np.float64 from ndarray.var() in the blur weight,
+ * analyze.py:245-248 + :441-445).  Python's operators then follow numpy's scalar promotion -- float32 with a Python
+ * float stays float32 (the Python value is rounded to float32 first), anything with np.float64 is float64 -- and the
+ * kernel applies that rule to every multiply and add.  Values travel as float64 (float32 values are exact in it);
+ * prev_type / cur_type / out_type hold two tags per location row, [total, probabilities]; blur_type is the tag of `blur` (MCL_T_F64 for the
+ * reference's Laplacian); NULL type arrays mean MCL_T_PY, with which the result equals mcl_filter_step's. */
+enum { MCL_T_PY = 0, MCL_T_F64 = 1, MCL_T_F32 = 2 };
+int mcl_filter_step_typed(mcl_ctx* ctx, int L, int I, int stages, char cmd, double blur, int blur_type, double* prev,
+                          const int8_t* prev_type, const double* cur, const int8_t* cur_type, double* out,
+                          int8_t* out_type, int* best);
+
+/* mcl_chi2: the colour-histogram search (search.py:7-26 Searcher.search / chisquared, called from Matcher.colorSearch,
+ * Matcher.py:89-99): out[q * n_map + m] = 0.5 * sum_b (a_b - b_b)^2 / (a_b + b_b + eps) for every (query histogram,
+ * map histogram) pair, host pointers, row-major (n, bins) float32.  Arithmetic is float32 in numpy's pairwise-summation
+ * order, i.e. bit-identical to the reference's np.float32 results on float32 histograms (cv2.calcHist + normalize);
+ * the reference's eps is 1e-10.  bins = 512 (the reference's [8, 8, 8]) takes the warp-per-pair kernel. */
+int mcl_chi2(mcl_ctx* ctx, int n_q, int n_map, int bins, const float* q_hist, const float* map_hist, float eps,
+             float* out);
 
 /* ---- roofline denominators ------------------------------------------------------------------------------
  * MEASURED_PEAKS.json carries HBM GB/s and bf16 TFLOP/s only; the hot path is bounded by the int8 tensor pipe

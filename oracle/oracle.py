@@ -199,6 +199,68 @@ def bow_score_from_words(words, idf, im_features, num_words):
 
 
 # --------------------------------------------------------------------------------------------
+# colour histograms: chi-squared search (search.py:7-26) and run()'s colour branch (Matcher.py:328-336)
+# --------------------------------------------------------------------------------------------
+def chi2_literal(hist_a, hist_b, eps=1e-10):
+    """search.py:22-26 as written: a Python list of per-bin terms summed by np.sum.  With float32 histograms every
+    term is an np.float32 (the Python float eps is a weak scalar under NEP 50) and np.sum reduces a float32 array."""
+    return 0.5 * np.sum([((a - b) ** 2) / (a + b + eps) for (a, b) in zip(hist_a, hist_b)])
+
+
+def chi2_matrix(q_hists, m_hists, eps=1e-10):
+    """The same arithmetic for all (query, map) pairs, vectorised per pair: elementwise float32 ops give the same terms
+    and np.sum over the contiguous float32 row uses the same pairwise summation as np.sum of the list."""
+    q = np.asarray(q_hists, dtype=np.float32)
+    m = np.asarray(m_hists, dtype=np.float32)
+    e = np.float32(eps)
+    out = np.zeros((q.shape[0], m.shape[0]), dtype=np.float32)
+    for i in range(q.shape[0]):
+        for j in range(m.shape[0]):
+            a, b = m[j], q[i]
+            out[i, j] = np.float32(0.5) * np.sum(((a - b) ** 2) / (a + b + e))
+    return out
+
+
+def pairwise_sum_f32(x):
+    """numpy's float32 pairwise summation spelled out (blocks <= 128 with 8 interleaved accumulators, split points rounded
+    down to multiples of 8): the order of additions the CUDA kernel implements."""
+    x = np.asarray(x, dtype=np.float32)
+    n = len(x)
+    f = np.float32
+    if n < 8:
+        r = f(0)
+        for v in x:
+            r = f(r + v)
+        return r
+    if n <= 128:
+        r = [x[k] for k in range(8)]
+        i = 8
+        while i < n - (n % 8):
+            for k in range(8):
+                r[k] = f(r[k] + x[i + k])
+            i += 8
+        res = f(f(f(r[0] + r[1]) + f(r[2] + r[3])) + f(f(r[4] + r[5]) + f(r[6] + r[7])))
+        while i < n:
+            res = f(res + x[i])
+            i += 1
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return f(pairwise_sum_f32(x[:n2]) + pairwise_sum_f32(x[n2:]))
+
+
+def color_run(results, data_dir, ext=".png"):
+    """Matcher.run()'s colour branch (Matcher.py:328-336): results = sorted [(chi2, filename)]."""
+    total_chi = sum([r[0] for r in results])
+    total_matches = 300000. / total_chi
+    raw = [(data_dir + "/" + r[1], 200. / r[0]) for r in results]
+    total_prob = sum([x[1] for x in raw])
+    raw_matches = [(x[0], x[1] / total_prob * total_matches) for x in raw]
+    matches = sorted(raw_matches, key=lambda x: int(x[0].replace(ext, "").replace(data_dir + "/angle", "")))
+    return total_matches, [x[1] / total_matches for x in matches]
+
+
+# --------------------------------------------------------------------------------------------
 # Laplacian variance (analyze.py:441-445)
 # --------------------------------------------------------------------------------------------
 def laplacian_var(img):
@@ -291,7 +353,9 @@ def initial_probs(n_loc=7, n_img=25):
 # text formats (analyze.py:351-398)
 # --------------------------------------------------------------------------------------------
 def write_prob(prob, filename):
-    with open(filename, "w") as f:
+    # legacy print options: np.float32 list elements (colour method) print as plain numbers, the format the golden run
+    # used (ref_shims item 4) and the only one analyzer.readProb can parse back
+    with open(filename, "w") as f, np.printoptions(legacy="1.25"):
         for item in prob:
             f.write(str(item[0]) + "\n")
             f.write(str(item[1]) + "\n")

@@ -118,3 +118,75 @@ def opt_p(root, kind, w, h, orb_mode="knn", n_locations=7):
         blur_p.extend(adjusted)
         previous = adjusted
     return blur_p, best
+
+
+# ---- colour-histogram method (Matcher.py:67-99, search.py) -------------------------------------------------------
+def color_histogram(image, bins=(8, 8, 8)):
+    """Matcher.createHistogram (Matcher.py:67-74)."""
+    hist = cv2.calcHist([image], [0, 1, 2], None, list(bins), [0, 256, 0, 256, 0, 256])
+    hist = cv2.normalize(hist, hist, 0, 255, cv2.NORM_MINMAX)
+    return hist.flatten()
+
+
+def color_index(root, loc):
+    """Matcher.createColorIndex (Matcher.py:76-88): {filename: histogram} of one location."""
+    idx = {}
+    for pth in sorted(glob.glob(os.path.join(root, "map", str(loc), "*" + EXT))):
+        idx[os.path.basename(pth)] = color_histogram(cv2.imread(pth))
+    return idx
+
+
+def color_query(path, w, h):
+    """Matcher.setQuery (Matcher.py:48-51) followed by createHistogram of the filtered, resized frame."""
+    img = cv2.imread(path)
+    img = cv2.bilateralFilter(img, 9, 75, 75)
+    img = cv2.resize(img, (w, h))
+    return color_histogram(img)
+
+
+def color_location(qh, index, data_dir):
+    """colorSearch (Matcher.py:89-99 + search.py:7-20) and the colour branch of run()."""
+    results = sorted([(oracle.chi2_literal(feat, qh), name) for name, feat in index.items()])
+    return oracle.color_run(results, data_dir)
+
+
+def create_raw_p_color(root, w, h, n_locations=7):
+    """analyzer('Color').createRawP (analyze.py:64-96)."""
+    idx = [color_index(root, loc) for loc in range(n_locations)]
+    p = []
+    for fp in frame_paths(root):
+        qh = color_query(fp, w, h)
+        for loc in range(n_locations):
+            total, probs = color_location(qh, idx[loc], "map/" + str(loc))
+            p.append([total, probs])
+    return p
+
+
+def opt_p_color(root, w, h, n_locations=7):
+    """analyzer('Color').optP (analyze.py:148-232).  The colour branch of optRun ignores the angle window; run()'s
+    np.float32 values flow into the filter, whose Python operators then follow numpy's scalar promotion (float32 with
+    Python floats as weak scalars) exactly as in the reference."""
+    commands = read_commands(root)
+    idx = [color_index(root, loc) for loc in range(n_locations)]
+    previous = oracle.initial_probs(n_locations)
+    best_circle = None
+    blur_p, best = [], []
+    for fp in frame_paths(root):
+        qh = color_query(fp, w, h)
+        p = []
+        for loc in range(n_locations):
+            if best_circle is None or (best_circle - 2 <= loc <= best_circle + 2):
+                total, probs = color_location(qh, idx[loc], "map/" + str(loc))
+                p.append([total, probs])
+            else:
+                p.append([1, [1 / 75] * 25])
+        stem = os.path.basename(fp).replace(EXT, "")
+        # ndarray.var() returns np.float64 (a strong type): with blur <= 200 the blur weight promotes the float32 values
+        # to float64, with blur > 200 the weight is the Python float 0.85 and they stay float32
+        blur = np.float64(oracle.laplacian_var(cv2.imread(fp, 0)))
+        adjusted, bg = oracle.filter_step(commands[stem], previous, p, blur)
+        best_circle = bg[0]
+        best.append([bg[0], bg[1]])
+        blur_p.extend(adjusted)
+        previous = adjusted
+    return blur_p, best

@@ -24,7 +24,9 @@ What differs, on purpose
   * ORBMatch in the reference raises NameError (Matcher.py:194).  ``orb_mode='knn'`` (default) is 2-NN +
     ratio test; ``orb_mode='crosscheck'`` is the mutual-nearest-neighbour count the authors' older bytecode ran;
   * an image (or query) with fewer than 2 descriptors counts 0 instead of raising;
-  * 'Color' matching is out of scope and raises NotImplementedError.
+  * 'Color': histograms come from cv2.calcHist / cv2.normalize exactly as in the reference (Matcher.py:67-85); the
+    chi-squared search of a query against a whole colour index (search.py:7-26) is one GPU call (mcl_chi2) whose
+    float32 results equal the reference's bit for bit, so ``colorSearch`` / ``run`` return the same numbers.
 '''
 
 import glob
@@ -126,7 +128,56 @@ class Matcher(object):
         self._counts = None
 
     def setColorIndex(self, colorIndex):
-        raise NotImplementedError("colour-histogram matching is outside the accelerated hot path (SURVEY.md section 2)")
+        self.colorIndex = colorIndex
+
+    ############################
+    ### Color-Based Matching ###
+    ############################
+
+    def createHistogram(self, image, bins=[8, 8, 8]):
+        '''
+        Creates a flattened 3D histogram (reference Matcher.py:67-74; stays on cv2 so the inputs are identical).
+        '''
+        hist = cv2.calcHist([image], [0, 1, 2], None, bins, [0, 256, 0, 256, 0, 256])
+        hist = cv2.normalize(hist, hist, 0, 255, cv2.NORM_MINMAX)
+        return hist.flatten()
+
+    def createColorIndex(self):
+        '''
+        Creates dictionary with keys as image names and histograms as values (reference Matcher.py:76-88).
+        '''
+        index = {}
+        for imagePath in glob.glob(self.data + "/*" + extension):
+            filename = imagePath[imagePath.rfind("/") + 1:]
+            image = cv2.imread(imagePath)
+            index[filename] = self.createHistogram(image)
+        return index
+
+    def colorSearch(self):
+        '''
+        Searches query image against index; results are (chi-squared distance, image name) sorted ascending
+        (reference Matcher.py:89-99 + search.py:7-26).  All distances of the index come from one mcl_chi2 call.
+        '''
+        names = list(self.colorIndex.keys())
+        queryFeatures = self.createHistogram(self.image)
+        if not names:
+            return []
+        d = self._context().chi2(queryFeatures[None, :], np.stack([self.colorIndex[k] for k in names]))[0]
+        return sorted([(v, k) for (k, v) in zip(names, d)])
+
+    def _color_finish(self, results):
+        """The colour branch of run()/optRun() (reference Matcher.py:328-336, :377-385): distances are inverted into
+        weights and normalised.  The reference does this with np.float32 scalars, summing in ascending-distance order;
+        the same operations in the same order are kept so that the float32 roundings agree."""
+        chi = [d for d, _ in results]
+        totalMatches = 300000. / sum(chi)
+        inverse = [200. / d for d in chi]
+        norm = sum(inverse)
+        weight = {}
+        for (_, name), w in zip(results, inverse):
+            weight[name] = w / norm * totalMatches
+        by_angle = sorted(weight, key=lambda name: int(name.replace(extension, '').replace('angle', '')))
+        return totalMatches, [weight[name] / totalMatches for name in by_angle]
 
     #############################
     ### Bag-of-Words Matching ###
@@ -300,13 +351,14 @@ class Matcher(object):
         elif self.alg == 'BOW':
             score = self.BOWMatch(self.data + '.pkl')
             return 10 * np.max(score), score[0].tolist()
-        raise NotImplementedError("colour-histogram matching is outside the accelerated hot path")
+        return self._color_finish(self.colorSearch())
 
     def optRun(self, bestAngleIndex):
         if bestAngleIndex is None:
             return self.run()
         if self.alg == 'Color' or self.alg == 'BOW':
-            raise NotImplementedError("optRun supports SIFT / SURF / ORB (reference falls back to colorSearch here)")
+            # the reference takes the colour branch for both here (Matcher.py:377-385)
+            return self._color_finish(self.colorSearch())
         kind = self.alg if self.alg in ('SIFT', 'SURF') else 'ORB'
         window = angle_window(bestAngleIndex)
         paths = self._angle_paths()

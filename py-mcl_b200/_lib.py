@@ -19,10 +19,11 @@ U8, F32 = 0, 1
 KNN2_RATIO, CROSSCHECK = 0, 1
 ALGO_AUTO, ALGO_TENSOR, ALGO_SIMT, ALGO_TENSOR_V1, ALGO_TENSOR_V2, ALGO_TENSOR_V3 = 0, 1, 2, 3, 4, 5
 F_COMMAND, F_PREV, F_BLUR, F_BEST, F_ALL = 1, 2, 4, 8, 15
+T_PY, T_F64, T_F32 = 0, 1, 2
 KIND_BY_NAME = {"SIFT": SIFT, "ORB": ORB, "SURF": SURF}
 ROW_DIM = {SIFT: 128, ORB: 32, SURF: 64, BOWQ: 128}
 PROFILE_SLOTS = {"sift_tc": 0, "sift_fixup": 1, "orb": 2, "surf": 3, "bow_vq": 4, "bow_score": 5, "laplacian": 6,
-                 "ingest": 7, "sift_simt": 8, "bow_vq_tc": 9, "bow_resolve": 10}
+                 "ingest": 7, "sift_simt": 8, "bow_vq_tc": 9, "bow_resolve": 10, "chi2": 11}
 
 
 class MclError(RuntimeError):
@@ -64,6 +65,8 @@ SIGNATURES = {
     "mcl_laplacian_var": (C.c_int, [_p, C.c_int, C.POINTER(_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _p]),
     "mcl_laplacian_sums": (C.c_int, [_p, C.c_int, C.POINTER(_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _p]),
     "mcl_filter_step": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_char, C.c_double, _p, _p, _p, _p]),
+    "mcl_filter_step_typed": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_char, C.c_double, C.c_int, _p, _p, _p, _p, _p, _p, _p]),
+    "mcl_chi2": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p, C.c_float, _p]),
     "mcl_microbench": (C.c_int, [_p, C.c_int, C.c_int, _p]),
 }
 
@@ -247,6 +250,38 @@ class Context:
         _check(self._lib.mcl_filter_step(self._h, prev.shape[0], prev.shape[1] - 1, int(stages), c, float(blur),
                                          _ptr(prev), _ptr(cur), _ptr(out), _ptr(best)), "mcl_filter_step")
         return prev, out, (int(best[0]), int(best[1]))
+
+    def filter_step_typed(self, stages, cmd, blur, blur_type, prev, prev_type, cur, cur_type):
+        """filter_step on lists that hold numpy scalars (include/mcl.h: mcl_filter_step_typed).  *_type: (L, 2) int8 tags
+        [total, probabilities] per row (T_PY / T_F64 / T_F32).  Returns (prev, out, out_type, best)."""
+        prev = np.ascontiguousarray(prev, dtype=np.float64).copy()
+        cur = np.ascontiguousarray(cur, dtype=np.float64)
+        if prev.shape != cur.shape or prev.ndim != 2:
+            raise MclError("filter_step: prev/cur must both be (L, 1+I)")
+        pt = np.ascontiguousarray(prev_type, dtype=np.int8)
+        ct = np.ascontiguousarray(cur_type, dtype=np.int8)
+        if pt.shape != (prev.shape[0], 2) or ct.shape != pt.shape:
+            raise MclError("filter_step_typed: type tags must be (L, 2)")
+        out = np.zeros_like(prev)
+        ot = np.zeros_like(pt)
+        best = np.zeros(2, dtype=np.int32)
+        c = (cmd or "s").encode()[:1]
+        _check(self._lib.mcl_filter_step_typed(self._h, prev.shape[0], prev.shape[1] - 1, int(stages), c, float(blur),
+                                               int(blur_type), _ptr(prev), _ptr(pt), _ptr(cur), _ptr(ct), _ptr(out), _ptr(ot),
+                                               _ptr(best)), "mcl_filter_step_typed")
+        return prev, out, ot, (int(best[0]), int(best[1]))
+
+    def chi2(self, q_hist, map_hist, eps=1e-10):
+        """(n_q, bins) x (n_map, bins) float32 histograms -> (n_q, n_map) float32 chi-squared distances, bit-identical to
+        the reference's Searcher.chisquared (search.py:22-26) on float32 histograms."""
+        q = np.ascontiguousarray(q_hist, dtype=np.float32)
+        m = np.ascontiguousarray(map_hist, dtype=np.float32)
+        if q.ndim != 2 or m.ndim != 2 or q.shape[1] != m.shape[1]:
+            raise MclError("chi2: histograms must be (n, bins) with equal bins")
+        out = np.zeros((q.shape[0], m.shape[0]), dtype=np.float32)
+        _check(self._lib.mcl_chi2(self._h, q.shape[0], m.shape[0], q.shape[1], _ptr(q), _ptr(m), float(np.float32(eps)),
+                                  _ptr(out)), "mcl_chi2")
+        return out
 
 
 _default_ctx = None

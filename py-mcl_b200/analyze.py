@@ -15,6 +15,7 @@ shift / reweight update.  Keypoint extraction and image decode stay on cv2 so th
 '''
 
 import glob
+import os
 import time
 
 import cv2
@@ -40,6 +41,8 @@ class analyzer(object):
         self.commands = self.readCommand('commands.txt')
         self.bestGuess = []
         self.orb_mode = 'knn'
+        # optional binary side-car of rawP.txt (rawP.npz): processRaw then skips the text parse
+        self.sidecar = bool(os.environ.get('MCL_SIDECAR'))
         self._map = None
         self._ctx = None
 
@@ -59,7 +62,7 @@ class analyzer(object):
                 if self.method != 'Color':
                     self.indices[i] = matcher.createFeatureIndex()
                 else:
-                    raise NotImplementedError("colour-histogram matching is outside the accelerated hot path")
+                    self.indices[i] = matcher.createColorIndex()
         else:
             matcher.writeIndices()
         self._map = None
@@ -96,14 +99,19 @@ class analyzer(object):
         (Matcher.py:48-51 + the extractor call of *Match), on a thread pool: cv2 releases the GIL, extraction is
         deterministic and independent per frame, and it is the end-to-end bottleneck once matching runs on the GPU
         (SURVEY D5 / hard part 7).  Order is preserved."""
-        import os
-        from concurrent.futures import ThreadPoolExecutor
         kind = kind or self._kind()
 
         def one(path):
             m = Matcher(self.method, width=self.w, height=self.h)
             m.setQuery(path)
             return m._query_descriptors(kind)
+
+        return self._per_frame(one, imagePaths)
+
+    def _per_frame(self, one, imagePaths):
+        """[one(path) for path in imagePaths] on a thread pool, the frames dealt round-robin to the ranks of the job."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
 
         def many(paths):
             workers = max(1, min(len(paths), int(os.environ.get("MCL_EXTRACT_THREADS", os.cpu_count() or 1))))
@@ -112,7 +120,7 @@ class analyzer(object):
             with ThreadPoolExecutor(max_workers=workers) as pool:
                 return list(pool.map(one, paths))
 
-        # one process per GPU: the frames are dealt to the ranks, each extracts its share, descriptors are all-gathered
+        # one process per GPU: the frames are dealt to the ranks, each extracts its share, the results are all-gathered
         from .engine import _dist
         d = _dist()
         if d is None or d.get_world_size() == 1:
@@ -148,7 +156,20 @@ class analyzer(object):
         print('Matching...')
         frames = glob.glob('cam1_img' + '/*' + extension)
 
-        if self.method != 'BOW':
+        if self.method == 'Color':
+            # every frame's histogram against every location's colour index: one chi-squared call
+            def hist(path):
+                m = Matcher(self.method, width=self.w, height=self.h)
+                m.setQuery(path)
+                return m.createHistogram(m.image)
+
+            qh = self._per_frame(hist, frames)
+            every = list(range(self.numLocations))
+            per_frame = self._color_locations(matcher, qh, every) if frames else []
+            for imagePath, results in zip(frames, per_frame):
+                p.extend(results)
+                print('\t' + imagePath)
+        elif self.method != 'BOW':
             qdes = self._extract_many(frames)
             counts = self._resident_map().match_counts(qdes, mode=self._mode())
             for f, imagePath in enumerate(frames):
@@ -172,26 +193,51 @@ class analyzer(object):
             bow.close()
         self.rawP = p
         self.writeProb(p, 'rawP.txt', 'w')
+        if self.sidecar:
+            self.writeSidecar(p, 'rawP.txt', counts if self.method not in ('BOW', 'Color') else None)
 
         end = time.time()
         print('Time elapsed: %0.1f' % (end - start))
+
+    def _color_locations(self, matcher, query_hists, locs):
+        """For each query histogram, run()'s [total, probs] of every location in `locs` (the others get the DOR prior):
+        the chi-squared distances to all those locations' colour indices come from one mcl_chi2 call."""
+        names = dict((i, list(self.indices[i].keys())) for i in locs)
+        stacked = [self.indices[i][k] for i in locs for k in names[i]]
+        chi = self._context().chi2(np.stack(query_hists), np.stack(stacked))
+        out = []
+        for f in range(len(query_hists)):
+            results, col = [], 0
+            for i in range(self.numLocations):
+                if i not in names:
+                    results.append([1, [1/75] * 25])
+                    continue
+                matcher.setDirectory('map/' + str(i))
+                d = chi[f, col:col + len(names[i])]
+                col += len(names[i])
+                totalMatches, probL = matcher._color_finish(sorted([(v, k) for (k, v) in zip(names[i], d)]))
+                results.append([totalMatches, probL])
+            out.append(results)
+        return out
 
     def _filter(self, command, previousProbs, p, blurFactor):
         """accountCommand -> prevWeight -> probUpdate -> best guess in one kernel (mcl_filter_step).
         Reproduces the reference's aliasing: the command shift is written back into the SAME inner lists of
         previousProbs (analyze.py:317-335 mutate a shallow copy)."""
-        prev = np.array([[c[0]] + list(c[1]) for c in previousProbs], dtype=np.float64)
-        cur = np.array([[c[0]] + list(c[1]) for c in p], dtype=np.float64)
-        prev2, out, best = self._context().filter_step(_lib.F_ALL, command, float(blurFactor), prev, cur)
-        if command == 'l' or command == 'r':
-            for circles, row in zip(previousProbs, prev2):
-                circles[1] = row[1:].tolist()
-        elif command == 'f':
-            for circles, row, old in zip(previousProbs, prev2, prev):
-                if row[0] != old[0]:
-                    circles[0] = float(row[0])
-        adjusted = [[float(row[0]), row[1:].tolist()] for row in out]
+        prev2, adjusted, best = self._stage(_lib.F_ALL, previousProbs, p, blurFactor, command)
+        self._write_back(command, previousProbs, prev2)
         return adjusted, best
+
+    @staticmethod
+    def _write_back(command, lists, shifted):
+        """accountCommand's in-place effects on the caller's lists: rotated probability lists, one bumped total."""
+        if command == 'l' or command == 'r':
+            for circles, row in zip(lists, shifted):
+                circles[1] = row[1]
+        elif command == 'f':
+            for circles, row in zip(lists, shifted):
+                if row[0] != circles[0]:
+                    circles[0] = row[0]
 
     def processRaw(self):
         """
@@ -202,7 +248,9 @@ class analyzer(object):
             previousProbs.append([1, [1/75] * 25])
 
         start = time.time()
-        probDict = self.readProb('rawP.txt')
+        probDict = self.readSidecar('rawP.txt') if self.sidecar else None
+        if probDict is None:
+            probDict = self.readProb('rawP.txt')
         blurP = []
         frames = glob.glob('cam1_img' + '/*' + extension)
         blurs = self._laplacians(frames)
@@ -246,28 +294,34 @@ class analyzer(object):
         matcher = Matcher(self.method, width=self.w, height=self.h)
         start = time.time()
         print('Matching...')
-        resident = self._resident_map()
+        color = self.method == 'Color'
+        resident = None if color else self._resident_map()
         n_img = self.numLocations * 25
 
         for imagePath in glob.glob('cam1_img' + '/*' + extension):
-            des = self._extract(matcher, imagePath)
-            window = angle_window(bestAngleIndex) if bestAngleIndex is not None else [True] * 25
             if bestCircleIndex is None:
                 locs = list(range(self.numLocations))
             else:
                 lower = bestCircleIndex - 2
                 upper = bestCircleIndex + 2
                 locs = [i for i in range(self.numLocations) if i >= lower and i <= upper]
-            mask = np.zeros((1, n_img), dtype=np.uint8)
-            for i in locs:
-                mask[0, i * 25:(i + 1) * 25] = window
-            counts = resident.match_counts([des], mode=self._mode(), mask=mask, fill_value=1)[0]
-            p = []
-            for i in range(self.numLocations):
-                if i in locs:
-                    p.append(self._run_result(counts[i * 25:(i + 1) * 25]))
-                else:
-                    p.append([1, [1/75] * 25])
+            if color:
+                # the colour branch of optRun ignores the angle window (reference Matcher.py:377-385)
+                matcher.setQuery(imagePath)
+                p = self._color_locations(matcher, [matcher.createHistogram(matcher.image)], locs)[0]
+            else:
+                des = self._extract(matcher, imagePath)
+                window = angle_window(bestAngleIndex) if bestAngleIndex is not None else [True] * 25
+                mask = np.zeros((1, n_img), dtype=np.uint8)
+                for i in locs:
+                    mask[0, i * 25:(i + 1) * 25] = window
+                counts = resident.match_counts([des], mode=self._mode(), mask=mask, fill_value=1)[0]
+                p = []
+                for i in range(self.numLocations):
+                    if i in locs:
+                        p.append(self._run_result(counts[i * 25:(i + 1) * 25]))
+                    else:
+                        p.append([1, [1/75] * 25])
             print('\t' + imagePath)
 
             command = self.commands[imagePath.replace('cam1_img/', '').replace(extension, '')]
@@ -288,34 +342,64 @@ class analyzer(object):
     ### Probability Updating ###
     ############################
 
+    @staticmethod
+    def _tag(x):
+        if isinstance(x, np.float32):
+            return _lib.T_F32
+        if isinstance(x, np.float64):
+            return _lib.T_F64
+        return _lib.T_PY
+
+    @classmethod
+    def _pack(cls, lists):
+        """[[total, [p...]]...] -> (L, 1+I) float64 values + (L, 2) scalar-type tags [total, probabilities]."""
+        values = np.array([[c[0]] + list(c[1]) for c in lists], dtype=np.float64)
+        tags = np.array([[cls._tag(c[0]), cls._tag(c[1][0]) if len(c[1]) else _lib.T_PY] for c in lists], dtype=np.int8)
+        return values, tags
+
+    @staticmethod
+    def _unpack(values, tags):
+        """The inverse of _pack: Python floats, np.float64 or np.float32 scalars according to the tags."""
+        out = []
+        for row, (t0, t1) in zip(values, tags):
+            total = float(row[0]) if t0 == _lib.T_PY else (np.float32(row[0]) if t0 == _lib.T_F32 else np.float64(row[0]))
+            if t1 == _lib.T_PY:
+                probs = row[1:].tolist()
+            elif t1 == _lib.T_F32:
+                probs = list(row[1:].astype(np.float32))
+            else:
+                probs = list(row[1:])
+            out.append([total, probs])
+        return out
+
     def _stage(self, stages, previousP, currentP, blurFactor=0.0, command='s'):
-        prev = np.array([[c[0]] + list(c[1]) for c in previousP], dtype=np.float64)
-        cur = np.array([[c[0]] + list(c[1]) for c in currentP], dtype=np.float64)
-        return self._context().filter_step(stages, command, float(blurFactor), prev, cur)
+        """Runs the selected filter stages on the GPU.  Lists that hold only Python numbers take mcl_filter_step
+        (float64); lists with np.float32 values (colour method) take mcl_filter_step_typed, which applies numpy's scalar
+        promotion per operation like the reference's Python operators do.
+        Returns (previousP after the command, result lists, (bestCircle, bestAngle))."""
+        prev, pt = self._pack(previousP)
+        cur, ct = self._pack(currentP)
+        if not (pt == _lib.T_F32).any() and not (ct == _lib.T_F32).any():
+            prev2, out, best = self._context().filter_step(stages, command, float(blurFactor), prev, cur)
+            return self._unpack(prev2, pt), [[float(r[0]), r[1:].tolist()] for r in out], best
+        prev2, out, ot, best = self._context().filter_step_typed(stages, command, float(blurFactor), self._tag(blurFactor),
+                                                                  prev, pt, cur, ct)
+        return self._unpack(prev2, pt), self._unpack(out, ot), best
 
     def probUpdate(self, previousP, currentP, blurFactor):
         """Blur-proportional blend (reference analyze.py:239-276)."""
-        _, out, _ = self._stage(_lib.F_BLUR, previousP, currentP, blurFactor)
-        return [[float(r[0]), r[1:].tolist()] for r in out]
+        return self._stage(_lib.F_BLUR, previousP, currentP, blurFactor)[1]
 
     def prevWeight(self, previousP, currentP):
         """0.7 / 0.3 blend (reference analyze.py:278-310)."""
-        _, out, _ = self._stage(_lib.F_PREV, previousP, currentP)
-        return [[float(r[0]), r[1:].tolist()] for r in out]
+        return self._stage(_lib.F_PREV, previousP, currentP)[1]
 
     def accountCommand(self, command, previousP):
         """Shift particles according to the current command (reference analyze.py:312-336); mutates the inner
         lists of previousP like the reference's shallow copy does."""
-        prev = np.array([[c[0]] + list(c[1]) for c in previousP], dtype=np.float64)
-        prev2, _, _ = self._context().filter_step(_lib.F_COMMAND, command, 0.0, prev, prev)
+        prev2 = self._stage(_lib.F_COMMAND, previousP, previousP, 0.0, command)[0]
         copy = previousP[:]
-        if command == 'l' or command == 'r':
-            for circles, row in zip(copy, prev2):
-                circles[1] = row[1:].tolist()
-        elif command == 'f':
-            for circles, row, old in zip(copy, prev2, prev):
-                if row[0] != old[0]:
-                    circles[0] = float(row[0])
+        self._write_back(command, copy, prev2)
         return copy
 
     ###################################
@@ -329,10 +413,50 @@ class analyzer(object):
         if d is not None and d.get_rank() != 0:
             return   # one process per GPU: every rank holds the same lists, rank 0 writes the files
         file = open(filename, mode)
-        for index in prob:
-            file.write(str(index[0]) + '\n')
-            file.write(str(index[1]) + '\n')
+        # np.float32 list elements (colour method) must print as plain numbers or readProb cannot parse them back
+        with np.printoptions(legacy='1.25'):
+            for index in prob:
+                file.write(str(index[0]) + '\n')
+                file.write(str(index[1]) + '\n')
         file.close()
+
+    @staticmethod
+    def _text_digest(filename):
+        import hashlib
+        with open(filename, 'rb') as f:
+            return hashlib.sha256(f.read()).hexdigest()
+
+    def writeSidecar(self, prob, filename, counts=None):
+        """Binary twin of a probability file (no reference counterpart): <stem>.npz with the float64 values readProb
+        would parse out of the text (float(str(x)) of every number written), the raw int32 match counts when the method
+        has them, and the SHA-256 of the text file it mirrors.  Written by rank 0 only, like the text."""
+        from .engine import _dist
+        d = _dist()
+        if d is not None and d.get_rank() != 0:
+            return
+        L = self.numLocations
+        with np.printoptions(legacy='1.25'):
+            total = np.array([float(str(c[0])) for c in prob], dtype=np.float64).reshape(-1, L)
+            probs = np.array([[float(str(x)) for x in c[1]] for c in prob], dtype=np.float64)
+        probs = probs.reshape(total.shape[0], L, -1)
+        extra = {} if counts is None else {'counts': np.asarray(counts, dtype=np.int32)}
+        np.savez(filename[:filename.rfind('.')] + '.npz', total=total, probs=probs,
+                 text_sha256=np.array(self._text_digest(filename)), **extra)
+
+    def readSidecar(self, filename):
+        """{frame stem: [[total, [p...]] * numLocations]} from <stem>.npz -- the same dictionary readProb(filename) builds --
+        or None when there is no side-car or it does not belong to the text file on disk."""
+        path = filename[:filename.rfind('.')] + '.npz'
+        if not (os.path.isfile(path) and os.path.isfile(filename)):
+            return None
+        with np.load(path) as z:
+            if str(z['text_sha256']) != self._text_digest(filename) or z['total'].shape[1] != self.numLocations:
+                return None
+            total, probs = z['total'], z['probs']
+        probD = {}
+        for f in range(total.shape[0]):
+            probD[str(f).zfill(4)] = [[float(total[f, l]), probs[f, l].tolist()] for l in range(total.shape[1])]
+        return probD
 
     def readCommand(self, filename):
         '''reads the command list from the robot (reference analyze.py:358-365)'''
@@ -387,9 +511,9 @@ class analyzer(object):
         imgs = [cv2.imread(pth, 0) for pth in paths]
         if not imgs:
             return []
-        return [float(v) for v in self._context().laplacian_var(imgs)]
+        return [np.float64(v) for v in self._context().laplacian_var(imgs)]
 
     def Laplacian(self, imagePath):
         ''' blurriness factor: variance of the Laplacian (reference analyze.py:441-445); decode stays on cv2 '''
         img = cv2.imread(imagePath, 0)
-        return float(self._context().laplacian_var([img])[0])
+        return np.float64(self._context().laplacian_var([img])[0])   # ndarray.var() returns np.float64

@@ -247,9 +247,29 @@ __device__ int first_argmax(const double* v, int n) {
     return best;
 }
 
-__global__ void filter_step_kernel(int L, int I, int stages, int cmd, double blur, double* __restrict__ prev,
-                                   const double* __restrict__ cur, const double* __restrict__ fwd_factor,
-                                   double* __restrict__ out, int* __restrict__ best /* 2 */,
+// Typed scalars.  The reference's lists hold Python floats/ints, and -- for the colour method -- np.float32 values
+// (cv2 histograms -> float32 chi-squared distances) and np.float64 values (the blur weight derives from ndarray.var()).
+// Python's operators then follow numpy's scalar promotion: a Python float is a weak scalar (float32 op python -> float32,
+// the Python value rounded to float32 first), np.float64 is strong (anything op float64 -> float64).  Rows carry a tag and
+// every multiply / add below applies that rule, so the float32 roundings of the reference are reproduced exactly.  Two tags per row: [total, probabilities].
+enum { T_PY = 0, T_F64 = 1, T_F32 = 2 };
+struct TV { double v; int t; };
+__device__ __forceinline__ int t_promote(int a, int b) { return a == b ? a : ((a == T_F64 || b == T_F64) ? T_F64 : T_F32); }
+__device__ __forceinline__ TV t_mul(TV a, TV b) {
+    TV r; r.t = t_promote(a.t, b.t);
+    r.v = (r.t == T_F32) ? (double)__fmul_rn((float)a.v, (float)b.v) : __dmul_rn(a.v, b.v);
+    return r;
+}
+__device__ __forceinline__ TV t_add(TV a, TV b) {
+    TV r; r.t = t_promote(a.t, b.t);
+    r.v = (r.t == T_F32) ? (double)__fadd_rn((float)a.v, (float)b.v) : __dadd_rn(a.v, b.v);
+    return r;
+}
+
+__global__ void filter_step_kernel(int L, int I, int stages, int cmd, double blur, int blur_t, double* __restrict__ prev,
+                                   const signed char* __restrict__ prev_t, const double* __restrict__ cur,
+                                   const signed char* __restrict__ cur_t, const double* __restrict__ fwd_factor,
+                                   double* __restrict__ out, signed char* __restrict__ out_t, int* __restrict__ best /* 2 */,
                                    double* __restrict__ scratch /* L*(1+I) */) {
     const int S = 1 + I;
     const int n = L * S;
@@ -272,24 +292,33 @@ __global__ void filter_step_kernel(int L, int I, int stages, int cmd, double blu
             if (threadIdx.x == 0) {
                 const int bc = lex_argmax_rows(prev, L, S);
                 const int ba = first_argmax(prev + (size_t)bc * S + 1, I);
-                const double onep = __dadd_rn(1.0, fwd_factor[ba]);
-                if (bc < L - 1 && ba * 15 < 180 && ba > 0) prev[(size_t)(bc + 1) * S] = __dmul_rn(prev[(size_t)(bc + 1) * S], onep);
-                else if (bc > 0 && ba * 15 > 180 && ba * 15 < 360) prev[(size_t)(bc - 1) * S] = __dmul_rn(prev[(size_t)(bc - 1) * S], onep);
+                const TV onep = {__dadd_rn(1.0, fwd_factor[ba]), T_PY};
+                int row = -1;
+                if (bc < L - 1 && ba * 15 < 180 && ba > 0) row = bc + 1;
+                else if (bc > 0 && ba * 15 > 180 && ba * 15 < 360) row = bc - 1;
+                if (row >= 0) {
+                    const TV tot = {prev[(size_t)row * S], prev_t ? prev_t[2 * row] : T_PY};
+                    prev[(size_t)row * S] = t_mul(tot, onep).v;   // `*=` with a Python float keeps the row's type
+                }
             }
             __syncthreads();
         }
     }
     // ---- prevWeight then probUpdate
-    const double cw1 = 0.7, pw1 = 1 - 0.7;
-    const double cw2 = (blur > 200) ? 0.85 : __dmul_rn(__ddiv_rn(blur, 200.0), 0.85);
-    const double pw2 = __dsub_rn(1.0, cw2);
+    const TV cw1 = {0.7, T_PY}, pw1 = {1 - 0.7, T_PY};
+    const bool sharp = blur > 200;
+    const int wt = sharp ? T_PY : blur_t;   // 0.85 is a literal; blur/200*0.85 has the blur's type
+    const TV cw2 = {sharp ? 0.85 : __dmul_rn(__ddiv_rn(blur, 200.0), 0.85), wt};
+    const TV pw2 = {__dsub_rn(1.0, cw2.v), wt};
     if (stages & 6) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const double p = prev[i];
-            double x = cur[i];
-            if (stages & 2) x = __dadd_rn(__dmul_rn(cw1, x), __dmul_rn(pw1, p));
-            if (stages & 4) x = __dadd_rn(__dmul_rn(cw2, x), __dmul_rn(pw2, p));
-            out[i] = x;
+            const int l = i / S, k = i % S, slot = 2 * l + (k != 0);   // tags: [total, probabilities] per row
+            const TV p = {prev[i], prev_t ? prev_t[slot] : T_PY};
+            TV x = {cur[i], cur_t ? cur_t[slot] : T_PY};
+            if (stages & 2) x = t_add(t_mul(cw1, x), t_mul(pw1, p));
+            if (stages & 4) x = t_add(t_mul(cw2, x), t_mul(pw2, p));
+            out[i] = x.v;
+            if (out_t && k <= 1) out_t[slot] = (signed char)x.t;
         }
         __syncthreads();
     }

@@ -23,6 +23,7 @@
 #include "bow_lap_filter.cuh"
 #include "bow_tc.cuh"
 #include "kmeans.cuh"
+#include "color.cuh"
 #include "microbench.cuh"
 
 namespace {
@@ -46,7 +47,7 @@ int fail(int code, const char* fmt, ...) {
             return fail(MCL_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-enum { PROF_SIFT_TC = 0, PROF_SIFT_FIX, PROF_ORB, PROF_SURF, PROF_VQ, PROF_SCORE, PROF_LAP, PROF_PREP, PROF_SIFT_SIMT, PROF_VQ_TC, PROF_VQ_RESOLVE, PROF_N };
+enum { PROF_SIFT_TC = 0, PROF_SIFT_FIX, PROF_ORB, PROF_SURF, PROF_VQ, PROF_SCORE, PROF_LAP, PROF_PREP, PROF_SIFT_SIMT, PROF_VQ_TC, PROF_VQ_RESOLVE, PROF_CHI2, PROF_N };
 constexpr int QROW_PAD = 768;  // lcm of the two tensor-core kernels' query blocks (256, 384)
 
 // growable device scratch buffer (never shrinks; avoids cudaMalloc on the per-frame path)
@@ -87,7 +88,7 @@ struct mcl_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[PROF_N];
     // scratch
     DevBuf stage, cand, flags /* [0]=cand_count [1]=overflow [2]=bad [3]=rescans [4]=norm min [5]=norm max */, row_arg, bow_best, lap_pix, lap_meta, filt, tmp_counts,
-        tmp_mask, tmp_words, tmp_scores, tq_off, tq_desc, tq_norm, tq_frame, bow_q8, bow_qaux, bow_tc_out;
+        tmp_mask, tmp_words, tmp_scores, chi2, tq_off, tq_desc, tq_norm, tq_frame, bow_q8, bow_qaux, bow_tc_out;
     bool bowtc_attr = false;
     size_t cand_cap_entries = 0;
     bool tc_attr_set = false, tc2_attr_set = false;
@@ -1597,31 +1598,92 @@ extern "C" int mcl_laplacian_sums(mcl_ctx* c, int n, const uint8_t* const* imgs,
     return laplacian_common(c, n, imgs, h, w, stride, sums, nullptr);
 }
 
-extern "C" int mcl_filter_step(mcl_ctx* c, int L, int I, int stages, char cmd, double blur, double* prev, const double* cur,
-                               double* out, int* best) {
+namespace {
+int filter_step_common(mcl_ctx* c, int L, int I, int stages, char cmd, double blur, int blur_type, double* prev,
+                       const int8_t* prev_type, const double* cur, const int8_t* cur_type, double* out, int8_t* out_type,
+                       int* best) {
     if (!c || !prev || !cur || !out || !best) return fail(MCL_EINVAL, "mcl_filter_step: NULL argument");
     if (L <= 0 || I <= 0) return fail(MCL_EINVAL, "mcl_filter_step: L and I must be positive");
     if (stages <= 0 || stages > MCL_F_ALL) return fail(MCL_EINVAL, "mcl_filter_step: bad stages mask");
+    if (blur_type < 0 || blur_type > 2) return fail(MCL_EINVAL, "mcl_filter_step: bad blur type");
+    for (int l = 0; l < 2 * L; ++l)
+        if ((prev_type && (prev_type[l] < 0 || prev_type[l] > 2)) || (cur_type && (cur_type[l] < 0 || cur_type[l] > 2)))
+            return fail(MCL_EINVAL, "mcl_filter_step: row %d: type tag must be MCL_T_PY, MCL_T_F64 or MCL_T_F32", l / 2);
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const size_t n = (size_t)L * (1 + I);
-    // layout: prev | cur | out | scratch | factor (I) | best (2 ints)
-    const size_t total = (4 * n + I) * 8 + 16;
+    // layout: prev | cur | out | scratch | factor (I) | best (2 ints) | prev types | cur types | out types (2L bytes each)
+    const size_t total = (4 * n + I) * 8 + 16 + 6 * (size_t)L;
     CU(c->filt.ensure(total));
     double* d = c->filt.as<double>();
     double *d_prev = d, *d_cur = d + n, *d_out = d + 2 * n, *d_scr = d + 3 * n, *d_fac = d + 4 * n;
     int* d_best = reinterpret_cast<int*>(d_fac + I);
+    signed char* d_pt = reinterpret_cast<signed char*>(d_best + 4);
+    signed char *d_ct = d_pt + 2 * L, *d_ot = d_ct + 2 * L;
     std::vector<double> fac(I);
     for (int k = 0; k < I; ++k) fac[k] = 0.05 * std::fabs(std::sin((double)(k * 15 * 180) / M_PI));  // analyze.py:331 (sic)
     CU(cudaMemcpyAsync(d_prev, prev, n * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_cur, cur, n * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_fac, fac.data(), (size_t)I * 8, cudaMemcpyHostToDevice, st));
+    if (prev_type) CU(cudaMemcpyAsync(d_pt, prev_type, (size_t)2 * L, cudaMemcpyHostToDevice, st));
+    if (cur_type) CU(cudaMemcpyAsync(d_ct, cur_type, (size_t)2 * L, cudaMemcpyHostToDevice, st));
     c->launches++;
-    mcl::filter_step_kernel<<<1, 256, 0, st>>>(L, I, stages, (int)cmd, blur, d_prev, d_cur, d_fac, d_out, d_best, d_scr);
+    mcl::filter_step_kernel<<<1, 256, 0, st>>>(L, I, stages, (int)cmd, blur, blur_type, d_prev, prev_type ? d_pt : nullptr, d_cur,
+                                               cur_type ? d_ct : nullptr, d_fac, d_out, out_type ? d_ot : nullptr, d_best, d_scr);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(prev, d_prev, n * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(out, d_out, n * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(best, d_best, 8, cudaMemcpyDeviceToHost, st));
+    if (out_type) {
+        if (stages & 6) CU(cudaMemcpyAsync(out_type, d_ot, (size_t)2 * L, cudaMemcpyDeviceToHost, st));
+        else std::memset(out_type, 0, (size_t)2 * L);
+    }
+    CU(cudaStreamSynchronize(st));
+    return MCL_OK;
+}
+}  // namespace
+
+extern "C" int mcl_filter_step(mcl_ctx* c, int L, int I, int stages, char cmd, double blur, double* prev, const double* cur,
+                               double* out, int* best) {
+    return filter_step_common(c, L, I, stages, cmd, blur, 0, prev, nullptr, cur, nullptr, out, nullptr, best);
+}
+extern "C" int mcl_filter_step_typed(mcl_ctx* c, int L, int I, int stages, char cmd, double blur, int blur_type, double* prev,
+                                     const int8_t* prev_type, const double* cur, const int8_t* cur_type, double* out,
+                                     int8_t* out_type, int* best) {
+    return filter_step_common(c, L, I, stages, cmd, blur, blur_type, prev, prev_type, cur, cur_type, out, out_type, best);
+}
+
+extern "C" int mcl_chi2(mcl_ctx* c, int n_q, int n_map, int bins, const float* q_hist, const float* map_hist, float eps,
+                        float* out) {
+    if (!c) return fail(MCL_EINVAL, "mcl_chi2: NULL context");
+    if (n_q < 0 || n_map < 0 || bins <= 0) return fail(MCL_EINVAL, "mcl_chi2: negative size");
+    if (n_q == 0 || n_map == 0) return MCL_OK;
+    if (!q_hist || !map_hist || !out) return fail(MCL_EINVAL, "mcl_chi2: NULL argument");
+    if (n_q > 65535) return fail(MCL_EINVAL, "mcl_chi2: at most 65535 query histograms per call");
+    if ((int64_t)bins > (1 << 24)) return fail(MCL_EINVAL, "mcl_chi2: too many bins");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t qb = (size_t)n_q * bins * 4, mb = (size_t)n_map * bins * 4, ob = (size_t)n_q * n_map * 4;
+    const size_t o_m = (qb + 255) & ~(size_t)255, o_o = (o_m + mb + 255) & ~(size_t)255;
+    CU(c->chi2.ensure(o_o + ob));
+    uint8_t* d = c->chi2.as<uint8_t>();
+    CU(cudaMemcpyAsync(d, q_hist, qb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d + o_m, map_hist, mb, cudaMemcpyHostToDevice, st));
+    {
+        ProfScope ps(c, PROF_CHI2, st);
+        if (bins == 512) {
+            // n_q rows of CTAs; enough CTAs per row to fill the SMs a few times over when n_q is small
+            const int gx = grid_for(n_map, mcl::CHI2_WARPS, std::max(1, 4 * c->sm_count / n_q));
+            mcl::chi2_512_kernel<<<dim3(gx, n_q), mcl::CHI2_WARPS * 32, 0, st>>>((const float*)d, (const float*)(d + o_m), n_q, n_map,
+                                                                                eps, (float*)(d + o_o));
+        } else {
+            const long long pairs = (long long)n_q * n_map;
+            mcl::chi2_generic_kernel<<<(unsigned)((pairs + 127) / 128), 128, 0, st>>>((const float*)d, (const float*)(d + o_m), n_q,
+                                                                                     n_map, bins, eps, (float*)(d + o_o));
+        }
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d + o_o, ob, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return MCL_OK;
 }

@@ -180,3 +180,84 @@ def test_bow_index_and_match_through_the_matcher(in_dataset, ctx):
         assert np.allclose(score, score_ref, rtol=0, atol=2e-6)
     total, probs = m.run()
     assert total == 10 * np.max(score) and probs == score[0].tolist()
+
+
+def test_matcher_color_search_and_run_equal_the_reference(in_dataset, golden_dir, ctx):
+    """Matcher('Color'): createColorIndex / setColorIndex / colorSearch / run, against the reference's own values."""
+    if not _same_descriptors_as_golden(golden_dir):
+        pytest.skip("different OpenCV build than the golden run")
+    from pymcl_b200.Matcher import Matcher
+    g = np.load(os.path.join(golden_dir, "color_case.npz"))
+    m = Matcher("Color", width=VIEW[0], height=VIEW[1])
+    m.setDirectory("map/0")
+    index = m.createColorIndex()
+    m.setColorIndex(index)
+    assert sorted(index.keys()) == ["angle" + str(i).zfill(3) + ".png" for i in range(0, 375, 15)]
+    for f, frame in enumerate(sorted(glob.glob("cam1_img/*.png"))):
+        m.setQuery(frame)
+        assert np.array_equal(m.createHistogram(m.image), g["q"][f])
+        results = m.colorSearch()
+        assert [r[1] for r in results] == [n for _, n in sorted(zip(g["chi"][f, :25].tolist(), sorted(index.keys())))]
+        assert all(isinstance(r[0], np.float32) for r in results)
+        total, probs = m.run()
+        assert isinstance(total, np.float32) and total.tobytes() == g["run_total"][f].tobytes()
+        assert np.array_equal(np.asarray(probs, dtype=np.float32).view(np.uint32), g["run_probs"][f].view(np.uint32))
+        assert m.optRun(7) == (total, probs)      # the colour branch ignores the angle window (Matcher.py:377-385)
+
+
+def test_analyzer_color_files_byte_identical_to_reference(in_dataset, golden_dir, ctx):
+    if not _same_descriptors_as_golden(golden_dir):
+        pytest.skip("different OpenCV build than the golden run")
+    from pymcl_b200.analyze import analyzer
+    a = analyzer("Color", VIEW[0], VIEW[1])
+    a.createRawP()
+    assert open("rawP.txt").read() == open(os.path.join(golden_dir, "color_rawP.txt")).read()
+    a.processRaw()
+    assert open("out.txt").read() == open(os.path.join(golden_dir, "color_out.txt")).read()
+    assert open("bestGuess.txt").read() == open(os.path.join(golden_dir, "color_bestGuess.txt")).read()
+
+
+def test_analyzer_color_dor_byte_identical_to_reference(in_dataset, golden_dir, ctx):
+    """optP with the colour method: np.float32 results flow through the filter (mcl_filter_step_typed)."""
+    if not _same_descriptors_as_golden(golden_dir):
+        pytest.skip("different OpenCV build than the golden run")
+    from pymcl_b200.analyze import analyzer
+    a = analyzer("Color", VIEW[0], VIEW[1])
+    a.optP()
+    assert open("out.txt").read() == open(os.path.join(golden_dir, "color_dor_out.txt")).read()
+    assert open("bestGuess.txt").read() == open(os.path.join(golden_dir, "color_dor_bestGuess.txt")).read()
+
+
+def test_analyzer_color_matches_oracle_pipeline_whatever_the_opencv_build(in_dataset, ctx, tmp_path):
+    from pymcl_b200.analyze import analyzer
+    a = analyzer("Color", VIEW[0], VIEW[1])
+    a.createRawP()
+    raw = str(tmp_path / "rawP.txt")
+    oracle.write_prob(pipeline.create_raw_p_color(in_dataset, *VIEW), raw)
+    assert open("rawP.txt").read() == open(raw).read()
+    a = analyzer("Color", VIEW[0], VIEW[1])
+    a.optP()
+    blur_p, best = pipeline.opt_p_color(in_dataset, *VIEW)
+    out = str(tmp_path / "out.txt")
+    oracle.write_prob(blur_p, out)
+    assert open("out.txt").read() == open(out).read()
+    assert a.bestGuess == best
+
+
+def test_analyzer_sidecar_gives_the_same_files(in_dataset, golden_dir, ctx):
+    """processRaw fed from rawP.npz instead of the text parse writes the same out.txt / bestGuess.txt."""
+    from pymcl_b200.analyze import analyzer
+    a = analyzer("SIFT", VIEW[0], VIEW[1])
+    a.sidecar = True
+    a.createRawP()
+    z = np.load("rawP.npz")
+    assert z["counts"].shape == (6, 175) and z["counts"].dtype == np.int32
+    assert a.readSidecar("rawP.txt") == a.readProb("rawP.txt")
+    a.processRaw()
+    with_sidecar = (open("out.txt").read(), open("bestGuess.txt").read())
+    b = analyzer("SIFT", VIEW[0], VIEW[1])
+    b.processRaw()
+    assert (open("out.txt").read(), open("bestGuess.txt").read()) == with_sidecar
+    if _same_descriptors_as_golden(golden_dir):
+        assert with_sidecar[0] == open(os.path.join(golden_dir, "sift_out.txt")).read()
+    os.remove("rawP.npz")

@@ -541,3 +541,87 @@ def test_filter_forward_factor_table(ctx):
         p = np.array([[c[0]] + c[1] for c in prev])
         prev2, _, _ = ctx.filter_step(_lib.F_COMMAND, "f", 0.0, p, p)
         assert prev2[1, 0] == 1.0 * (1 + oracle.forward_factor(k))
+
+
+def _typed_state(rng, L, I, kinds):
+    """Rows whose scalars are Python floats, np.float64 or np.float32 (what the colour method feeds the filter)."""
+    rows = []
+    for l in range(L):
+        k = kinds[l % len(kinds)]
+        conv = {"py": float, "f64": np.float64, "f32": np.float32}[k]
+        rows.append([conv(rng.integers(1, 400) + rng.random()), [conv(v) for v in rng.random(I)]])
+    return rows
+
+
+def _tags(rows):
+    def t(x):
+        return _lib.T_F32 if isinstance(x, np.float32) else (_lib.T_F64 if isinstance(x, np.float64) else _lib.T_PY)
+    return np.array([[t(r[0]), t(r[1][0])] for r in rows], dtype=np.int8)
+
+
+@pytest.mark.parametrize("kinds_prev,kinds_cur", [(("py",), ("f32",)), (("f32",), ("f32", "py")), (("f64",), ("f32", "py")),
+                                                  (("f32", "py", "f64"), ("py", "f32", "f32", "f64"))])
+def test_filter_step_typed_follows_numpy_scalar_promotion(ctx, kinds_prev, kinds_cur):
+    """The reference's filter is plain Python operators over lists; with np.float32 / np.float64 elements (colour method)
+    every multiply and add follows numpy's promotion rules.  The oracle is those operators; the kernel must give the same
+    values AND the same result types, bit for bit."""
+    import copy
+    L, I = 7, 25
+    rng = np.random.default_rng(len(kinds_prev) * 10 + len(kinds_cur))
+    for trial in range(20):
+        prev = _typed_state(rng, L, I, kinds_prev)
+        cur = _typed_state(rng, L, I, kinds_cur)
+        cmd = "lrfbs"[trial % 5]
+        blur = [np.float64(0.0), np.float64(37.5), np.float64(199.999), np.float64(200.1), 913.2, 12.25][trial % 6]
+        if cmd == "f":
+            bc = 0 if trial % 2 else L - 1
+            prev[bc][0] = type(prev[bc][0])(1000.0)
+            prev[bc][1][3 if trial % 2 else 20] = type(prev[bc][1][0])(2.0)
+        o_prev = copy.deepcopy(prev)
+        adj, best = oracle.filter_step(cmd, o_prev, cur, blur)
+        p = np.array([[c[0]] + c[1] for c in prev], dtype=np.float64)
+        c = np.array([[x[0]] + x[1] for x in cur], dtype=np.float64)
+        bt = _lib.T_F64 if isinstance(blur, np.float64) else _lib.T_PY
+        prev2, out, ot, gbest = ctx.filter_step_typed(_lib.F_ALL, cmd, float(blur), bt, p, _tags(prev), c, _tags(cur))
+        want = np.array([[a[0]] + a[1] for a in adj], dtype=np.float64)
+        assert np.array_equal(out, want), (cmd, blur, trial)
+        assert np.array_equal(ot, _tags(adj)), (cmd, blur, trial)
+        assert np.array_equal(prev2, np.array([[a[0]] + a[1] for a in o_prev], dtype=np.float64))
+        assert gbest == tuple(best)
+
+
+# ------------------------------------------------------------------------------------------------
+# colour histograms: chi-squared search
+# ------------------------------------------------------------------------------------------------
+def test_chi2_equals_reference_searcher_bitwise(ctx, golden_dir):
+    g = np.load(os.path.join(golden_dir, "color_case.npz"))
+    got = ctx.chi2(g["q"], g["m"])
+    assert got.dtype == np.float32
+    assert np.array_equal(got.view(np.uint32), g["chi"].view(np.uint32))
+
+
+@pytest.mark.parametrize("bins", [1, 5, 8, 9, 64, 127, 128, 129, 200, 511, 512, 513, 1000, 4096])
+def test_chi2_any_bin_count_follows_numpy_pairwise_order(ctx, bins):
+    rng = np.random.default_rng(bins)
+    q = (rng.random((5, bins)) * 255).astype(np.float32)
+    m = (rng.random((9, bins)) * 255).astype(np.float32)
+    m[0] = q[0]                      # identical histograms: distance 0
+    q[1] = 0
+    m[1] = 0                         # empty bins on both sides: 0 / eps = 0, not NaN
+    m[2, ::3] = 0
+    got = ctx.chi2(q, m)
+    want = oracle.chi2_matrix(q, m)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert got[0, 0] == 0 and got[1, 1] == 0
+
+
+def test_chi2_large_batch_and_empty(ctx):
+    rng = np.random.default_rng(8)
+    hist = lambda n: np.floor(rng.gamma(0.5, 40.0, size=(n, 512))).clip(0, 255).astype(np.float32)
+    q, m = hist(40), hist(700)
+    got = ctx.chi2(q, m)
+    want = oracle.chi2_matrix(q, m)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert ctx.chi2(q[:0], m).shape == (0, 700) and ctx.chi2(q, m[:0]).shape == (40, 0)
+    with pytest.raises(_lib.MclError):
+        ctx.chi2(q, m[:, :100])

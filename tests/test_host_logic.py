@@ -38,8 +38,56 @@ def test_analyzer_signature():
     sig = inspect.signature(analyzer.__init__)
     assert list(sig.parameters)[:4] == ["self", "method", "width", "height"]
     for name in ("createIndex", "createRawP", "processRaw", "optP", "probUpdate", "prevWeight", "accountCommand",
-                 "writeProb", "readProb", "readCommand", "readBestGuess", "Laplacian"):
+                 "writeProb", "readProb", "readCommand", "readBestGuess", "Laplacian", "writeSidecar", "readSidecar"):
         assert callable(getattr(analyzer, name))
+
+
+def test_matcher_color_host_logic_equals_oracle(golden_dir):
+    """The colour branch of run() (float32 scalar arithmetic in ascending-distance order) against the oracle restatement
+    and the reference's own numbers; createHistogram / setColorIndex / createColorIndex exist with the reference's names."""
+    g = np.load(os.path.join(golden_dir, "color_case.npz"))
+    names = ["angle" + str(i).zfill(3) + ".png" for i in range(0, 375, 15)]
+    m = Matcher("Color", width=160, height=120)
+    m.setDirectory("map/0")
+    for f in range(len(g["q"])):
+        results = sorted([(v, k) for k, v in zip(names, g["chi"][f, :25])])
+        total, probs = m._color_finish(results)
+        want_total, want_probs = oracle.color_run(results, "map/0")
+        assert type(total) is np.float32 and total.tobytes() == np.float32(want_total).tobytes()
+        assert [p.tobytes() for p in probs] == [p.tobytes() for p in want_probs]
+        assert total.tobytes() == g["run_total"][f].tobytes()
+    for name in ("createHistogram", "createColorIndex", "setColorIndex", "colorSearch"):
+        assert callable(getattr(Matcher, name))
+
+
+def test_sidecar_round_trips_what_readprob_parses(tmp_path, monkeypatch):
+    """rawP.npz: the dictionary it yields equals readProb() of the text it mirrors -- for integer counts,
+    float32 values (colour / BOW) and Python floats -- and it is ignored once the text changes."""
+    from pymcl_b200.analyze import analyzer
+    monkeypatch.chdir(tmp_path)
+    open("commands.txt", "w").write("0000 s\n")
+    a = analyzer("SIFT", 160, 120, numLocations=3)
+    rng = np.random.default_rng(4)
+    p = []
+    for f in range(4):
+        counts = rng.integers(0, 50, size=(3, 25))
+        for l in range(3):
+            if f == 0:
+                p.append(a._run_result(counts[l]))
+            elif f == 1:
+                v = rng.random(25).astype(np.float32)
+                p.append([np.float32(10) * v.max(), list(v)])
+            elif f == 2:
+                p.append([1, [1 / 75] * 25])
+            else:
+                p.append([float(rng.random() * 1e-7), list(rng.random(25) * 1e5)])
+    a.writeProb(p, "rawP.txt", "w")
+    assert a.readSidecar("rawP.txt") is None
+    a.writeSidecar(p, "rawP.txt", counts=np.zeros((4, 75), np.int32))
+    assert a.readSidecar("rawP.txt") == a.readProb("rawP.txt")
+    assert np.load("rawP.npz")["counts"].shape == (4, 75)
+    open("rawP.txt", "a").write("1\n[1.0]\n")
+    assert a.readSidecar("rawP.txt") is None
 
 
 def test_pack_descriptors():

@@ -105,6 +105,54 @@ def test_pipeline_orb_rawp_byte_identical(dataset, golden_dir, tmp_path, mode, t
     assert open(raw).read() == open(os.path.join(golden_dir, tag + "_rawP.txt")).read()
 
 
+def test_color_chi2_restatements_equal_the_reference_searcher(golden_dir):
+    """search.py's chisquared on float32 histograms: the literal restatement, the vectorised one and the spelled-out
+    pairwise summation order (what the CUDA kernel implements) all give the reference's np.float32 bit for bit."""
+    g = np.load(os.path.join(golden_dir, "color_case.npz"))
+    q, m, chi = g["q"], g["m"], g["chi"]
+    assert chi.dtype == np.float32 and chi.shape == (len(q), len(m)) and q.shape[1] == 512
+    assert np.array_equal(oracle.chi2_matrix(q, m).view(np.uint32), chi.view(np.uint32))
+    e = np.float32(1e-10)
+    for i, j in [(0, 0), (1, 30), (3, 99), (5, 174)]:
+        lit = oracle.chi2_literal(m[j], q[i])
+        assert isinstance(lit, np.float32) and lit.tobytes() == chi[i, j].tobytes()
+        terms = ((m[j] - q[i]) ** 2) / (m[j] + q[i] + e)
+        assert (np.float32(0.5) * oracle.pairwise_sum_f32(terms)).tobytes() == chi[i, j].tobytes()
+    # the pairwise order for lengths that are not 512 (tails, sub-8, odd splits), against numpy itself
+    rng = np.random.default_rng(11)
+    for n in (1, 5, 8, 9, 64, 127, 128, 129, 200, 511, 513, 1000, 4096):
+        x = (rng.random(n, dtype=np.float32) * 1000).astype(np.float32)
+        assert oracle.pairwise_sum_f32(x).tobytes() == np.sum(x).tobytes(), n
+
+
+def test_color_run_matches_reference_matcher(golden_dir):
+    g = np.load(os.path.join(golden_dir, "color_case.npz"))
+    names = ["angle" + str(i).zfill(3) + ".png" for i in range(0, 375, 15)]
+    for f in range(len(g["q"])):
+        results = sorted([(v, k) for k, v in zip(names, g["chi"][f, :25])])
+        total, probs = oracle.color_run(results, "map/0")
+        assert np.float32(total).tobytes() == g["run_total"][f].tobytes()
+        assert np.array_equal(np.asarray(probs, dtype=np.float32).view(np.uint32), g["run_probs"][f].view(np.uint32))
+
+
+def test_pipeline_color_byte_identical(dataset, golden_dir, tmp_path):
+    p = pipeline.create_raw_p_color(dataset, *VIEW)
+    raw = str(tmp_path / "rawP.txt")
+    oracle.write_prob(p, raw)
+    assert open(raw).read() == open(os.path.join(golden_dir, "color_rawP.txt")).read()
+    blur_p, best = pipeline.process_raw(dataset, raw)
+    out, bg = str(tmp_path / "out.txt"), str(tmp_path / "bestGuess.txt")
+    oracle.write_prob(blur_p, out)
+    oracle.write_prob(best, bg)
+    assert open(out).read() == open(os.path.join(golden_dir, "color_out.txt")).read()
+    assert open(bg).read() == open(os.path.join(golden_dir, "color_bestGuess.txt")).read()
+    blur_p, best = pipeline.opt_p_color(dataset, *VIEW)
+    oracle.write_prob(blur_p, out)
+    oracle.write_prob(best, bg)
+    assert open(out).read() == open(os.path.join(golden_dir, "color_dor_out.txt")).read()
+    assert open(bg).read() == open(os.path.join(golden_dir, "color_dor_bestGuess.txt")).read()
+
+
 # ---- (b) the third-party routines themselves ----------------------------------------------------
 def test_l2_restatement_equals_cv2_bfmatcher():
     rng = np.random.default_rng(0)
