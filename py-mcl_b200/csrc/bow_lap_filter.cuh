@@ -132,13 +132,25 @@ __global__ void __launch_bounds__(256) bow_score_kernel(
 
 // ------------------------------------------------------------------------------------------
 // variance of the Laplacian (analyze.py:441-445): 4-neighbour kernel, BORDER_REFLECT_101, population var.
-// HBM-bound by nature (one byte per pixel).  Each thread owns a 16-pixel-wide column block over LAP_RY rows and slides a
-// three-row window down it: one aligned 128-bit load per row (rows are stored with a 16-byte pitch), each row unpacked
-// to ints once and used three times from registers; ~6 integer instructions per pixel.  Exact integer sums
-// (sum L in s64, sum L^2 in u64; per-thread partials fit 32 bits).
-// grid = (ceil(W/1024), ceil(H/(4*LAP_RY)), n_images), block = (64, 4).
+// One byte of HBM traffic per pixel, so the instruction count per pixel decides whether the kernel can follow HBM:
+// at 6.5 TB/s the SMs have ~5.6 issue slots per pixel.  The arithmetic is therefore done on PAIRS of pixels held as two
+// 16-bit lanes of one register (every intermediate is non-negative and < 2^16, so plain 32-bit adds never carry across
+// the lanes):
+//     P[j]  = (px[2j], px[2j+1])                      one PRMT per pair, per row, reused as up / mid / down row
+//     Q[j]  = (px[2j-1], px[2j])                      one PRMT per pair of the mid row (odd-aligned pairs)
+//     Lb[j] = upP + dnP + Q[j] + Q[j+1] + 1020 - 4*midP     two IADD3 + one IMAD per pair;  Lb = L + 1020 in [0, 2040]
+// then one lane extraction and one IMAD per pixel for sum Lb^2.  sum L needs no per-pixel work at all: the stencil's
+// coefficients add up to zero, so the sum over the image telescopes to the two outermost rows and columns
+// (laplacian_finish_kernel), which also removes the bias exactly: sum Lb = sum L + 1020 N,
+// sum L^2 = sum Lb^2 - 2040 sum Lb + 1020^2 N.  ~4.6 instructions per pixel instead of ~12 for the scalar form.
+// A thread owns a 16-pixel-wide column block (one aligned 128-bit load per row; rows are stored with a 16-byte pitch)
+// over LAP_RY rows; the two halo pixels come from the neighbouring lanes by shuffle (byte loads only at warp edges).
+// Threads are numbered (row strip, column block) within an image so that no lane idles on widths like 800 = 50 * 16.
+// grid = (ceil(strips * col_blocks / 256), n_images), block = 256.
 // ------------------------------------------------------------------------------------------
-constexpr int LAP_RY = 16;
+constexpr int LAP_RY = 16;   // rows per thread
+constexpr int LAP_PF = 4;    // rows loaded per batch (loads in flight per thread)
+constexpr uint32_t LAP_BIAS = 1020u | (1020u << 16);
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
@@ -148,74 +160,174 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 }
 
 struct LapRow {
-    int px[16];
-    int lh, rh;  // the pixels left of px[0] and right of px[15] (already border-reflected)
+    uint32_t p[8];    // p[j] = px[2j] | px[2j+1] << 16
+    uint32_t lh, rh;  // pixel left of px[0] / right of px[15] (border-reflected), as plain integers
 };
 
-__device__ __forceinline__ void lap_load_row(const uint8_t* __restrict__ img, int pitch, int W, int y, int x0, LapRow& r) {
-    const uint8_t* row = img + (int64_t)y * pitch;
-    const uint4 v = *reinterpret_cast<const uint4*>(row + x0);
+__device__ __forceinline__ void lap_unpack(const uint4& v, LapRow& r) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int i = 0; i < 16; ++i) r.px[i] = (int)((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
-    r.lh = x0 > 0 ? (int)row[x0 - 1] : (W > 1 ? r.px[1] : r.px[0]);
-    r.rh = x0 + 16 < W ? (int)row[x0 + 16] : 0;  // only read when the block's last pixel has an in-image right neighbour
+    for (int i = 0; i < 4; ++i) {
+        r.p[2 * i] = __byte_perm(w[i], 0u, 0x4140);
+        r.p[2 * i + 1] = __byte_perm(w[i], 0u, 0x4342);
+    }
+}
+
+// lane extraction on the FMA pipe (IMAD.HI) instead of a shift on the ALU pipe, which carries most of this kernel's work
+__device__ __forceinline__ uint32_t lap_hi16(uint32_t x) {
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, 65536;" : "=r"(r) : "r"(x));
+    return r;
+}
+// MASKED: the image width is not a multiple of 16, i.e. the last column block has pixels outside the image
+template <bool MASKED>
+__device__ __forceinline__ void lap_body(const uint8_t* __restrict__ img, int H, int W, int pitch, uint32_t& s2) {
+    const int CB = (W + 15) >> 4, NS = (H + LAP_RY - 1) / LAP_RY;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool active = t < CB * NS;
+    const int strip = active ? t / CB : NS - 1, cb = active ? t % CB : CB - 1;
+    const int x0 = cb * 16, ys = strip * LAP_RY;
+    const int k = MASKED ? min(16, W - x0) : 16;    // valid pixels of this column block
+    const bool from_left = cb > 0 && lane > 0;      // lane-1 holds the column block to the left, same rows
+    const bool from_right = cb < CB - 1 && lane < 31;
+    const bool load_left = cb > 0 && lane == 0, load_right = cb < CB - 1 && lane == 31;   // halo not in a neighbouring lane
+
+    uint32_t m[8];   // MASKED: which lanes of each pair are pixels of the image
+    if (MASKED) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = (2 * j + 1 < k) ? 0xffffffffu : (2 * j < k ? 0x0000ffffu : 0u);
+    }
+
+    // rows are clamped into the image: rows past the strip's end are loaded (harmlessly) but never accumulated.
+    // issue(): the loads only, so that a batch of rows is in flight before anything waits on one of them;
+    // halo(): the neighbour pixels, from the adjacent lanes' words where possible
+    auto issue = [&](int y, uint4& v, uint32_t& bl, uint32_t& br) {
+        const uint8_t* row = img + (int64_t)min(max(y, 0), H - 1) * pitch;
+        v = *reinterpret_cast<const uint4*>(row + x0);
+        bl = 0;
+        br = 0;
+        if (load_left) bl = row[x0 - 1];
+        if (load_right) br = row[x0 + 16];
+    };
+    auto halo = [&](const uint4& v, uint32_t bl, uint32_t br, uint32_t& lh, uint32_t& rh) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, v.w, 1), dn = __shfl_down_sync(0xffffffffu, v.x, 1);
+        lh = from_left ? up >> 24 : bl;
+        rh = from_right ? dn & 0xffu : br;
+        if (cb == 0) lh = W > 1 ? (v.x >> 8) & 0xffu : v.x & 0xffu;   // REFLECT_101: pixel -1 mirrors pixel 1
+        if (cb == CB - 1) rh = (v.w >> 16) & 0xffu;                   // k == 16: pixel W mirrors pixel W-2 (else patched below)
+    };
+    auto finish_row = [&](const uint4& v, uint32_t lh, uint32_t rh, LapRow& r) {
+        lap_unpack(v, r);
+        r.lh = lh;
+        r.rh = rh;
+        if (MASKED && k < 16) {  // pixel k (the first one outside the image) mirrors pixel k-2
+            const int kj = k >> 1;
+            const uint32_t lm = (k & 1) ? 0xffff0000u : 0x0000ffffu;
+#pragma unroll
+            for (int j = 1; j < 8; ++j)
+                if (j == kj) r.p[j] = (r.p[j] & ~lm) | (r.p[j - 1] & lm);
+            if (k == 1) r.p[0] = (r.p[0] & 0xffffu) | ((W > 1 ? lh : (r.p[0] & 0xffffu)) << 16);
+        }
+    };
+
+    LapRow up, mid, dn;
+    {
+        uint4 v0, v1;
+        uint32_t bl0, br0, bl1, br1, l0, r0, l1, r1;
+        issue(reflect101(ys - 1, H), v0, bl0, br0);
+        issue(ys, v1, bl1, br1);
+        halo(v0, bl0, br0, l0, r0);
+        halo(v1, bl1, br1, l1, r1);
+        finish_row(v0, l0, r0, up);
+        finish_row(v1, l1, r1, mid);
+    }
+#pragma unroll 1
+    for (int g = 0; g < LAP_RY / LAP_PF; ++g) {
+        uint4 v[LAP_PF];
+        uint32_t bl[LAP_PF], br[LAP_PF], lh[LAP_PF], rh[LAP_PF];
+#pragma unroll
+        for (int r = 0; r < LAP_PF; ++r) {
+            const int y = ys + g * LAP_PF + r;   // the row whose Laplacian this step computes; loads row y+1
+            issue(y + 1 < H ? y + 1 : reflect101(y + 1, H), v[r], bl[r], br[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < LAP_PF; ++r) halo(v[r], bl[r], br[r], lh[r], rh[r]);
+#pragma unroll
+        for (int r = 0; r < LAP_PF; ++r) {
+            const int y = ys + g * LAP_PF + r;
+            finish_row(v[r], lh[r], rh[r], dn);
+            uint32_t q[9];
+            q[0] = __byte_perm(mid.lh, mid.p[0], 0x5410);
+#pragma unroll
+            for (int j = 1; j < 8; ++j) q[j] = __byte_perm(mid.p[j - 1], mid.p[j], 0x5432);
+            q[8] = __byte_perm(mid.p[7], mid.rh, 0x5432);
+            uint32_t rs2 = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t qq = q[j] + q[j + 1] + LAP_BIAS;
+                uint32_t lb = up.p[j] + dn.p[j] + qq;
+                lb -= 4u * mid.p[j];
+                if (MASKED) lb &= m[j];
+                const uint32_t lo = lb & 0xffffu, hi = lap_hi16(lb);
+                rs2 += lo * lo;
+                rs2 += hi * hi;
+            }
+            if (active && y < H) s2 += rs2;
+            up = mid;
+            mid = dn;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) laplacian_sums_kernel(const uint8_t* __restrict__ pixels,
                                                              const int64_t* __restrict__ img_off,
                                                              const int* __restrict__ pitches,
                                                              const int* __restrict__ hs, const int* __restrict__ ws,
-                                                             long long* __restrict__ sums /* [n][2] */) {
-    const int im = blockIdx.z;
-    const int H = hs[im], W = ws[im], pitch = pitches[im];
-    const int x0 = (blockIdx.x * 64 + threadIdx.x) * 16;
-    const int ys = (blockIdx.y * 4 + threadIdx.y) * LAP_RY;
-    int s1 = 0;
-    unsigned s2 = 0;
-    if (x0 < W && ys < H) {
-        const uint8_t* img = pixels + img_off[im];
-        const int ye = min(H, ys + LAP_RY);
-        LapRow up, mid, dn;
-        lap_load_row(img, pitch, W, reflect101(ys - 1, H), x0, up);
-        lap_load_row(img, pitch, W, ys, x0, mid);
-        for (int y = ys; y < ye; ++y) {
-            lap_load_row(img, pitch, W, reflect101(y + 1, H), x0, dn);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int x = x0 + i;
-                const int left = i == 0 ? mid.lh : mid.px[i - 1];
-                int right = i == 15 ? mid.rh : mid.px[i + 1];
-                if (x == W - 1) right = W > 1 ? left : mid.px[i];  // REFLECT_101: the neighbour beyond the edge mirrors x-1
-                const int l = up.px[i] + dn.px[i] + left + right - 4 * mid.px[i];
-                if (x < W) {
-                    s1 += l;
-                    s2 += (unsigned)(l * l);
-                }
-            }
-            up = mid;
-            mid = dn;
-        }
-    }
-    long long t1 = s1;
+                                                             unsigned long long* __restrict__ sums /* [n][2]: -, sum Lb^2 */) {
+    const int im = blockIdx.y;
+    const int H = hs[im], W = ws[im];
+    uint32_t s2 = 0;   // per thread: <= 256 pixels * 2040^2 (1.07e9) fits 32 bits
+    if (W & 15) lap_body<true>(pixels + img_off[im], H, W, pitches[im], s2);
+    else lap_body<false>(pixels + img_off[im], H, W, pitches[im], s2);
     unsigned long long t2 = s2;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
-        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
-    }
-    if (threadIdx.x % 32 == 0 && (t1 != 0 || t2 != 0)) {
-        atomicAdd(reinterpret_cast<unsigned long long*>(&sums[2 * im]), (unsigned long long)t1);
-        atomicAdd(reinterpret_cast<unsigned long long*>(&sums[2 * im + 1]), t2);
-    }
+    for (int o = 16; o > 0; o >>= 1) t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    if ((threadIdx.x & 31) == 0 && t2 != 0) atomicAdd(&sums[2 * im + 1], t2);
 }
 
-__global__ void laplacian_var_kernel(const long long* __restrict__ sums, const int* __restrict__ hs,
-                                     const int* __restrict__ ws, int n, double* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per image.  sum L: with E the REFLECT_101 extension of the image I,
+//     sum_{y,x} (E(y-1,x) + E(y+1,x) - 2 I(y,x)) = sum_x  I(r(1),x) - I(0,x) + I(r(H-2),x) - I(H-1,x)      (telescoping in y)
+// and likewise in x, r() / c() being the reflected row / column index -- O(H + W) pixels.  Then the +1020 bias of the
+// main kernel is removed exactly (64-bit integers): sums[2i] = sum L, sums[2i+1] = sum L^2, and
+// var = (sum L^2 - (sum L)^2 / N) / N in float64 (the formula SURVEY 8(a) found to match ndarray.var() to 1 ulp).
+__global__ void __launch_bounds__(128) laplacian_finish_kernel(const uint8_t* __restrict__ pixels, const int64_t* __restrict__ img_off,
+                                                               const int* __restrict__ pitches, const int* __restrict__ hs,
+                                                               const int* __restrict__ ws, int n, long long* __restrict__ sums,
+                                                               double* __restrict__ out) {
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= n) return;
-    const double N = (double)hs[i] * (double)ws[i];
-    const double s1 = (double)sums[2 * i], s2 = (double)sums[2 * i + 1];
+    const int H = hs[i], W = ws[i], pitch = pitches[i];
+    const uint8_t* img = pixels + img_off[i];
+    const uint8_t *r0 = img, *r1 = img + (int64_t)reflect101(1, H) * pitch, *r2 = img + (int64_t)reflect101(H - 2, H) * pitch,
+                  *r3 = img + (int64_t)(H - 1) * pitch;
+    const int c1 = reflect101(1, W), c2 = reflect101(W - 2, W), c3 = W - 1;
+    int acc = 0;   // |acc| <= 2 * 255 * (H + W) / 32 per lane
+    for (int x = lane; x < W; x += 32) acc += (int)r1[x] - (int)r0[x] + (int)r2[x] - (int)r3[x];
+    for (int y = lane; y < H; y += 32) {
+        const uint8_t* row = img + (int64_t)y * pitch;
+        acc += (int)row[c1] - (int)row[0] + (int)row[c2] - (int)row[c3];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane != 0) return;
+    const long long cnt = (long long)H * (long long)W;
+    const long long l1 = acc;
+    const long long b1 = l1 + 1020LL * cnt, b2 = sums[2 * i + 1];
+    const long long l2 = b2 - 2040LL * b1 + 1020LL * 1020LL * cnt;
+    sums[2 * i] = l1;
+    sums[2 * i + 1] = l2;
+    const double N = (double)cnt, s1 = (double)l1, s2 = (double)l2;
     out[i] = __ddiv_rn(__dsub_rn(s2, __ddiv_rn(__dmul_rn(s1, s1), N)), N);
 }
 

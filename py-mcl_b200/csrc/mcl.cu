@@ -1567,20 +1567,20 @@ int laplacian_common(mcl_ctx* c, int n, const uint8_t* const* imgs, const int* h
     CU(cudaMemcpyAsync(mb + o_p, pitch.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(mb + o_s, 0, (size_t)n * 16, st));
     {
-        dim3 grid((max_w + 1023) / 1024, (max_h + 4 * mcl::LAP_RY - 1) / (4 * mcl::LAP_RY), n);
+        const int64_t threads = (int64_t)((max_w + 15) / 16) * ((max_h + mcl::LAP_RY - 1) / mcl::LAP_RY);
+        dim3 grid((unsigned)((threads + 255) / 256), n);
         ProfScope ps(c, PROF_LAP, st);
-        mcl::laplacian_sums_kernel<<<grid, dim3(64, 4), 0, st>>>(c->lap_pix.as<uint8_t>(), (const int64_t*)mb,
-                                                                 (const int*)(mb + o_p), (const int*)(mb + o_h),
-                                                                 (const int*)(mb + o_w), (long long*)(mb + o_s));
+        mcl::laplacian_sums_kernel<<<grid, 256, 0, st>>>(c->lap_pix.as<uint8_t>(), (const int64_t*)mb, (const int*)(mb + o_p),
+                                                         (const int*)(mb + o_h), (const int*)(mb + o_w),
+                                                         (unsigned long long*)(mb + o_s));
     }
     CU(cudaGetLastError());
-    if (var_out) {
-        c->launches++;
-        mcl::laplacian_var_kernel<<<(n + 127) / 128, 128, 0, st>>>((const long long*)(mb + o_s), (const int*)(mb + o_h),
-                                                                   (const int*)(mb + o_w), n, (double*)(mb + o_v));
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(var_out, mb + o_v, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    }
+    c->launches++;
+    mcl::laplacian_finish_kernel<<<(n + 3) / 4, 128, 0, st>>>(c->lap_pix.as<uint8_t>(), (const int64_t*)mb, (const int*)(mb + o_p),
+                                                              (const int*)(mb + o_h), (const int*)(mb + o_w), n,
+                                                              (long long*)(mb + o_s), (double*)(mb + o_v));
+    CU(cudaGetLastError());
+    if (var_out) CU(cudaMemcpyAsync(var_out, mb + o_v, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     if (sums_out) CU(cudaMemcpyAsync(sums_out, mb + o_s, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return MCL_OK;
