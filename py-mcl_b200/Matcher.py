@@ -220,8 +220,15 @@ class Matcher(object):
         joblib.dump((im_features, image_paths, idf, numWords, voc), trainingPath + ".pkl", compress=3)
 
     def writeIndices(self):
-        for mapp in glob.glob('map/*/'):
+        """Reference Matcher.py:143-145.  One process per GPU: the locations are dealt round-robin to the ranks (each index is
+        an independent k-means + histogram pass writing its own .pkl), then the ranks meet at a barrier."""
+        from .engine import _dist
+        d = _dist()
+        world, rank = (d.get_world_size(), d.get_rank()) if d is not None else (1, 0)
+        for mapp in sorted(glob.glob('map/*/'))[rank::world] if world > 1 else glob.glob('map/*/'):
             self.createIndex(mapp[:-1])
+        if world > 1:
+            d.barrier()
 
     def createFeatureIndex(self):
         '''

@@ -22,7 +22,7 @@ import cv2
 import numpy as np
 
 from . import _lib
-from .engine import ShardedMap
+from .engine import ShardedBow, ShardedMap
 from .Matcher import Matcher, angle_window
 
 extension = '.png'
@@ -178,13 +178,15 @@ class analyzer(object):
                 print('\t' + imagePath)
         else:
             import joblib
-            locs = []
-            for i in range(self.numLocations):
+
+            def load(i):
                 im_features, image_paths, idf, numWords, voc = joblib.load('map/' + str(i) + '.pkl')
-                locs.append((im_features, idf, voc))
-            bow = _lib.BowIndex(self._context(), locs, int(np.asarray(locs[0][0]).shape[1]))
+                return im_features, idf, voc
+
+            # locations (code book + index) are the unit of sharding; the float32 scores are all-gathered
+            bow = ShardedBow(self.numLocations, load, ctx=self._context())
             qdes = self._extract_many(frames, 'SIFT')
-            scores, _ = bow.score(qdes)
+            scores = bow.score(qdes)
             for f, imagePath in enumerate(frames):
                 for i in range(self.numLocations):
                     s = scores[f:f + 1, bow.img_off[i]:bow.img_off[i + 1]]

@@ -89,22 +89,80 @@ class ShardedMap(object):
 
     def gather(self, local):
         """all-gather of the per-image counts: local (F, hi-lo) -> (F, n_images)."""
-        if self.world == 1:
-            return local
-        import torch
+        return gather_columns(local, self.bounds, self.group)
+
+
+def gather_columns(local, bounds, group=None):
+    """The one data-path collective: every rank holds columns [lo, hi) = bounds[rank] of an (F, n) result; one
+    all_gather_into_tensor of the zero-padded slices gives every rank the full matrix (NCCL on the GPU, gloo in tests)."""
+    d = _dist()
+    world = d.get_world_size(group) if d else 1
+    if world == 1:
+        return local
+    import torch
+    F = local.shape[0]
+    maxw = max(h - l for l, h in bounds)
+    pad = np.zeros((F, maxw), dtype=local.dtype)
+    pad[:, :local.shape[1]] = local
+    t = torch.from_numpy(pad)
+    if d.get_backend(group) == "nccl":
+        t = t.cuda()
+    out = torch.empty((world * F, maxw), dtype=t.dtype, device=t.device)   # concatenation along dim 0
+    d.all_gather_into_tensor(out, t, group=group)
+    out = out.cpu().numpy().reshape(world, F, maxw)
+    full = np.empty((F, bounds[-1][1]), dtype=local.dtype)
+    for r, (l, h) in enumerate(bounds):
+        full[:, l:h] = out[r][:, :h - l]
+    return full
+
+
+class ShardedBow(object):
+    """Bag-of-words indices of all locations, with this rank's LOCATIONS resident on its GPU (a
+    location owns its code book + tf-idf index, so locations are the unit; the float32 scores are all-gathered).
+    `loader(i)` returns location i's (im_features, idf, voc) -- joblib.load of its .pkl -- and is only called for the
+    locations of this rank, so index loading is sharded too."""
+
+    def __init__(self, n_locations, loader, num_words=None, ctx=None, local_factory=None, group=None):
         d = _dist()
-        F = local.shape[0]
-        maxw = max(h - l for l, h in self.bounds)
-        pad = np.zeros((F, maxw), dtype=local.dtype)
-        pad[:, :local.shape[1]] = local
-        t = torch.from_numpy(pad)
-        cuda = d.get_backend(self.group) == "nccl"
-        if cuda:
-            t = t.cuda()
-        out = torch.empty((self.world * F, maxw), dtype=t.dtype, device=t.device)   # concatenation along dim 0
-        d.all_gather_into_tensor(out, t, group=self.group)
-        out = out.cpu().numpy().reshape(self.world, F, maxw)
-        full = np.empty((F, self.n_images), dtype=local.dtype)
-        for r, (l, h) in enumerate(self.bounds):
-            full[:, l:h] = out[r][:, :h - l]
-        return full
+        self.group = group
+        self.world = d.get_world_size(group) if d else 1
+        self.rank = d.get_rank(group) if d else 0
+        self.n_loc = int(n_locations)
+        self.loc_bounds = shard_bounds([1] * self.n_loc, self.world)
+        lo, hi = self.loc_bounds[self.rank]
+        mine = [loader(i) for i in range(lo, hi)]
+        counts = [int(np.asarray(m[0]).shape[0]) for m in mine]
+        widths = [int(np.asarray(m[0]).shape[1]) for m in mine]
+        if self.world > 1:
+            parts = [None] * self.world
+            d.all_gather_object(parts, (counts, widths), group=group)
+            counts = [c for part in parts for c in part[0]]
+            widths = [w for part in parts for w in part[1]]
+        if num_words is None:
+            num_words = widths[0] if widths else 0
+        self.W = int(num_words)
+        self.img_off = np.zeros(self.n_loc + 1, dtype=np.int64)
+        np.cumsum(counts, out=self.img_off[1:])
+        self.total_images = int(self.img_off[-1])
+        # column range of every rank in the (frames, total_images) score matrix
+        self.bounds = [(int(self.img_off[l]), int(self.img_off[h])) for l, h in self.loc_bounds]
+        if not mine:
+            self.local = None
+        elif local_factory is None:
+            self.local = _lib.BowIndex(ctx or _lib.default_context(), mine, self.W)
+        else:
+            self.local = local_factory(mine, self.W)
+
+    def close(self):
+        if self.local is not None and hasattr(self.local, "close"):
+            self.local.close()
+
+    def score(self, q_descs):
+        """(n_queries, total_images) float32 on every rank: BOWMatch of every query against every location."""
+        lo, hi = self.bounds[self.rank]
+        if self.local is None:
+            local = np.zeros((len(q_descs), 0), dtype=np.float32)
+        else:
+            local = self.local.score(q_descs)[0]
+        assert local.shape[1] == hi - lo
+        return gather_columns(local, self.bounds, self.group)

@@ -135,6 +135,50 @@ class OracleLocal(object):
         return out
 
 
+class OracleBow:
+    """Stands in for _lib.BowIndex on CPU: BOWMatch of every query against every location through the oracle."""
+
+    def __init__(self, locations, num_words):
+        self.locations = locations
+        self.W = num_words
+
+    def score(self, q_descs, want_words=False):
+        cols = sum(len(l[0]) for l in self.locations)
+        out = np.zeros((len(q_descs), cols), dtype=np.float32)
+        for f, q in enumerate(q_descs):
+            c = 0
+            for imf, idf, voc in self.locations:
+                if q is not None and len(q):
+                    words, _ = oracle.bow_words(np.asarray(q, np.float32), voc)
+                    out[f, c:c + len(imf)] = oracle.bow_score_from_words(words, idf, imf, self.W)[0]
+                c += len(imf)
+        return out, None
+
+
+def synthetic_bow_locations(seed, n_loc, W=40):
+    rng = np.random.default_rng(seed)
+    locs = []
+    for i in range(n_loc):
+        voc = synth.sift_like(rng, W - (i % 3)).astype(np.float32) + rng.random((W - (i % 3), 128)).astype(np.float32)
+        n_img = 3 + (i * 7) % 5
+        imf = rng.random((n_img, W)).astype(np.float32) * (rng.random((n_img, W)) < 0.3)
+        imf /= np.maximum(np.linalg.norm(imf, axis=1, keepdims=True), 1e-9)
+        idf = np.log((n_img + 1.0) / (rng.integers(0, n_img + 1, W) + 1.0)).astype(np.float32)
+        locs.append((imf.astype(np.float32), idf, voc))
+    return locs
+
+
+def test_sharded_bow_single_process_matches_unsharded():
+    locs = synthetic_bow_locations(1, 5)
+    rng = np.random.default_rng(2)
+    frames = [synth.sift_like(rng, 30), None, synth.sift_like(rng, 11)]
+    sb = engine.ShardedBow(len(locs), lambda i: locs[i], local_factory=OracleBow)
+    want = OracleBow(locs, 40).score(frames)[0]
+    got = sb.score(frames)
+    assert got.shape == (3, sum(len(l[0]) for l in locs)) and np.array_equal(got, want)
+    assert list(sb.img_off) == list(np.cumsum([0] + [len(l[0]) for l in locs]))
+
+
 def test_sharded_map_single_process_matches_unsharded():
     map_des, frames = synth.sift_map_and_frames(2, 9, 60, 3, 50)
     sm = engine.ShardedMap("SIFT", map_des, local_factory=OracleLocal)
@@ -148,7 +192,7 @@ sys.path.insert(0, {repo!r}); sys.path.insert(0, os.path.join({repo!r}, "oracle"
 import numpy as np, torch, torch.distributed as dist
 import pymcl_b200
 from pymcl_b200 import engine, synth
-from test_host_logic import OracleLocal
+from test_host_logic import OracleLocal, OracleBow, synthetic_bow_locations
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 sizes = [40, 0, 75, 33, 64, 1, 90, 55, 20, 61, 48]
@@ -172,9 +216,19 @@ assert sm.hi - sm.lo < len(sizes)
 items = list(range(11))
 res = engine.sharded_apply(lambda i: (np.full((i % 3, 4), i, np.uint8) if i % 4 else None), items)
 assert len(res) == 11 and res[4] is None and res[5].shape == (2, 4) and int(res[10][0, 0]) == 10
+# bag of words: LOCATIONS are sharded (each owns its code book + index), float32 scores all-gathered
+locs = synthetic_bow_locations(1, 5)
+loaded = []
+sb = engine.ShardedBow(len(locs), lambda i: (loaded.append(i), locs[i])[1], local_factory=OracleBow)
+assert loaded == list(range(*sb.loc_bounds[rank])) and 0 < len(loaded) < len(locs)   # only this rank's indices were loaded
+bf = [synth.sift_like(rng, 30), None, synth.sift_like(rng, 11)]
+got_b = sb.score(bf)
+want_b = OracleBow(locs, 40).score(bf)[0]
+assert got_b.dtype == np.float32 and np.array_equal(got_b, want_b), rank
+assert list(sb.img_off) == list(np.cumsum([0] + [len(l[0]) for l in locs]))
 dist.barrier()
 if rank == 0:
-    print("SHARD_OK", sm.bounds)
+    print("SHARD_OK", sm.bounds, sb.loc_bounds)
 dist.destroy_process_group()
 '''
 
