@@ -153,6 +153,10 @@ class Context:
         self._h = h
         self.device = int(device)
         self._lib = lib
+        # development aid: MCL_OPTIONS="4=1,1=0" applies mcl_set_option(which, value) pairs to every new context
+        for item in filter(None, os.environ.get("MCL_OPTIONS", "").split(",")):
+            which, value = item.split("=")
+            self.set_option(int(which), int(value))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -849,11 +849,15 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         CU(cudaFuncSetAttribute(sift_tc3_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         m->tc3_attr = true;
     }
-    const size_t smem4 = sizeof(mcl::sifttc4::Smem);
+    const int ss_tiles = std::max(0, std::min(c->opt[4], 2));   // option 4: A tiles the MMAs read from shared memory
+    const size_t smem4 = ss_tiles == 0 ? sizeof(mcl::sifttc4::SmemT<0>) : (ss_tiles == 1 ? sizeof(mcl::sifttc4::SmemT<1>) : sizeof(mcl::sifttc4::SmemT<2>));
     if (gen4 && !m->tc4_attr) {
-        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<1>)));
+        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<2>)));
+        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
+        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
+        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
+        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
         m->tc4_attr = true;
     }
     const int n_qblocks_total = (int)(q->padded_rows / QBLK);
@@ -897,8 +901,23 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
             ProfScope ps(c, PROF_SIFT_TC, st);
             if (gen4) {
                 using namespace mcl::sifttc4;
-                if (c->opt[0] == 3) sift_tc4_kernel<3><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
-                else if (c->opt[0] == 4) sift_tc4_kernel<4><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
+                if (c->opt[0] == 3) sift_tc4_kernel<3><<<grid, mcl::sifttc4::THREADS, sizeof(SmemT<0>), st>>>(p);
+                else if (c->opt[0] == 4) sift_tc4_kernel<4><<<grid, mcl::sifttc4::THREADS, sizeof(SmemT<0>), st>>>(p);
+                else if (c->opt[0] == 5) {   // timeline of 64 consecutive tiles: epilogue warp 5 and the MMA warp of CTA 0
+                    sift_tc4_kernel<5><<<grid, mcl::sifttc4::THREADS, sizeof(SmemT<0>), st>>>(p);
+                    long long tl[64 * 5], tm[64 * 6];
+                    cudaStreamSynchronize(st);
+                    cudaMemcpy(tl, reinterpret_cast<long long*>(c->cand.as<int4>() + (cap - 1024)), sizeof tl, cudaMemcpyDeviceToHost);
+                    cudaMemcpy(tm, reinterpret_cast<long long*>(c->cand.as<int4>() + (cap - 1024)) + 1024, sizeof tm, cudaMemcpyDeviceToHost);
+                    for (int i = 0; i < 64; ++i)
+                        fprintf(stderr, "tile %2d epi: wait_full %5lld ld1 %5lld max+ld2+arrive %5lld compute %5lld period %5lld | mma: wait_b %5lld wait_e0 %5lld e1 %5lld e2 %5lld rest %5lld period %5lld | full->empty %5lld\n", i,
+                                tl[i * 5 + 1] - tl[i * 5], tl[i * 5 + 2] - tl[i * 5 + 1], tl[i * 5 + 3] - tl[i * 5 + 2], tl[i * 5 + 4] - tl[i * 5 + 3],
+                                i ? tl[i * 5] - tl[i * 5 - 5] : 0, tm[i * 6 + 1] - tm[i * 6], tm[i * 6 + 2] - tm[i * 6 + 1], tm[i * 6 + 3] - tm[i * 6 + 2],
+                                tm[i * 6 + 4] - tm[i * 6 + 3], tm[i * 6 + 5] - tm[i * 6 + 4], i ? tm[i * 6] - tm[i * 6 - 6] : 0,
+                                tl[i * 5 + 3] - tl[i * 5 + 1]);
+                }
+                else if (ss_tiles == 1) sift_tc4_kernel<0, 1><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
+                else if (ss_tiles == 2) sift_tc4_kernel<0, 2><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
                 else sift_tc4_kernel<0><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
             } else if (c->opt[0] == 3) sift_tc3_kernel<3><<<grid, THREADS, smem, st>>>(p);
             else if (c->opt[0] == 4) sift_tc3_kernel<4><<<grid, THREADS, smem, st>>>(p);

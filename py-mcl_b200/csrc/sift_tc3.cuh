@@ -48,6 +48,7 @@ constexpr int THREADS = (EPI_WARPS + 1 + MMA_WARPS) * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int META_CAP = 352;          // tiles of a chunk whose metadata is staged in shared memory (longer chunks read it from L2)
 constexpr int NONE = INT_MIN / 2;      // "no group yet": Q - NONE still fits in int32
+constexpr int POS_WIDE = 1 << 24;      // flag in a group position / candidate row: G1 is a whole 128-row tile (sift_tc4)
 
 struct TileMeta {
     int32_t img[GROUPS];    // image id of each group (-1: padding group)
@@ -56,8 +57,11 @@ struct TileMeta {
     int32_t nmax[GROUPS];
     int32_t end_mask;       // bit g: group g is the last group of its image
     int32_t tnmin, tnmax;   // bracket of the whole 64-row tile (meaningful when both groups belong to one image)
-    int32_t pad;
+    int32_t merge;          // even tiles: 1 = this tile and the next lie inside one image, no image ends before the end of the
+                            // pair, and the pair's |m|^2 bracket is at most MERGE_WIDTH wide -> sift_tc4 updates its brackets
+                            // once per 128 rows.  A wide bracket (outlier norms) would only multiply the candidates.
 };
+constexpr int MERGE_WIDTH = 1024;
 static_assert(sizeof(TileMeta) == META_BYTES, "meta size");
 
 struct Smem {
@@ -114,7 +118,18 @@ __global__ void build_meta_kernel(const int32_t* __restrict__ m_norm, const int3
     mt.end_mask = mask;
     mt.tnmin = min(mt.nmin[0], mt.nmin[1]);
     mt.tnmax = max(mt.nmax[0], mt.nmax[1]);
-    mt.pad = 0;
+    mt.merge = 0;
+    if ((t & 1) == 0 && t + 1 < n_tiles && mask == 0 && mt.img[0] >= 0 && mt.img[0] == mt.img[1]) {
+        const int64_t r0 = (int64_t)(t + 1) * TILE_N;
+        // the next tile: both groups in the same image, and the image does not end after its first group
+        bool ok = img_of[r0] == mt.img[0] && img_of[r0 + GROUP] == mt.img[0];
+        int lo = mt.tnmin, hi = mt.tnmax;
+        for (int r = 0; r < TILE_N; ++r) {
+            const int n = m_norm[r0 + r];
+            if (n >= 0) { lo = min(lo, n); hi = max(hi, n); }
+        }
+        mt.merge = (ok && hi - lo <= MERGE_WIDTH) ? 1 : 0;
+    }
     meta[t] = mt;
 }
 
@@ -139,7 +154,7 @@ __device__ __noinline__ void finalize_image(const Params& p, int lane, bool row_
         if (pass) {
             const unsigned idx = base + __popc(bal & ((1u << lane) - 1u));
             if (idx < p.cand_cap)
-                p.cand[idx] = make_int4(p.q_row_base + (int)qrow, pos * GROUP, H2, L2);
+                p.cand[idx] = make_int4(p.q_row_base + (int)qrow, (pos & (POS_WIDE - 1)) * GROUP | ((pos & POS_WIDE) << 6), H2, L2);
             else
                 *p.overflow = 1;
         }
@@ -397,17 +412,28 @@ __global__ void sift_fixup3_kernel(const int4* __restrict__ cand, const unsigned
 #pragma unroll
         for (int chunk = 0; chunk < 8; ++chunk) q[chunk] = *reinterpret_cast<const uint4*>(q_desc + sw128_chunk_offset(qrow, chunk));
         const int Q = q_norm[qrow];
-        const int img = m_img_of[cd.y];
-        // G1 is a 32-row group or the whole 64-row tile: recompute the tile's rows of this image exactly (2 per lane)
-        const int64_t tile0 = (int64_t)cd.y & ~(int64_t)(TILE_N - 1);
+        // G1 is a 32-row group, a 64-row tile, or (flag, sift_tc4's merged brackets) a 128-row tile of one image:
+        // recompute the tile's rows of this image exactly (2 or 4 per lane)
+        const bool wide = (cd.y & (POS_WIDE << 6)) != 0;
+        const int64_t g1row = (int64_t)(cd.y & ((POS_WIDE << 6) - 1));
+        const int img = m_img_of[g1row];
+        const int64_t tile0 = g1row & ~(int64_t)((wide ? 2 * TILE_N : TILE_N) - 1);
         int va = INT_MIN, vb = INT_MIN;
         {
             const int64_t ra = tile0 + lane, rb = tile0 + 32 + lane;
             if (m_img_of[ra] == img) va = exact_key(q, m_desc, ra, m_norm[ra]);
             if (m_img_of[rb] == img) vb = exact_key(q, m_desc, rb, m_norm[rb]);
         }
+        int m1 = max(va, vb), s1 = min(va, vb);
+        if (wide) {   // warp-uniform
+            const int64_t rc = tile0 + 64 + lane, rd = tile0 + 96 + lane;
+            const int vc = exact_key(q, m_desc, rc, m_norm[rc]), vd = exact_key(q, m_desc, rd, m_norm[rd]);   // one image by construction
+            const int m2 = max(vc, vd), s2 = min(vc, vd);
+            s1 = max(min(m1, m2), max(s1, s2));
+            m1 = max(m1, m2);
+        }
         int k1, k2;
-        warp_top2(max(va, vb), min(va, vb), k1, k2);
+        warp_top2(m1, s1, k1, k2);
         // the best key of the other groups lies in [lo, hi]; no key exceeds Q (d^2 >= 0), and an unclamped upper bound
         // would turn into a negative d^2 (NaN under sqrtf: the reading would silently count as a failed test)
         const int hi = min(cd.z, Q), lo = min(cd.w, Q);

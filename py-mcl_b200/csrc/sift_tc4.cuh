@@ -36,20 +36,32 @@ constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int META_CAP = sifttc3::META_CAP;  // 64-row records staged per chunk
 
-struct Smem {
+constexpr int A_TILE_BYTES = QTILE * 128;    // 16 KB
+
+// SS = number of A tiles (query tiles) the MMAs read from SHARED memory instead of tensor memory.  With all three in tensor
+// memory the kernel sits on the tensor-memory read bandwidth (per 128 map rows: 3 x 64 KB of accumulators for the epilogue
+// + 3 x 16 KB of A operand = 240 KB per 768 MMA cycles = 312 B/clk) while shared memory idles at ~83 B/clk of its 128
+// (B operand 3 x 16 KB + the TMA writes).  Moving ONE A tile to shared memory trades 16 KB of tensor-memory reads for 16 KB
+// of shared-memory reads per B tile (292 / 104 B/clk).  The tile is double buffered across work items and loaded by the
+// TMA warp with one linear bulk copy (the query rows are stored as SW128 atoms, like the map).
+template <int SS>
+struct SmemT {
     alignas(1024) uint8_t stage[B_STAGES][B_TILE_BYTES];
+    alignas(1024) uint8_t a_tile[2][SS > 0 ? SS : 1][SS > 0 ? A_TILE_BYTES : 16];
     alignas(16) int4 meta[META_CAP * 3];
     alignas(8) uint64_t b_full[B_STAGES];
     uint64_t b_empty[B_STAGES];
     uint64_t acc_full[ATILES], acc_empty[ATILES];
     uint64_t a_full, a_free;
+    uint64_t as_full[2], as_empty[2];
     uint32_t tmem_base;
 };
+using Smem = SmemT<0>;
 
-template <int MODE>
+template <int MODE, int SS = 0>
 __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    SmemT<SS>& s = *reinterpret_cast<SmemT<SS>*>(smem_raw);
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     const int warp = warp_id_uniform();
     const int lane = threadIdx.x & 31;
@@ -58,8 +70,9 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
     if (threadIdx.x == 0) {
         for (int i = 0; i < B_STAGES; ++i) { mbar_init(&s.b_full[i], 1); mbar_init(&s.b_empty[i], 1); }
         for (int a = 0; a < ATILES; ++a) { mbar_init(&s.acc_full[a], 1); mbar_init(&s.acc_empty[a], 4); }
-        mbar_init(&s.a_full, EPI_WARPS);
+        mbar_init(&s.a_full, EPI_WARPS - 4 * SS);   // the warps whose A tile lives in tensor memory
         mbar_init(&s.a_free, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&s.as_full[i], 1); mbar_init(&s.as_empty[i], 1); }
         mbar_fence_init();
     }
     if (warp == EPI_WARPS + 1) tmem_alloc<TMEM_COLS>(&s.tmem_base);
@@ -71,9 +84,19 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
 
     if (warp == EPI_WARPS) {
         // ================= TMA producer: one 128-row map tile (16 KB) per stage ========================================
-        uint32_t bn = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        uint32_t bn = 0, item_n = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
             const Chunk ch = p.chunks[item / p.n_qblocks];
+            if (SS > 0) {   // this item's shared-memory A tiles (buffer item_n & 1; free once the MMAs of item_n - 2 retired)
+                const uint32_t ab = item_n & 1;
+                mbar_wait(&s.as_empty[ab], ((item_n >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx_if(leader, &s.as_full[ab], SS * A_TILE_BYTES);
+                const int qb = item % p.n_qblocks;
+#pragma unroll
+                for (int a = 0; a < SS; ++a)
+                    bulk_g2s_if(leader, s.a_tile[ab][a], p.q_desc + ((size_t)qb * QBLK + (size_t)a * QTILE) * 128, A_TILE_BYTES,
+                                &s.as_full[ab]);
+            }
             for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
                 const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
                 mbar_wait(&s.b_empty[bs], bph ^ 1);
@@ -87,11 +110,15 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
         uint32_t bn = 0, item_n = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
             const Chunk ch = p.chunks[item / p.n_qblocks];
-            mbar_wait(&s.a_full, item_n & 1);
+            if (SS < ATILES) mbar_wait(&s.a_full, item_n & 1);
+            if (SS > 0) mbar_wait(&s.as_full[item_n & 1], (item_n >> 1) & 1);
             tc_fence_after();
             for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
                 const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
+                long long tm[8];
+                if (MODE == 5) tm[0] = clock64();
                 mbar_wait(&s.b_full[bs], bph);
+                if (MODE == 5) tm[1] = clock64();
                 const uint64_t b_desc = umma_desc_sw128(smem_u32(s.stage[bs]));
                 // round robin over the A tiles: accumulator a was filled first last time, so it is drained first; a blocking
                 // try_wait wakes ~60 cycles after the arrive, a polling loop over three barriers costs ~150 per probe
@@ -99,16 +126,28 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
                 for (int a = 0; a < ATILES; ++a) {
                     mbar_wait(&s.acc_empty[a], (bn & 1) ^ 1);
                     tc_fence_after();
+                    if (MODE == 5) tm[2 + a] = clock64();
                     const uint32_t d = tmem_base + ACC_COL0 + a * TILE_N;
-                    const uint32_t ta = tmem_base + a * A_COLS;
+                    if (a < SS) {
+                        const uint64_t a_desc = umma_desc_sw128(smem_u32(s.a_tile[item_n & 1][a < SS ? a : 0]));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_i8_ts_if(leader, d, ta + 8 * k, b_desc + 2 * k, idesc, k > 0);
+                        for (int k = 0; k < 4; ++k) umma_i8_if(leader, d, a_desc + 2 * k, b_desc + 2 * k, idesc, k > 0);
+                    } else {
+                        const uint32_t ta = tmem_base + a * A_COLS;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_i8_ts_if(leader, d, ta + 8 * k, b_desc + 2 * k, idesc, k > 0);
+                    }
                     tc_commit_if(leader, &s.acc_full[a]);
                 }
                 tc_commit_if(leader, &s.b_empty[bs]);
                 __syncwarp();
+                if (MODE == 5 && blockIdx.x == 0 && lane == 0 && bn >= 100 && bn < 164) {
+                    long long* tl = reinterpret_cast<long long*>(p.cand + (p.cand_cap - 1024)) + 1024 + (bn - 100) * 6;   // tail of the candidate buffer
+                    tl[0] = tm[0]; tl[1] = tm[1]; tl[2] = tm[2]; tl[3] = tm[3]; tl[4] = tm[4]; tl[5] = clock64();
+                }
             }
             tc_commit_if(leader, &s.a_free);
+            if (SS > 0) tc_commit_if(leader, &s.as_empty[item_n & 1]);
             __syncwarp();
         }
     } else {
@@ -122,7 +161,7 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
             const int qb = item % p.n_qblocks;
             const Chunk ch = p.chunks[item / p.n_qblocks];
             const int64_t qrow = (int64_t)qb * QBLK + row_in_blk;
-            {   // this thread's query row -> tensor memory (row = TMEM lane, 4 K-bytes per column)
+            if (atile >= SS) {   // this thread's query row -> tensor memory (row = TMEM lane, 4 K-bytes per column)
                 uint32_t w[32];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -153,24 +192,32 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
             const int n_rec = 2 * (ch.tile_end - ch.tile_begin);
             const int4* mp = reinterpret_cast<const int4*>(p.m_meta + 2 * (int64_t)ch.tile_begin);
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-            if (n_rec <= p.meta_cap) {
+            const bool staged = n_rec <= p.meta_cap;
+            if (staged) {
                 for (int i = threadIdx.x; i < n_rec * 3; i += EPI_WARPS * 32) s.meta[i] = __ldg(mp + i);
-                mp = s.meta;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            const uint32_t meta_s = smem_u32(s.meta);
+            // record i of the chunk (16 bytes): an explicit shared-memory load when staged (a generic pointer would compile
+            // to generic LD.E), the read-only path otherwise.  `staged` is uniform over the CTA.
+            auto ldrec = [&](int i) {
+                int4 r;
+                if (staged) asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(meta_s + 16u * (uint32_t)i));
+                else r = __ldg(mp + i);
+                return r;
+            };
             // one 64-row half: maxima of its two 32-row groups, bracket update, end-of-image test
-            auto half = [&](int g0, int g1, const int4* rec, int unit /* 64-row unit index */) {
-                const int4 c2 = rec[2];     // {end_mask, tnmin, tnmax, -}
+            auto half = [&](int g0, int g1, int rec, const int4 c2 /* {end_mask, tnmin, tnmax, -} */, int unit /* 64-row unit index */) {
                 const int end_mask = c2.x;
                 if ((end_mask & 1) == 0) {
                     join(max(g0, g1), c2.y, c2.z, unit * 2);
                     if (end_mask & 2) {
-                        const int4 c0 = rec[0];   // {img0, img1, nval0, nval1}
+                        const int4 c0 = ldrec(rec);   // {img0, img1, nval0, nval1}
                         sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.y, c0.w, ch);
                         H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
                     }
                 } else {
-                    const int4 c0 = rec[0], c1 = rec[1];   // c1 = {nmin0, nmin1, nmax0, nmax1}
+                    const int4 c0 = ldrec(rec), c1 = ldrec(rec + 1);   // c1 = {nmin0, nmin1, nmax0, nmax1}
                     join(g0, c1.x, c1.z, unit * 2);
                     sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.x, c0.z, ch);
                     H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
@@ -185,10 +232,15 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
             };
 #pragma unroll 1
             for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
+                long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
+                if (MODE == 5) tk0 = clock64();
+                // the two 64-row records of this tile, fetched before the wait so that their latency is hidden
+                const int rec = (t - ch.tile_begin) * 6;
+                const int4 c2a = ldrec(rec + 2), c2b = ldrec(rec + 5);
                 mbar_wait(&s.acc_full[atile], bn & 1);
                 tc_fence_after();
+                if (MODE == 5) tk1 = clock64();
                 const uint32_t tcol = t_lane + ACC_COL0 + atile * TILE_N;
-                const int4* rec = mp + (size_t)(t - ch.tile_begin) * 6;
                 uint32_t v[2][32];
                 if (MODE != 4) {
                     tmem_ld64(tcol, reinterpret_cast<uint32_t(&)[64]>(v));
@@ -200,6 +252,7 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
                     for (int i = 0; i < 32; ++i) { v[0][i] = 0; v[1][i] = 0; }
                 }
                 // first half: only the two max trees run before the second load is issued; the brackets follow the release
+                if (MODE == 5) tk2 = clock64();
                 const int e0 = sifttc3::group_max<MODE>(v[0]), e1 = sifttc3::group_max<MODE>(v[1]);
                 if (MODE != 4) {
                     tmem_ld64(tcol + HALF, reinterpret_cast<uint32_t(&)[64]>(v));
@@ -208,8 +261,26 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
                     tmem_fence_regs(v[1]);
                 }
                 if (lane == 0) mbar_arrive(&s.acc_empty[atile]);   // both halves are out of tensor memory: the accumulator is free
-                half(e0, e1, rec, 2 * t);
-                half(sifttc3::group_max<MODE>(v[0]), sifttc3::group_max<MODE>(v[1]), rec + 3, 2 * t + 1);
+                if (MODE == 5) tk3 = clock64();
+                const int f0 = sifttc3::group_max<MODE>(v[0]), f1 = sifttc3::group_max<MODE>(v[1]);
+                if (c2a.w != 0) {
+                    // the whole 128-row tile lies inside one image and its norms are close (TileMeta::merge): ONE bracket update
+                    // instead of two (the bracket is the union of the two units' -- exact whatever the row order).
+                    // Warp-uniform: the records are the same for every lane.
+                    join(max(max3(e0, e1, f0), f1), min(c2a.y, c2b.y), max(c2a.z, c2b.z), (4 * t) | sifttc3::POS_WIDE);
+                    if (c2b.x & 2) {
+                        const int4 c0 = ldrec(rec + 3);
+                        sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.y, c0.w, ch);
+                        H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
+                    }
+                } else {
+                    half(e0, e1, rec, c2a, 2 * t);
+                    half(f0, f1, rec + 3, c2b, 2 * t + 1);
+                }
+                if (MODE == 5 && blockIdx.x == 0 && warp == 5 && lane == 0 && bn >= 100 && bn < 164) {
+                    long long* tl = reinterpret_cast<long long*>(p.cand + (p.cand_cap - 1024)) + (bn - 100) * 5;
+                    tl[0] = tk0; tl[1] = tk1; tl[2] = tk2; tl[3] = tk3; tl[4] = clock64();
+                }
             }
         }
     }
