@@ -236,6 +236,32 @@ __device__ __forceinline__ void tc_commit_if(uint32_t pred, uint64_t* bar) {
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}" ::"r"(pred), "r"(smem_u32(bar))
         : "memory");
 }
+// ---- thread-block clusters: one bulk copy delivered to the same shared-memory offset of several CTAs --------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the data and the complete_tx land in every CTA of `cta_mask`, at this CTA's offsets of smem_dst / bar
+__device__ __forceinline__ void bulk_g2s_multicast_if(uint32_t pred, void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                                      uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%1], [%2], %3, [%4], %5;\n\t}" ::"r"(pred),
+        "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+// arrives on the mbarrier at this offset in every CTA of `cta_mask` once all prior tcgen05 operations of this thread retired
+__device__ __forceinline__ void tc_commit_multicast_if(uint32_t pred, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%1], %2;\n\t}" ::"r"(pred),
+        "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
 __device__ __forceinline__ void umma_i8_if(uint32_t pred, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                            uint32_t accumulate) {
     asm volatile(

@@ -855,6 +855,7 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<1>)));
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<2>)));
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
+        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
@@ -895,8 +896,12 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         p.overflow = d_overflow;
         p.q_row_base = qb0 * QBLK;
         p.meta_cap = c->opt[1] == 1 ? 0 : META_CAP;   // option 1 = 1: always read the tile metadata from global memory
-        const int64_t n_items = (int64_t)nqb * cs->n;
-        const int grid = (int)std::min<int64_t>(n_items, c->sm_count);
+        // CTA pairs share the map tiles (multicast): worth it for long launches (less L2 traffic -> less power); an odd
+        // number of query blocks idles one CTA for one item.  option 5: 0 = this rule, 1 = never, 2 = always
+        const bool cl2 = gen4 && c->opt[0] == 0 && ss_tiles == 0 && c->sm_count >= 2 &&
+                         (c->opt[5] == 2 || (c->opt[5] == 0 && ((nqb % 2 == 0 && nqb >= 2) || nqb >= 32)));
+        const int64_t n_items = cl2 ? (int64_t)((nqb + 1) / 2) * cs->n : (int64_t)nqb * cs->n;
+        const int grid = cl2 ? 2 * (int)std::min<int64_t>(n_items, c->sm_count / 2) : (int)std::min<int64_t>(n_items, c->sm_count);
         {
             ProfScope ps(c, PROF_SIFT_TC, st);
             if (gen4) {
@@ -915,6 +920,21 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
                                 i ? tl[i * 5] - tl[i * 5 - 5] : 0, tm[i * 6 + 1] - tm[i * 6], tm[i * 6 + 2] - tm[i * 6 + 1], tm[i * 6 + 3] - tm[i * 6 + 2],
                                 tm[i * 6 + 4] - tm[i * 6 + 3], tm[i * 6 + 5] - tm[i * 6 + 4], i ? tm[i * 6] - tm[i * 6 - 6] : 0,
                                 tl[i * 5 + 3] - tl[i * 5 + 1]);
+                }
+                else if (cl2) {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(grid);
+                    cfg.blockDim = dim3(mcl::sifttc4::THREADS);
+                    cfg.dynamicSmemBytes = sizeof(SmemT<0>);
+                    cfg.stream = st;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = 2;
+                    at[0].val.clusterDim.y = 1;
+                    at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at;
+                    cfg.numAttrs = 1;
+                    CU(cudaLaunchKernelEx(&cfg, sift_tc4_kernel<0, 0, 2>, p));
                 }
                 else if (ss_tiles == 1) sift_tc4_kernel<0, 1><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
                 else if (ss_tiles == 2) sift_tc4_kernel<0, 2><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);

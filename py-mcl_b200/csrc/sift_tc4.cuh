@@ -58,7 +58,12 @@ struct SmemT {
 };
 using Smem = SmemT<0>;
 
-template <int MODE, int SS = 0>
+// CL = CTAs per thread-block cluster (1 or 2).  With CL = 2 the two CTAs of a cluster work on the same chunk of map tiles
+// for two different query blocks, in lockstep: every map tile is fetched from L2 ONCE, each CTA issuing one half of it as a
+// multicast bulk copy that lands in both CTAs' shared memory (halves the L2 -> SM traffic, 6 TB/s at full speed, which is
+// what pushes the kernel into the power cap).  A stage may be refilled only when BOTH CTAs' MMAs have consumed it: the
+// MMA warps commit to the stage's empty barrier in both CTAs (tcgen05.commit multicast).
+template <int MODE, int SS = 0, int CL = 1>
 __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SmemT<SS>& s = *reinterpret_cast<SmemT<SS>*>(smem_raw);
@@ -68,7 +73,7 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
     const uint32_t leader = lane == 0;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < B_STAGES; ++i) { mbar_init(&s.b_full[i], 1); mbar_init(&s.b_empty[i], 1); }
+        for (int i = 0; i < B_STAGES; ++i) { mbar_init(&s.b_full[i], 1); mbar_init(&s.b_empty[i], CL); }
         for (int a = 0; a < ATILES; ++a) { mbar_init(&s.acc_full[a], 1); mbar_init(&s.acc_empty[a], 4); }
         mbar_init(&s.a_full, EPI_WARPS - 4 * SS);   // the warps whose A tile lives in tensor memory
         mbar_init(&s.a_free, 1);
@@ -78,20 +83,26 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
     if (warp == EPI_WARPS + 1) tmem_alloc<TMEM_COLS>(&s.tmem_base);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync();   // the peer's barriers exist before any multicast copy or commit can reach them
     tc_fence_after();
     const uint32_t tmem_base = s.tmem_base;
-    const int n_items = p.n_qblocks * p.n_chunks;
+    // work items: (chunk, group of CL query blocks); CTA `crank` of the cluster takes query block group * CL + crank
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    const int n_qgroups = (p.n_qblocks + CL - 1) / CL;
+    const int n_items = n_qgroups * p.n_chunks;
+    const int item0 = blockIdx.x / CL, item_step = gridDim.x / CL;
+    constexpr uint16_t ALL_CTAS = (1u << CL) - 1u;
 
     if (warp == EPI_WARPS) {
         // ================= TMA producer: one 128-row map tile (16 KB) per stage ========================================
         uint32_t bn = 0, item_n = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
-            const Chunk ch = p.chunks[item / p.n_qblocks];
+        for (int item = item0; item < n_items; item += item_step, ++item_n) {
+            const Chunk ch = p.chunks[item / n_qgroups];
             if (SS > 0) {   // this item's shared-memory A tiles (buffer item_n & 1; free once the MMAs of item_n - 2 retired)
                 const uint32_t ab = item_n & 1;
                 mbar_wait(&s.as_empty[ab], ((item_n >> 1) & 1) ^ 1);
                 mbar_arrive_expect_tx_if(leader, &s.as_full[ab], SS * A_TILE_BYTES);
-                const int qb = item % p.n_qblocks;
+                const int qb = min((item % n_qgroups) * CL + (int)crank, p.n_qblocks - 1);
 #pragma unroll
                 for (int a = 0; a < SS; ++a)
                     bulk_g2s_if(leader, s.a_tile[ab][a], p.q_desc + ((size_t)qb * QBLK + (size_t)a * QTILE) * 128, A_TILE_BYTES,
@@ -101,15 +112,21 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
                 const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
                 mbar_wait(&s.b_empty[bs], bph ^ 1);
                 mbar_arrive_expect_tx_if(leader, &s.b_full[bs], B_TILE_BYTES);
-                bulk_g2s_if(leader, s.stage[bs], p.m_desc + (size_t)t * B_TILE_BYTES, B_TILE_BYTES, &s.b_full[bs]);
+                if (CL == 1) {
+                    bulk_g2s_if(leader, s.stage[bs], p.m_desc + (size_t)t * B_TILE_BYTES, B_TILE_BYTES, &s.b_full[bs]);
+                } else {   // this CTA's share of the tile, delivered to every CTA of the cluster
+                    constexpr uint32_t part = B_TILE_BYTES / CL;
+                    bulk_g2s_multicast_if(leader, s.stage[bs] + crank * part, p.m_desc + (size_t)t * B_TILE_BYTES + crank * part, part,
+                                          &s.b_full[bs], ALL_CTAS);
+                }
             }
         }
     } else if (warp == EPI_WARPS + 1) {
         // ================= MMA issuer: A from tensor memory, B from shared memory, N = 128 ==============================
         constexpr uint32_t idesc = umma_idesc(/*c=S32*/ 2, /*a=u8*/ 0, /*b=u8*/ 0, QTILE, TILE_N);
         uint32_t bn = 0, item_n = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
-            const Chunk ch = p.chunks[item / p.n_qblocks];
+        for (int item = item0; item < n_items; item += item_step, ++item_n) {
+            const Chunk ch = p.chunks[item / n_qgroups];
             if (SS < ATILES) mbar_wait(&s.a_full, item_n & 1);
             if (SS > 0) mbar_wait(&s.as_full[item_n & 1], (item_n >> 1) & 1);
             tc_fence_after();
@@ -139,7 +156,8 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
                     }
                     tc_commit_if(leader, &s.acc_full[a]);
                 }
-                tc_commit_if(leader, &s.b_empty[bs]);
+                if (CL == 1) tc_commit_if(leader, &s.b_empty[bs]);
+                else tc_commit_multicast_if(leader, &s.b_empty[bs], ALL_CTAS);
                 __syncwarp();
                 if (MODE == 5 && blockIdx.x == 0 && lane == 0 && bn >= 100 && bn < 164) {
                     long long* tl = reinterpret_cast<long long*>(p.cand + (p.cand_cap - 1024)) + 1024 + (bn - 100) * 6;   // tail of the candidate buffer
@@ -157,9 +175,10 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
         const int row_in_blk = atile * QTILE + lane_base + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)lane_base << 16);
         uint32_t bn = 0, item_n = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
-            const int qb = item % p.n_qblocks;
-            const Chunk ch = p.chunks[item / p.n_qblocks];
+        for (int item = item0; item < n_items; item += item_step, ++item_n) {
+            const int qb_raw = (item % n_qgroups) * CL + (int)crank;
+            const int qb = min(qb_raw, p.n_qblocks - 1);   // an odd tail: the second CTA repeats the last block and reports nothing
+            const Chunk ch = p.chunks[item / n_qgroups];
             const int64_t qrow = (int64_t)qb * QBLK + row_in_blk;
             if (atile >= SS) {   // this thread's query row -> tensor memory (row = TMEM lane, 4 K-bytes per column)
                 uint32_t w[32];
@@ -177,7 +196,7 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
                 if (lane == 0) mbar_arrive(&s.a_full);
             }
             const int Q = p.q_norm[qrow];
-            const bool row_valid = Q >= 0;
+            const bool row_valid = Q >= 0 && qb_raw < p.n_qblocks;
             int H1 = NONE, L1 = NONE, H2 = NONE, L2 = NONE, pos = 0;
             auto join = [&](int gm, int nmin, int nmax, int id) {
                 const int hi = 2 * gm - nmin, lo = 2 * gm - nmax;
@@ -286,6 +305,7 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync();   // no CTA leaves while its peer may still multicast into it
     if (warp == EPI_WARPS + 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
