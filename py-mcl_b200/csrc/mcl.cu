@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -93,6 +94,7 @@ struct mcl_ctx {
     size_t cand_cap_entries = 0;
     bool tc_attr_set = false, tc2_attr_set = false;
     int opt[8] = {0};  // mcl_set_option: [0] = sift_tc diagnostic mode
+    int max_clusters[2] = {0, 0};   // co-resident sift_tc4 clusters of 2 / of 4 CTAs
 };
 
 struct mcl_queries {
@@ -856,6 +858,26 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<2>)));
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
+        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
+        for (int cl = 2; cl <= 4; cl += 2) {   // how many clusters of this size are co-resident (GPC boundaries may strand SMs)
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((c->sm_count / cl) * cl);
+            cfg.blockDim = dim3(mcl::sifttc4::THREADS);
+            cfg.dynamicSmemBytes = sizeof(mcl::sifttc4::SmemT<0>);
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cl;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int n = 0;
+            cudaError_t e = cl == 2 ? cudaOccupancyMaxActiveClusters(&n, mcl::sifttc4::sift_tc4_kernel<0, 0, 2>, &cfg)
+                                    : cudaOccupancyMaxActiveClusters(&n, mcl::sifttc4::sift_tc4_kernel<0, 0, 4>, &cfg);
+            if (e != cudaSuccess) { n = 0; cudaGetLastError(); }
+            c->max_clusters[cl / 2 - 1] = n;
+            if (getenv("MCL_DEBUG")) fprintf(stderr, "[mcl] co-resident sift_tc4 clusters of %d CTAs: %d (%d SMs)\n", cl, n, c->sm_count);
+        }
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
@@ -896,12 +918,18 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         p.overflow = d_overflow;
         p.q_row_base = qb0 * QBLK;
         p.meta_cap = c->opt[1] == 1 ? 0 : META_CAP;   // option 1 = 1: always read the tile metadata from global memory
-        // CTA pairs share the map tiles (multicast): worth it for long launches (less L2 traffic -> less power); an odd
-        // number of query blocks idles one CTA for one item.  option 5: 0 = this rule, 1 = never, 2 = always
-        const bool cl2 = gen4 && c->opt[0] == 0 && ss_tiles == 0 && c->sm_count >= 2 &&
-                         (c->opt[5] == 2 || (c->opt[5] == 0 && ((nqb % 2 == 0 && nqb >= 2) || nqb >= 32)));
-        const int64_t n_items = cl2 ? (int64_t)((nqb + 1) / 2) * cs->n : (int64_t)nqb * cs->n;
-        const int grid = cl2 ? 2 * (int)std::min<int64_t>(n_items, c->sm_count / 2) : (int)std::min<int64_t>(n_items, c->sm_count);
+        // CTAs of a cluster share the map tiles (multicast): worth it for long launches (less L2 traffic -> less power); a
+        // query-block count that is not a multiple of the cluster size idles CTAs for one item.
+        // option 5: 0 = automatic (pairs), 1 = never, 2 / 4 = always that cluster size
+        int cl = 1;
+        if (gen4 && c->opt[0] == 0 && ss_tiles == 0) {
+            if (c->opt[5] == 2 || c->opt[5] == 4) cl = c->opt[5];
+            else if (c->opt[5] == 0 && ((nqb % 2 == 0 && nqb >= 2) || nqb >= 32)) cl = 2;
+            if (cl > 1 && c->max_clusters[cl / 2 - 1] < 1) cl = 1;
+        }
+        const bool cl2 = cl > 1;
+        const int64_t n_items = (int64_t)((nqb + cl - 1) / cl) * cs->n;
+        const int grid = cl > 1 ? cl * (int)std::min<int64_t>(n_items, c->max_clusters[cl / 2 - 1]) : (int)std::min<int64_t>(n_items, c->sm_count);
         {
             ProfScope ps(c, PROF_SIFT_TC, st);
             if (gen4) {
@@ -929,12 +957,13 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
                     cfg.stream = st;
                     cudaLaunchAttribute at[1];
                     at[0].id = cudaLaunchAttributeClusterDimension;
-                    at[0].val.clusterDim.x = 2;
+                    at[0].val.clusterDim.x = cl;
                     at[0].val.clusterDim.y = 1;
                     at[0].val.clusterDim.z = 1;
                     cfg.attrs = at;
                     cfg.numAttrs = 1;
-                    CU(cudaLaunchKernelEx(&cfg, sift_tc4_kernel<0, 0, 2>, p));
+                    if (cl == 2) CU(cudaLaunchKernelEx(&cfg, sift_tc4_kernel<0, 0, 2>, p));
+                    else CU(cudaLaunchKernelEx(&cfg, sift_tc4_kernel<0, 0, 4>, p));
                 }
                 else if (ss_tiles == 1) sift_tc4_kernel<0, 1><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
                 else if (ss_tiles == 2) sift_tc4_kernel<0, 2><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
