@@ -9,7 +9,7 @@ from pymcl_b200 import _lib, synth
 import oracle
 
 ctx = _lib.Context(0)
-names = sys.argv[1:] or ["orb", "orb_batch", "sift_cfg2", "surf", "bow", "kmeans", "laplacian"]
+names = sys.argv[1:] or ["orb", "orb_batch", "sift_cfg2", "surf", "bow", "bow_batch", "kmeans", "laplacian", "chi2"]
 POPC_PEAK = None
 
 
@@ -27,6 +27,8 @@ def timeit(fn, reps=10, warm=3):
 def prof(fn, slot, reps=10, warm=3):
     for _ in range(warm):
         fn()
+    for k in _lib.PROFILE_SLOTS:      # drop whatever earlier measurements left in the other slots
+        ctx.profile_read(k)
     ctx.profile_enable(True)
     for _ in range(reps):
         fn()
@@ -178,5 +180,35 @@ if "laplacian" in names:
     cpu = cpu_rate(lambda: [oracle.cv2_laplacian_var(i) for i in imgs[:20]], 3.0) * 20
     out.append({"config": "Laplacian 200 x 800x600", "e2e_ms": e2e * 1e3, "kernel_ms": k_ms,
                 "kernel_GBps": 200 * 480000 / (k_ms * 1e-3) / 1e9, "images_per_s_e2e": 200 / e2e, "cpu_images_per_s": cpu})
+if "bow_batch" in names:   # createRawP's shape: many frames against every location in one call
+    L, F = 16, 50
+    locs = []
+    for l in range(L):
+        rng = np.random.default_rng(500 + l)
+        voc = np.clip(synth.sift_like(rng, 10000) + rng.normal(0, 0.3, size=(10000, 128)), 0, 255).astype(np.float32)
+        im = rng.random((100, 10000), dtype=np.float32) * (rng.random((100, 10000)) < 0.03)
+        im /= np.maximum(np.linalg.norm(im, axis=1, keepdims=True), 1e-9)
+        locs.append((im.astype(np.float32), rng.random(10000, dtype=np.float32) + 0.5, voc))
+    bow = _lib.BowIndex(ctx, locs, 10000)
+    rng = np.random.default_rng(9)
+    frames = [np.clip(np.rint(locs[f % L][2][rng.choice(10000, 300)] + rng.normal(0, 6.0, size=(300, 128))), 0, 255).astype(np.float32)
+              for f in range(F)]
+    e2e = timeit(lambda: bow.score(frames), reps=3, warm=2)
+    r = {k: prof(lambda: bow.score(frames), k, reps=3, warm=1) for k in ("bow_vq_tc", "bow_resolve", "bow_vq", "bow_score")}
+    out.append({"config": "cfg5 BOW batched: %d frames x %d locations x 100 images (W=10000, Nq=300)" % (F, L), "e2e_ms": e2e * 1e3,
+                "vq_tc_ms": r["bow_vq_tc"], "vq_resolve_ms": r["bow_resolve"], "vq_simt_fallback_ms": r["bow_vq"], "score_ms": r["bow_score"],
+                "vq_tc_TOPs": 2.0 * 2 * F * 300 * 10000 * 128 * L / (r["bow_vq_tc"] * 1e-3) / 1e12,
+                "frame_locations_per_s_e2e": F * L / e2e})
+    bow.close()
+if "chi2" in names:   # colour method: 200 frame histograms vs 7 x 25 map histograms (512 bins)
+    rng = np.random.default_rng(12)
+    hist = lambda n: np.floor(rng.gamma(0.5, 40.0, size=(n, 512))).clip(0, 255).astype(np.float32)
+    q, m = hist(200), hist(175)
+    e2e = timeit(lambda: ctx.chi2(q, m), reps=20)
+    k_ms = prof(lambda: ctx.chi2(q, m), "chi2", reps=20)
+    cpu = cpu_rate(lambda: oracle.chi2_matrix(q[:4], m), 3.0) * 4 * 175
+    out.append({"config": "Color chi-squared 200 x 175 histograms (512 bins)", "e2e_ms": e2e * 1e3, "kernel_ms": k_ms,
+                "pairs_per_s_e2e": 200 * 175 / e2e, "kernel_GBps_from_L2": 200 * 175 * 2 * 2048 / (k_ms * 1e-3) / 1e9,
+                "cpu_pairs_per_s_numpy_1_thread": cpu})
 for o in out:
     print(json.dumps(o))
