@@ -161,6 +161,20 @@ __device__ __noinline__ void finalize_image(const Params& p, int lane, bool row_
     }
 }
 
+// Inline gate in front of finalize_image (sift_tc4): most (query row, image) pairs fail the ratio test by a wide margin, and
+// the exact test costs two correctly rounded square roots, float64 arithmetic and a function call per image end -- which is
+// every second tile for 256-row images.  A pair whose most favourable reading has d0 > ratio^2 * d1 * (1 + 1e-4) + 2 cannot
+// pass the exact float test (its roundings are ~1e-7 relative), so a warp in which every lane is that far off skips the call.
+// c2 = (float)(ratio^2 * 1.0001).
+__device__ __forceinline__ void finalize_gate(const Params& p, float c2, int lane, bool row_valid, int Q, int64_t qrow, int H1, int L1,
+                                              int H2, int L2, int pos, int img, int nval, const Chunk& ch) {
+    if (nval < 2 || img < ch.img_begin || img >= ch.img_end) return;   // warp-uniform
+    const int d0lo = max(0, Q - H1);
+    const int d1hi = L2 <= NONE ? (1 << 30) : Q - min(L1, L2);
+    const bool maybe = row_valid && !((float)d0lo > fmaf((float)d1hi, c2, 2.0f));
+    if (__any_sync(0xffffffffu, maybe)) finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, img, nval, ch);
+}
+
 template <int MODE>
 __device__ __forceinline__ int group_max(const uint32_t (&v)[32]) {
     if (MODE == 3) return (int)(v[0] | v[31]);  // diagnostic: no arithmetic (MODE 5 = product arithmetic + timeline dump)

@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
     } else {
         // ================= epilogue warps ===========================================================================
         const int atile = warp >> 2;
+        const float ratio_gate = (float)(p.ratio * p.ratio * 1.0001);
         const int lane_base = (warp & 3) * 32;
         const int row_in_blk = atile * QTILE + lane_base + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)lane_base << 16);
@@ -232,18 +233,18 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
                     join(max(g0, g1), c2.y, c2.z, unit * 2);
                     if (end_mask & 2) {
                         const int4 c0 = ldrec(rec);   // {img0, img1, nval0, nval1}
-                        sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.y, c0.w, ch);
+                        sifttc3::finalize_gate(p, ratio_gate, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.y, c0.w, ch);
                         H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
                     }
                 } else {
                     const int4 c0 = ldrec(rec), c1 = ldrec(rec + 1);   // c1 = {nmin0, nmin1, nmax0, nmax1}
                     join(g0, c1.x, c1.z, unit * 2);
-                    sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.x, c0.z, ch);
+                    sifttc3::finalize_gate(p, ratio_gate, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.x, c0.z, ch);
                     H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
                     if (c0.y >= 0) {
                         join(g1, c1.y, c1.w, unit * 2 + 1);
                         if (end_mask & 2) {
-                            sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.y, c0.w, ch);
+                            sifttc3::finalize_gate(p, ratio_gate, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.y, c0.w, ch);
                             H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
                         }
                     }
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
                     join(max(max3(e0, e1, f0), f1), min(c2a.y, c2b.y), max(c2a.z, c2b.z), (4 * t) | sifttc3::POS_WIDE);
                     if (c2b.x & 2) {
                         const int4 c0 = ldrec(rec + 3);
-                        sifttc3::finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.y, c0.w, ch);
+                        sifttc3::finalize_gate(p, ratio_gate, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.y, c0.w, ch);
                         H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
                     }
                 } else {
