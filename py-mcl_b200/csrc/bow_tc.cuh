@@ -6,14 +6,17 @@
 // centroids (float32, NOT integer valued).  The codebook is quantised to 16-bit fixed point g = rint(256 c)
 // and split into two u8 planes, g = 256 hi + lo, so that o.g = 256 (o.hi) + (o.lo) is two u8 x u8 -> s32 tensor-core
 // contractions (tcgen05.mma kind::i8) into two accumulators.  The epilogue forms T = 2 (256 P_hi + P_lo) - rint(256 |c|^2)
-// (the key in units of 1/256), and keeps per query row the best T, its word and the second-best T.
-// |256 key - T| <= sum_k o_k + 1/2, so when best - second > 2 (sum_k o_k + 1) the approximate argmax IS the exact argmin
-// (and is far from any float32 tie); otherwise (about a percent of the rows, and every exact tie) bow_resolve_kernel
-// rescans that row over the whole codebook in float32 direct-difference form with lowest-index tie-breaking, exactly
-// like the SIMT kernel.  Words are therefore identical to the SIMT path's.
+// (the key in units of 1/256) and keeps, per query row and branch-free, the largest key of any 32-word GROUP, that group,
+// and the largest group maximum among the OTHER groups (5 ALU operations per group on top of the 3-input max tree).
+// |256 key - T| <= sum_k o_k + 1/2, so when best - second > 2 (sum_k o_k + 1) the exact argmin lies inside the best group
+// (and is far from any float32 tie with a word outside it): bow_accept_kernel then evaluates that group's 32 words in
+// float32 direct-difference form with lowest-index tie-breaking, exactly like the SIMT kernel; otherwise (every exact tie
+// across groups, and the near-ties) bow_rescan_kernel rescans the row over the whole codebook the same way.  Words are
+// therefore identical to the SIMT path's.
 //
-// Work item = (location, block of 128 query rows); one CTA per item, persistent grid.  Warps 0-3 epilogue (TMEM lane
-// quadrants), warp 4 TMA producer, warp 5 MMA issuer.  TMEM: 2 stages x (hi, lo) x 128 columns.
+// Work item = (word-range split, location, block of 128 query rows); one CTA per item, persistent grid.  Warps 0-7 epilogue
+// (warp % 4 = TMEM lane quadrant, warp / 4 = which half of a tile's 128 words; the halves report like two more splits),
+// warp 8 TMA producer, warp 9 MMA issuer.  TMEM: 2 stages x (hi, lo) x 128 columns.
 #pragma once
 #include "common.cuh"
 
@@ -27,7 +30,8 @@ constexpr int TILE_BYTES = 2 * PLANE_BYTES + TILE_N * 4;   // hi plane | lo plan
 constexpr int STAGE_BYTES = 33792;          // 32 KB + 512 B, rounded to 1 KB
 constexpr int B_STAGES = 4;
 constexpr int ACC_STAGES = 2;
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;
+constexpr int HALVES = EPI_WARPS / 4;       // epilogue warps per TMEM lane quadrant, each owning TILE_N / HALVES words of a tile
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int NB_PAD = 1 << 30;             // nb of a padding word: its key can never win
@@ -47,7 +51,7 @@ struct Params {
     const int32_t* tile_off;    // n_loc+1: first tile of each location
     int n_loc, n_qtiles, n_q;
     int n_splits;               // each location's tiles are cut into n_splits contiguous ranges (more work items)
-    int4* out;                  // [n_splits][n_loc][n_q]: {best word, best T, second T, -}
+    int4* out;                  // [n_splits * HALVES][n_loc][n_q]: {best 32-word group, its largest T, largest T of the other groups, -}
 };
 
 // codebook -> planes (built once per index).  One warp per word row; lane l owns dims 4l..4l+3.
@@ -101,10 +105,11 @@ __device__ __forceinline__ void keys32(const uint32_t (&h)[32], const uint32_t (
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
         const int4 c = *reinterpret_cast<const int4*>(nb + i);
-        k[i] = (int)h[i] * 512 + ((int)l[i] * 2 - c.x);
-        k[i + 1] = (int)h[i + 1] * 512 + ((int)l[i + 1] * 2 - c.y);
-        k[i + 2] = (int)h[i + 2] * 512 + ((int)l[i + 2] * 2 - c.z);
-        k[i + 3] = (int)h[i + 3] * 512 + ((int)l[i + 3] * 2 - c.w);
+        // one IMAD (FMA pipe) + one shift-add (ALU pipe) per key: both pipes run at half rate, so the work is split
+        k[i] = (int)((h[i] << 9) + (uint32_t)((int)l[i] * 2 - c.x));
+        k[i + 1] = (int)((h[i + 1] << 9) + (uint32_t)((int)l[i + 1] * 2 - c.y));
+        k[i + 2] = (int)((h[i + 2] << 9) + (uint32_t)((int)l[i + 2] * 2 - c.z));
+        k[i + 3] = (int)((h[i + 3] << 9) + (uint32_t)((int)l[i + 3] * 2 - c.w));
     }
 }
 
@@ -188,14 +193,15 @@ __global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_cons
         }
     } else {
         // ================= epilogue warps =================
-        const int lane_base = warp * 32;
+        const int half = warp >> 2;
+        const int lane_base = (warp & 3) * 32;
         const uint32_t t_lane = tmem_base + ((uint32_t)lane_base << 16);
         uint32_t bn = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             int sp, loc, qt, tb, te, t0;
             decode(item, sp, loc, qt, tb, te, t0);
             const int row = qt * QTILE + lane_base + lane;
-            int b1 = INT_MIN, b2 = INT_MIN, idx = 0;
+            int b1 = INT_MIN, b2 = INT_MIN, grp = 0;
             for (int t = tb; t < te; ++t, ++bn) {
                 const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
                 const uint32_t as = bn % ACC_STAGES, aph = (bn / ACC_STAGES) & 1;
@@ -204,8 +210,9 @@ __global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_cons
                 mbar_wait(&s.b_full[bs], bph);   // complete already; orders the read of nb[]
                 const int32_t* nb = reinterpret_cast<const int32_t*>(s.stage[bs] + 2 * PLANE_BYTES);
                 const uint32_t tcol = t_lane + as * (2 * TILE_N);
-#pragma unroll 1
-                for (int g = 0; g < TILE_N / 32; ++g) {
+#pragma unroll
+                for (int gg = 0; gg < TILE_N / 32 / HALVES; ++gg) {
+                    const int g = half * (TILE_N / 32 / HALVES) + gg;
                     uint32_t h[32], l[32];
                     tmem_ld32(tcol + g * 32, h);
                     tmem_ld32(tcol + TILE_N + g * 32, l);
@@ -219,23 +226,11 @@ __global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_cons
                     for (int i = 0; i < 10; ++i) m[i] = max3(k[3 * i], k[3 * i + 1], k[3 * i + 2]);
                     m[10] = max(k[30], k[31]);
                     const int gm = max3(max3(max3(m[0], m[1], m[2]), max3(m[3], m[4], m[5]), max3(m[6], m[7], m[8])), m[9], m[10]);
-                    if (gm > b1) {
-                        // new best inside this group: find its (first) column and the group's second best
-                        int gi = 0, sec = INT_MIN;
-                        bool seen = false;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const bool is = (k[i] == gm) && !seen;
-                            gi = is ? i : gi;
-                            sec = is ? sec : max(sec, k[i]);
-                            seen = seen || is;
-                        }
-                        b2 = max(b1, sec);
-                        b1 = gm;
-                        idx = (t - t0) * TILE_N + g * 32 + gi;
-                    } else {
-                        b2 = max(b2, gm);
-                    }
+                    // top-2 over the GROUP maxima, branch-free (the word inside the best group is found later, exactly)
+                    const bool better = gm > b1;
+                    b2 = max(b2, min(b1, gm));
+                    grp = better ? (t - t0) * (TILE_N / 32) + g : grp;
+                    b1 = max(b1, gm);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -244,7 +239,7 @@ __global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_cons
                     mbar_arrive(&s.b_empty[bs]);
                 }
             }
-            if (row < p.n_q) p.out[((size_t)sp * p.n_loc + loc) * p.n_q + row] = make_int4(idx, b1, b2, 0);
+            if (row < p.n_q) p.out[((size_t)(sp * HALVES + half) * p.n_loc + loc) * p.n_q + row] = make_int4(grp, b1, b2, 0);
         }
     }
     tc_fence_before();
@@ -253,11 +248,13 @@ __global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_cons
 }
 
 // ---- resolve ---------------------------------------------------------------------------------------------------
-// Pass 1 (one warp per (location, row)): merge the splits' (best, second), accept the tensor-core argmax when its lead
-// exceeds the quantisation bound 2 (sum_k o_k + 1), else queue the row for an exact float32 rescan.
+// Pass 1 (one warp per (location, row)): merge the splits' (best group, its maximum, maximum of the other groups); when the
+// lead exceeds the quantisation bound 2 (sum_k o_k + 1) the exact argmin is one of the best group's 32 words, which are
+// evaluated here in float32 direct-difference form (lowest index on ties); else the row is queued for a full rescan.
 // state: [0] = queued rows, [1] = run-the-SIMT-kernel flag (written by bow_decide_kernel), [2] = rows rescanned (statistics)
 __global__ void __launch_bounds__(256) bow_accept_kernel(const int4* __restrict__ tc, int n_splits, const float* __restrict__ q_desc,
                                                          int n_q, int n_loc, const int* __restrict__ bad,
+                                                         const float* __restrict__ voc, const int64_t* __restrict__ voc_off,
                                                          unsigned long long* __restrict__ best, int* __restrict__ queue,
                                                          unsigned int* __restrict__ state) {
     const int lane = threadIdx.x & 31;
@@ -266,23 +263,49 @@ __global__ void __launch_bounds__(256) bow_accept_kernel(const int4* __restrict_
     const int64_t n_jobs = (int64_t)n_loc * n_q;
     const bool all_bad = *bad != 0;   // non-integer query rows: nothing from the tensor-core pass can be trusted
     for (int64_t job = wid; job < n_jobs; job += n_w) {
-        const int row = (int)(job % n_q);
+        const int row = (int)(job % n_q), loc = (int)(job / n_q);
         const float4 o = reinterpret_cast<const float4*>(q_desc + (size_t)row * 128)[lane];
         float sum = o.x + o.y + o.z + o.w;   // integer valued: exact
 #pragma unroll
         for (int k = 16; k > 0; k >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, k);
-        int b1 = INT_MIN, b2 = INT_MIN, idx = 0;
+        int b1 = INT_MIN, b2 = INT_MIN, grp = 0;
         for (int sp = 0; sp < n_splits; ++sp) {
             const int4 r = tc[(size_t)sp * n_jobs + job];
-            if (r.y > b1) { b2 = max(b1, r.z); b1 = r.y; idx = r.x; }
+            if (r.y > b1) { b2 = max(b1, r.z); b1 = r.y; grp = r.x; }
             else { b2 = max(b2, r.y); }
         }
         const long long lead = (long long)b1 - (long long)b2;
-        const bool accept = !all_bad && (b2 == INT_MIN || lead > 2LL * ((long long)sum + 1));   // a single word cannot tie
-        if (lane == 0) {
-            if (accept) best[job] = (unsigned long long)(unsigned)idx;
-            else queue[atomicAdd(&state[0], 1u)] = (int)job;
+        const bool accept = !all_bad && (b2 == INT_MIN || lead > 2LL * ((long long)sum + 1));   // a single group cannot tie
+        if (!accept) {
+            if (lane == 0) queue[atomicAdd(&state[0], 1u)] = (int)job;
+            continue;
         }
+        const int64_t v0 = voc_off[loc];
+        const int n_words = (int)(voc_off[loc + 1] - v0);
+        unsigned long long bk = ~0ULL;
+        for (int w0 = grp * 32; w0 < grp * 32 + 32; w0 += 4) {
+            float d[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int w = min(w0 + j, n_words - 1);
+                const float4 cc = reinterpret_cast<const float4*>(voc + (v0 + w) * 128)[lane];
+                const float dx = o.x - cc.x, dy = o.y - cc.y, dz = o.z - cc.z, dw = o.w - cc.w;
+                d[j] = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+            }
+#pragma unroll
+            for (int k = 16; k > 0; k >>= 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[j] += __shfl_xor_sync(0xffffffffu, d[j], k);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (w0 + j < n_words) {
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(d[j]) << 32) | (unsigned)(w0 + j);
+                    bk = key < bk ? key : bk;
+                }
+            }
+        }
+        if (lane == 0) best[job] = bk;
     }
 }
 

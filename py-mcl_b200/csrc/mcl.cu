@@ -1352,8 +1352,9 @@ int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
             const int n_qt = n_qtiles;
             int n_splits = (2 * c->sm_count + b->n_loc * n_qt - 1) / (b->n_loc * n_qt);
             n_splits = std::max(1, std::min(n_splits, 8));
-            CU(c->bow_tc_out.ensure((size_t)n_splits * nbest * sizeof(int4) + nbest * 4));
-            int* queue = reinterpret_cast<int*>(c->bow_tc_out.as<int4>() + (size_t)n_splits * nbest);
+            const int n_parts = n_splits * HALVES;   // records per (location, row): every split reports once per epilogue half
+            CU(c->bow_tc_out.ensure((size_t)n_parts * nbest * sizeof(int4) + nbest * 4));
+            int* queue = reinterpret_cast<int*>(c->bow_tc_out.as<int4>() + (size_t)n_parts * nbest);
             int32_t* q_norm = c->bow_qaux.as<int32_t>();
             int32_t* q_seg = q_norm + padded;
             int64_t* q_off = reinterpret_cast<int64_t*>(q_seg + padded);
@@ -1392,8 +1393,9 @@ int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
             CU(cudaGetLastError());
             {
                 ProfScope ps(c, PROF_VQ_RESOLVE, st);
-                bow_accept_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->bow_tc_out.as<int4>(), n_splits, d_q, n_q,
-                                                                  b->n_loc, bad, c->bow_best.as<unsigned long long>(), queue, state);
+                bow_accept_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->bow_tc_out.as<int4>(), n_parts, d_q, n_q, b->n_loc, bad,
+                                                                  b->d_voc, b->d_voc_off, c->bow_best.as<unsigned long long>(),
+                                                                  queue, state);
                 bow_decide_kernel<<<1, 1, 0, st>>>(bad, (int64_t)nbest, state);
                 bow_rescan_kernel<<<c->sm_count * 8, 256, 0, st>>>(queue, d_q, n_q, b->d_voc, b->d_voc_off,
                                                                   c->bow_best.as<unsigned long long>(), state);
