@@ -38,9 +38,10 @@ constexpr int NB_PAD = 1 << 30;             // nb of a padding word: its key can
 
 struct Smem {
     alignas(1024) uint8_t a[QTILE * 128];
-    alignas(1024) uint8_t stage[B_STAGES][STAGE_BYTES];
+    alignas(1024) uint8_t stage[B_STAGES][2 * PLANE_BYTES];   // hi plane | lo plane
+    alignas(16) int32_t nb[B_STAGES][TILE_N];                  // rint(256 |c|^2) of the stage's words
     alignas(8) uint64_t a_full, a_empty;
-    uint64_t b_full[B_STAGES], b_empty[B_STAGES];
+    uint64_t b_full[B_STAGES], b_empty[B_STAGES], nb_empty[B_STAGES];
     uint64_t acc_full[ACC_STAGES], acc_empty[ACC_STAGES];
     uint32_t tmem_base;
 };
@@ -113,6 +114,13 @@ __device__ __forceinline__ void keys32(const uint32_t (&h)[32], const uint32_t (
     }
 }
 
+// CL = CTAs per thread-block cluster.  A work item uses every codebook tile for only one 128-row query tile, so at full
+// speed the CTAs would pull 32 KB per 512 MMA cycles each out of L2 (17 TB/s over the chip): the kernel is L2-bound.  With
+// CL = 2 the two CTAs of a cluster take two query tiles of the same (split, location) and fetch each codebook tile ONCE:
+// CTA 0 issues the hi plane, CTA 1 the lo plane, both as multicast bulk copies that land in both CTAs' shared memory; a
+// stage is refilled when the MMAs of BOTH CTAs have consumed it (tcgen05.commit multicast).  The 512-byte nb[] vector is
+// loaded by each CTA for itself and released by its own epilogue warps.
+template <int CL>
 __global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
@@ -124,21 +132,31 @@ __global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_cons
     if (threadIdx.x == 0) {
         mbar_init(&s.a_full, 1);
         mbar_init(&s.a_empty, 1);
-        for (int i = 0; i < B_STAGES; ++i) { mbar_init(&s.b_full[i], 1); mbar_init(&s.b_empty[i], 1 + EPI_WARPS); }
+        for (int i = 0; i < B_STAGES; ++i) {
+            mbar_init(&s.b_full[i], 1);
+            mbar_init(&s.b_empty[i], CL);
+            mbar_init(&s.nb_empty[i], EPI_WARPS);
+        }
         for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&s.acc_full[i], 1); mbar_init(&s.acc_empty[i], EPI_WARPS); }
         mbar_fence_init();
     }
     if (warp == EPI_WARPS + 1) tmem_alloc<TMEM_COLS>(&s.tmem_base);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync();   // the peer's barriers exist before a multicast copy or commit can reach them
     tc_fence_after();
     const uint32_t tmem_base = s.tmem_base;
-    const int n_items = p.n_splits * p.n_loc * p.n_qtiles;
-    // item -> (split, location, query tile) and the split's tile range
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t ALL_CTAS = (1u << CL) - 1u;
+    const int n_qgroups = (p.n_qtiles + CL - 1) / CL;
+    const int n_items = p.n_splits * p.n_loc * n_qgroups;
+    const int item0 = blockIdx.x / CL, item_step = gridDim.x / CL;
+    // item -> (split, location, group of CL query tiles) and the split's tile range; this CTA takes tile group * CL + crank
+    // (an odd tail: the last CTA repeats the last query tile and reports nothing)
     auto decode = [&](int item, int& sp, int& loc, int& qt, int& tb, int& te, int& t0) {
-        qt = item % p.n_qtiles;
-        loc = (item / p.n_qtiles) % p.n_loc;
-        sp = item / (p.n_qtiles * p.n_loc);
+        qt = (item % n_qgroups) * CL + (int)crank;
+        loc = (item / n_qgroups) % p.n_loc;
+        sp = item / (n_qgroups * p.n_loc);
         t0 = p.tile_off[loc];
         const int nt = p.tile_off[loc + 1] - t0;
         const int per = (nt + p.n_splits - 1) / p.n_splits;
@@ -149,17 +167,25 @@ __global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_cons
     if (warp == EPI_WARPS) {
         // ================= TMA producer =================
         uint32_t bn = 0, item_n = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+        for (int item = item0; item < n_items; item += item_step, ++item_n) {
             int sp, loc, qt, tb, te, t0;
             decode(item, sp, loc, qt, tb, te, t0);
             mbar_wait(&s.a_empty, (item_n & 1) ^ 1);
             mbar_arrive_expect_tx_if(leader, &s.a_full, QTILE * 128);
-            bulk_g2s_if(leader, s.a, p.q_desc + (size_t)qt * QTILE * 128, QTILE * 128, &s.a_full);
+            bulk_g2s_if(leader, s.a, p.q_desc + (size_t)min(qt, p.n_qtiles - 1) * QTILE * 128, QTILE * 128, &s.a_full);
             for (int t = tb; t < te; ++t, ++bn) {
                 const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
                 mbar_wait(&s.b_empty[bs], bph ^ 1);
+                mbar_wait(&s.nb_empty[bs], bph ^ 1);
                 mbar_arrive_expect_tx_if(leader, &s.b_full[bs], TILE_BYTES);
-                bulk_g2s_if(leader, s.stage[bs], p.tiles + (size_t)t * STAGE_BYTES, TILE_BYTES, &s.b_full[bs]);
+                const uint8_t* rec = p.tiles + (size_t)t * STAGE_BYTES;
+                if (CL == 1) {
+                    bulk_g2s_if(leader, s.stage[bs], rec, 2 * PLANE_BYTES, &s.b_full[bs]);
+                } else {   // CL == 2: one plane per CTA, delivered to both
+                    bulk_g2s_multicast_if(leader, s.stage[bs] + crank * PLANE_BYTES, rec + crank * PLANE_BYTES, PLANE_BYTES, &s.b_full[bs],
+                                          ALL_CTAS);
+                }
+                bulk_g2s_if(leader, s.nb[bs], rec + 2 * PLANE_BYTES, TILE_N * 4, &s.b_full[bs]);
             }
         }
     } else if (warp == EPI_WARPS + 1) {
@@ -167,7 +193,7 @@ __global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_cons
         constexpr uint32_t idesc = umma_idesc(/*c=S32*/ 2, /*a=u8*/ 0, /*b=u8*/ 0, QTILE, TILE_N);
         const uint64_t a_desc = umma_desc_sw128(smem_u32(s.a));
         uint32_t bn = 0, item_n = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+        for (int item = item0; item < n_items; item += item_step, ++item_n) {
             int sp, loc, qt, tb, te, t0;
             decode(item, sp, loc, qt, tb, te, t0);
             mbar_wait(&s.a_full, item_n & 1);
@@ -184,7 +210,8 @@ __global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_cons
                 for (int k = 0; k < 4; ++k) umma_i8_if(leader, d, a_desc + 2 * k, hi_desc + 2 * k, idesc, k > 0);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_i8_if(leader, d + TILE_N, a_desc + 2 * k, lo_desc + 2 * k, idesc, k > 0);
-                tc_commit_if(leader, &s.b_empty[bs]);
+                if (CL == 1) tc_commit_if(leader, &s.b_empty[bs]);
+                else tc_commit_multicast_if(leader, &s.b_empty[bs], ALL_CTAS);
                 tc_commit_if(leader, &s.acc_full[as]);
                 __syncwarp();
             }
@@ -197,7 +224,7 @@ __global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_cons
         const int lane_base = (warp & 3) * 32;
         const uint32_t t_lane = tmem_base + ((uint32_t)lane_base << 16);
         uint32_t bn = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int item = item0; item < n_items; item += item_step) {
             int sp, loc, qt, tb, te, t0;
             decode(item, sp, loc, qt, tb, te, t0);
             const int row = qt * QTILE + lane_base + lane;
@@ -208,7 +235,7 @@ __global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_cons
                 mbar_wait(&s.acc_full[as], aph);
                 tc_fence_after();
                 mbar_wait(&s.b_full[bs], bph);   // complete already; orders the read of nb[]
-                const int32_t* nb = reinterpret_cast<const int32_t*>(s.stage[bs] + 2 * PLANE_BYTES);
+                const int32_t* nb = s.nb[bs];
                 const uint32_t tcol = t_lane + as * (2 * TILE_N);
 #pragma unroll
                 for (int gg = 0; gg < TILE_N / 32 / HALVES; ++gg) {
@@ -236,14 +263,15 @@ __global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_cons
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&s.acc_empty[as]);
-                    mbar_arrive(&s.b_empty[bs]);
+                    mbar_arrive(&s.nb_empty[bs]);
                 }
             }
-            if (row < p.n_q) p.out[((size_t)(sp * HALVES + half) * p.n_loc + loc) * p.n_q + row] = make_int4(grp, b1, b2, 0);
+            if (row < p.n_q && qt < p.n_qtiles) p.out[((size_t)(sp * HALVES + half) * p.n_loc + loc) * p.n_q + row] = make_int4(grp, b1, b2, 0);
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync();   // no CTA leaves while its peer may still multicast into it
     if (warp == EPI_WARPS + 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 

@@ -95,6 +95,7 @@ struct mcl_ctx {
     bool tc_attr_set = false, tc2_attr_set = false;
     int opt[8] = {0};  // mcl_set_option: [0] = sift_tc diagnostic mode
     int max_clusters[2] = {0, 0};   // co-resident sift_tc4 clusters of 2 / of 4 CTAs
+    int bow_max_clusters = 0;       // co-resident bow_vq_tc clusters of 2 CTAs
 };
 
 struct mcl_queries {
@@ -1373,7 +1374,22 @@ int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
             CU(cudaGetLastError());
             const size_t smem = sizeof(Smem);
             if (!c->bowtc_attr) {
-                CU(cudaFuncSetAttribute(bow_vq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CU(cudaFuncSetAttribute(bow_vq_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CU(cudaFuncSetAttribute(bow_vq_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((c->sm_count / 2) * 2);
+                cfg.blockDim = dim3(THREADS);
+                cfg.dynamicSmemBytes = smem;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = 2;
+                at[0].val.clusterDim.y = 1;
+                at[0].val.clusterDim.z = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                int n = 0;
+                if (cudaOccupancyMaxActiveClusters(&n, bow_vq_tc_kernel<2>, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+                c->bow_max_clusters = n;
                 c->bowtc_attr = true;
             }
             Params p;
@@ -1385,10 +1401,28 @@ int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
             p.n_q = n_q;
             p.n_splits = n_splits;
             p.out = c->bow_tc_out.as<int4>();
-            const int n_items = n_splits * b->n_loc * n_qtiles;
+            // CTA pairs share the codebook tiles (multicast) when there are query tiles to pair; option 5 = 1 turns it off
+            const bool cl2 = c->bow_max_clusters > 0 && c->opt[5] != 1 && n_qtiles >= 2 && (n_qtiles % 2 == 0 || n_qtiles >= 16);
+            const int n_items = n_splits * b->n_loc * (cl2 ? (n_qtiles + 1) / 2 : n_qtiles);
             {
                 ProfScope ps(c, PROF_VQ_TC, st);
-                bow_vq_tc_kernel<<<std::min(n_items, c->sm_count), THREADS, smem, st>>>(p);
+                if (cl2) {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(2 * std::min(n_items, c->bow_max_clusters));
+                    cfg.blockDim = dim3(THREADS);
+                    cfg.dynamicSmemBytes = smem;
+                    cfg.stream = st;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = 2;
+                    at[0].val.clusterDim.y = 1;
+                    at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at;
+                    cfg.numAttrs = 1;
+                    CU(cudaLaunchKernelEx(&cfg, bow_vq_tc_kernel<2>, p));
+                } else {
+                    bow_vq_tc_kernel<1><<<std::min(n_items, c->sm_count), THREADS, smem, st>>>(p);
+                }
             }
             CU(cudaGetLastError());
             {
