@@ -15,37 +15,45 @@ constexpr int VQ_WORDS = 64;
 __global__ void __launch_bounds__(128) bow_vq_kernel(
     const float4* __restrict__ q_desc /* (n_q,128) f32 */, int n_q, const float4* __restrict__ voc,
     const int64_t* __restrict__ voc_off /* rows, n_loc+1 */, const int* __restrict__ only_if /* optional device flag */,
+    int gx /* word chunks */, int gy /* row blocks */, int gz /* locations */,
     unsigned long long* __restrict__ best /* [n_loc][n_q] */) {
+    // as the fallback of the tensor-core path the kernel is launched with a small grid that walks the (gx, gy, gz) work
+    // space: when the device flag says "not needed" that is a few hundred empty blocks instead of a few hundred thousand
     if (only_if && *only_if == 0) return;
-    const int loc = blockIdx.z;
-    const int64_t v0 = voc_off[loc];
-    const int n_words = (int)(voc_off[loc + 1] - v0);
-    const int w0 = blockIdx.x * VQ_WORDS;
-    if (w0 >= n_words) return;
-    const int nw = min(VQ_WORDS, n_words - w0);
     __shared__ float4 sm[VQ_WORDS][32];
-    for (int i = threadIdx.x; i < nw * 32; i += blockDim.x) sm[i >> 5][i & 31] = voc[(v0 + w0) * 32 + i];
-    __syncthreads();
-    const int row = blockIdx.y * blockDim.x + threadIdx.x;
-    if (row >= n_q) return;
-    float4 a[32];
+    const int64_t n_work = (int64_t)gx * gy * gz;
+    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
+        const int bx = (int)(work % gx), by = (int)((work / gx) % gy), loc = (int)(work / ((int64_t)gx * gy));
+        const int64_t v0 = voc_off[loc];
+        const int n_words = (int)(voc_off[loc + 1] - v0);
+        const int w0 = bx * VQ_WORDS;
+        if (w0 >= n_words) continue;   // block-uniform
+        const int nw = min(VQ_WORDS, n_words - w0);
+        __syncthreads();               // the previous work item's readers are done with sm
+        for (int i = threadIdx.x; i < nw * 32; i += blockDim.x) sm[i >> 5][i & 31] = voc[(v0 + w0) * 32 + i];
+        __syncthreads();
+        const int row = by * blockDim.x + threadIdx.x;
+        if (row < n_q) {
+            float4 a[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) a[c] = q_desc[(int64_t)row * 32 + c];
-    float bd = INFINITY;
-    int bj = 0;
-    for (int j = 0; j < nw; ++j) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            for (int c = 0; c < 32; ++c) a[c] = q_desc[(int64_t)row * 32 + c];
+            float bd = INFINITY;
+            int bj = 0;
+            for (int j = 0; j < nw; ++j) {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const float4 b = sm[j][c];
-            const float dx = a[c].x - b.x, dy = a[c].y - b.y, dz = a[c].z - b.z, dw = a[c].w - b.w;
-            s0 = fmaf(dx, dx, s0); s1 = fmaf(dy, dy, s1); s2 = fmaf(dz, dz, s2); s3 = fmaf(dw, dw, s3);
+                for (int c = 0; c < 32; ++c) {
+                    const float4 b = sm[j][c];
+                    const float dx = a[c].x - b.x, dy = a[c].y - b.y, dz = a[c].z - b.z, dw = a[c].w - b.w;
+                    s0 = fmaf(dx, dx, s0); s1 = fmaf(dy, dy, s1); s2 = fmaf(dz, dz, s2); s3 = fmaf(dw, dw, s3);
+                }
+                const float d = (s0 + s1) + (s2 + s3);
+                if (d < bd) { bd = d; bj = w0 + j; }
+            }
+            const unsigned long long key = ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned)bj;
+            atomicMin(&best[(int64_t)loc * n_q + row], key);
         }
-        const float d = (s0 + s1) + (s2 + s3);
-        if (d < bd) { bd = d; bj = w0 + j; }
     }
-    const unsigned long long key = ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned)bj;
-    atomicMin(&best[(int64_t)loc * n_q + row], key);
 }
 
 // tf-idf scoring (Matcher.py:249-258): histogram of words, *idf, L2 normalise, dot with every image row.

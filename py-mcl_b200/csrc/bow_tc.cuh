@@ -31,6 +31,7 @@ constexpr int STAGE_BYTES = 33792;          // 32 KB + 512 B, rounded to 1 KB
 constexpr int B_STAGES = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int EPI_WARPS = 8;
+constexpr int GROUP_W = 16;                 // words per group whose maximum the epilogue tracks
 constexpr int HALVES = EPI_WARPS / 4;       // epilogue warps per TMEM lane quadrant, each owning TILE_N / HALVES words of a tile
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr int TMEM_COLS = 512;
@@ -52,7 +53,7 @@ struct Params {
     const int32_t* tile_off;    // n_loc+1: first tile of each location
     int n_loc, n_qtiles, n_q;
     int n_splits;               // each location's tiles are cut into n_splits contiguous ranges (more work items)
-    int4* out;                  // [n_splits * HALVES][n_loc][n_q]: {best 32-word group, its largest T, largest T of the other groups, -}
+    int4* out;                  // [n_splits * HALVES][n_loc][n_q]: {best GROUP_W-word group, its largest T, largest T of the other groups, -}
 };
 
 // codebook -> planes (built once per index).  One warp per word row; lane l owns dims 4l..4l+3.
@@ -248,16 +249,18 @@ __global__ void __launch_bounds__(THREADS, 1) bow_vq_tc_kernel(const __grid_cons
                     tmem_fence_regs(l);
                     int k[32];
                     keys32(h, l, nb + g * 32, k);
-                    int m[11];
+                    // top-2 over the maxima of GROUP_W-word groups, branch-free (the word inside the best group is found later,
+                    // exactly, by bow_accept_kernel: the narrower the group, the less of the float32 codebook it has to read)
 #pragma unroll
-                    for (int i = 0; i < 10; ++i) m[i] = max3(k[3 * i], k[3 * i + 1], k[3 * i + 2]);
-                    m[10] = max(k[30], k[31]);
-                    const int gm = max3(max3(max3(m[0], m[1], m[2]), max3(m[3], m[4], m[5]), max3(m[6], m[7], m[8])), m[9], m[10]);
-                    // top-2 over the GROUP maxima, branch-free (the word inside the best group is found later, exactly)
-                    const bool better = gm > b1;
-                    b2 = max(b2, min(b1, gm));
-                    grp = better ? (t - t0) * (TILE_N / 32) + g : grp;
-                    b1 = max(b1, gm);
+                    for (int sub = 0; sub < 32 / GROUP_W; ++sub) {
+                        const int* kk = k + sub * GROUP_W;
+                        const int gm = max(max3(max3(kk[0], kk[1], kk[2]), max3(kk[3], kk[4], kk[5]), max3(kk[6], kk[7], kk[8])),
+                                           max3(max3(kk[9], kk[10], kk[11]), max3(kk[12], kk[13], kk[14]), kk[15]));
+                        const bool better = gm > b1;
+                        b2 = max(b2, min(b1, gm));
+                        grp = better ? ((t - t0) * (TILE_N / 32) + g) * (32 / GROUP_W) + sub : grp;
+                        b1 = max(b1, gm);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -310,28 +313,60 @@ __global__ void __launch_bounds__(256) bow_accept_kernel(const int4* __restrict_
         }
         const int64_t v0 = voc_off[loc];
         const int n_words = (int)(voc_off[loc + 1] - v0);
-        unsigned long long bk = ~0ULL;
-        for (int w0 = grp * 32; w0 < grp * 32 + 32; w0 += 4) {
-            float d[4];
+        // The group's GROUP_W words against this row.  Lane l holds dims 4l..4l+3 of the row; it forms its partial sum for all
+        // GROUP_W words (coalesced 512-byte row loads), then the partials are summed ACROSS lanes by a transposing reduction:
+        // at distance 16 a lane keeps the half of the word list that matches its bit 4 and adds the partner's partials of
+        // those words, and so on -- 15 + 1 shuffles instead of 16 x 5, after which lanes 2i and 2i+1 own word i.
+        // Every word's sum is formed by the same pairing (l, l^16), (l, l^8), ... as bow_rescan_kernel's butterfly, so the
+        // float32 distances are bit-identical to the rescan's and the SIMT kernel's tie-breaking is preserved.
+        const int w0 = grp * GROUP_W;
+        float pw[GROUP_W];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int w = min(w0 + j, n_words - 1);
-                const float4 cc = reinterpret_cast<const float4*>(voc + (v0 + w) * 128)[lane];
-                const float dx = o.x - cc.x, dy = o.y - cc.y, dz = o.z - cc.z, dw = o.w - cc.w;
-                d[j] = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+        for (int j = 0; j < GROUP_W; ++j) {
+            const int w = min(w0 + j, n_words - 1);
+            const float4 cc = reinterpret_cast<const float4*>(voc + (v0 + w) * 128)[lane];
+            const float dx = o.x - cc.x, dy = o.y - cc.y, dz = o.z - cc.z, dw = o.w - cc.w;
+            pw[j] = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+        }
+        static_assert(GROUP_W == 16, "the reduction below is written for 16 words");
+        float p8[8], p4[4], p2[2];
+        {
+            const bool up = (lane & 16) != 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float keep = up ? pw[i + 8] : pw[i], send = up ? pw[i] : pw[i + 8];
+                p8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
             }
+        }
+        {
+            const bool up = (lane & 8) != 0;
 #pragma unroll
-            for (int k = 16; k > 0; k >>= 1) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) d[j] += __shfl_xor_sync(0xffffffffu, d[j], k);
+            for (int i = 0; i < 4; ++i) {
+                const float keep = up ? p8[i + 4] : p8[i], send = up ? p8[i] : p8[i + 4];
+                p4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
             }
+        }
+        {
+            const bool up = (lane & 4) != 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (w0 + j < n_words) {
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(d[j]) << 32) | (unsigned)(w0 + j);
-                    bk = key < bk ? key : bk;
-                }
+            for (int i = 0; i < 2; ++i) {
+                const float keep = up ? p4[i + 2] : p4[i], send = up ? p4[i] : p4[i + 2];
+                p2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
             }
+        }
+        float dist;
+        {
+            const bool up = (lane & 2) != 0;
+            const float keep = up ? p2[1] : p2[0], send = up ? p2[0] : p2[1];
+            dist = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        dist += __shfl_xor_sync(0xffffffffu, dist, 1);   // lanes 2i and 2i+1 both own word i now
+        const int wi = w0 + (lane >> 1);
+        unsigned long long bk = (wi < n_words) ? (((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)wi) : ~0ULL;
+#pragma unroll
+        for (int k = 16; k > 1; k >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, bk, k);
+            bk = other < bk ? other : bk;
         }
         if (lane == 0) best[job] = bk;
     }

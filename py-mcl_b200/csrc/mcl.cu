@@ -1438,11 +1438,14 @@ int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
             CU(cudaGetLastError());
             only_if = reinterpret_cast<const int*>(state + 1);   // many ambiguous rows or non-integer queries: float32 SIMT pass
         }
-        dim3 grid((b->max_words + mcl::VQ_WORDS - 1) / mcl::VQ_WORDS, (n_q + 127) / 128, b->n_loc);
-        if (grid.y > 65535 || grid.z > 65535) return fail(MCL_EINVAL, "bow batch too large");
+        const int gx = (b->max_words + mcl::VQ_WORDS - 1) / mcl::VQ_WORDS, gy = (n_q + 127) / 128, gz = b->n_loc;
+        const int64_t n_work = (int64_t)gx * gy * gz;
+        // on its own the kernel gets one block per work item; as the (usually idle) fallback of the tensor-core path a
+        // small grid walks the work space
+        const int64_t blocks = only_if ? std::min<int64_t>(n_work, (int64_t)c->sm_count * 16) : std::min<int64_t>(n_work, (int64_t)1 << 30);
         ProfScope ps(c, PROF_VQ, st);
-        mcl::bow_vq_kernel<<<grid, 128, 0, st>>>((const float4*)d_q, n_q, (const float4*)b->d_voc, b->d_voc_off, only_if,
-                                                 c->bow_best.as<unsigned long long>());
+        mcl::bow_vq_kernel<<<(unsigned)blocks, 128, 0, st>>>((const float4*)d_q, n_q, (const float4*)b->d_voc, b->d_voc_off, only_if,
+                                                             gx, gy, gz, c->bow_best.as<unsigned long long>());
     }
     CU(cudaGetLastError());
     return MCL_OK;
