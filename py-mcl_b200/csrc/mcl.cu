@@ -1674,7 +1674,7 @@ int laplacian_common(mcl_ctx* c, int n, const uint8_t* const* imgs, const int* h
     CU(cudaMemcpyAsync(mb + o_p, pitch.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(mb + o_s, 0, (size_t)n * 16, st));
     {
-        const int64_t threads = (int64_t)((max_w + 15) / 16) * ((max_h + mcl::LAP_RY - 1) / mcl::LAP_RY);
+        const int64_t threads = (int64_t)((max_w + mcl::LAP_PX - 1) / mcl::LAP_PX) * ((max_h + mcl::LAP_RY - 1) / mcl::LAP_RY);
         dim3 grid((unsigned)((threads + 255) / 256), n);
         ProfScope ps(c, PROF_LAP, st);
         mcl::laplacian_sums_kernel<<<grid, 256, 0, st>>>(c->lap_pix.as<uint8_t>(), (const int64_t*)mb, (const int*)(mb + o_p),
