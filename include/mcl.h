@@ -56,7 +56,7 @@ void mcl_host_free(void* p);
 /* tuning / diagnostic switches (development aid, no reference counterpart).  option 0: SIFT tensor-core kernel
  * epilogue variant, 0 = product, other values = profiling variants with meaningless counts; option 1 = 1: tile metadata from
  * global memory; option 2 = 1: BOW word assignment on the float32 SIMT kernel only; option 3 = n > 0: cap the SIFT candidate
- * list at n entries (tests: forces the overflow -> exact SIMT repair path); option 4 = n: sift_tc4 reads n (0..2) query tiles
+ * list at n entries (tests: forces the overflow -> exact SIMT repair path); option 4 = n: sift_tc4 reads n (0..1) query tiles
  * from shared instead of tensor memory; option 5: sift_tc4 thread-block clusters of 2 sharing the map tiles by multicast,
  * 0 = automatic, 1 = never, 2 = always. */
 int mcl_set_option(mcl_ctx* ctx, int option, int value);

@@ -261,12 +261,26 @@ void build_chunks(const mcl_map* m, int TILE_N, int target_tiles, std::vector<mc
     }
 }
 
-const mcl_map::ChunkSet* pick_chunks(const std::vector<mcl_map::ChunkSet>& sets, int n_qblocks, int sm_count) {
-    // want >= ~3 waves of work items (qblocks x chunks), chunks as long as possible beyond that
-    const mcl_map::ChunkSet* best = &sets.back();
-    for (const auto& cs : sets) {  // sorted by decreasing target
-        best = &cs;
-        if ((int64_t)cs.n * n_qblocks >= (int64_t)3 * sm_count) break;
+const mcl_map::ChunkSet* pick_chunks(const std::vector<mcl_map::ChunkSet>& sets, int n_qblocks, int sm_count, int64_t total_tiles = 0) {
+    if (total_tiles <= 0) {
+        // want >= ~3 waves of work items (qblocks x chunks), chunks as long as possible beyond that
+        const mcl_map::ChunkSet* best = &sets.back();
+        for (const auto& cs : sets) {  // sorted by decreasing target
+            best = &cs;
+            if ((int64_t)cs.n * n_qblocks >= (int64_t)3 * sm_count) break;
+        }
+        return best;
+    }
+    // sift_tc4: every work item pays a pipeline refill (the query tiles in tensor memory are single buffered: ~2.5 tile
+    // times), and the last round of items is only partly filled: take the set with the smallest estimated makespan
+    const mcl_map::ChunkSet* best = &sets.front();
+    double best_cost = 1e300;
+    for (const auto& cs : sets) {
+        if (cs.n == 0) continue;
+        const int64_t items = (int64_t)cs.n * n_qblocks;
+        const int64_t rounds = (items + sm_count - 1) / sm_count;
+        const double cost = (double)rounds * ((double)total_tiles / cs.n + 2.5);
+        if (cost < best_cost) { best_cost = cost; best = &cs; }
     }
     return best;
 }
@@ -521,7 +535,8 @@ extern "C" int mcl_map_create(mcl_ctx* c, int kind, int n_images, const int64_t*
             }
             return cudaSuccess;
         };
-        MCU(make_sets(m->chunk_sets, TILE_N, {64, 32, 16, 8, 4, 2, 1}));
+        // long chunks amortise sift_tc4's per-item pipeline refill; (448 + one image) x 2 records stay within its staged metadata
+        MCU(make_sets(m->chunk_sets, TILE_N, {448, 144, 64, 32, 16, 8, 4, 2, 1}));
         MCU(make_sets(m->chunk_sets2, mcl::sifttc2::TILE_N, {256, 128, 64, 32, 16, 8, 4, 2, 1}));
         // ---- second-generation kernel: norm range -> C, extension bytes + metadata per 64-row tile
         {
@@ -852,11 +867,10 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         CU(cudaFuncSetAttribute(sift_tc3_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         m->tc3_attr = true;
     }
-    const int ss_tiles = std::max(0, std::min(c->opt[4], 2));   // option 4: A tiles the MMAs read from shared memory
-    const size_t smem4 = ss_tiles == 0 ? sizeof(mcl::sifttc4::SmemT<0>) : (ss_tiles == 1 ? sizeof(mcl::sifttc4::SmemT<1>) : sizeof(mcl::sifttc4::SmemT<2>));
+    const int ss_tiles = std::max(0, std::min(c->opt[4], 1));   // option 4: A tiles the MMAs read from shared memory (2 no longer fit beside the staged metadata)
+    const size_t smem4 = ss_tiles == 0 ? sizeof(mcl::sifttc4::SmemT<0>) : sizeof(mcl::sifttc4::SmemT<1>);
     if (gen4 && !m->tc4_attr) {
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<1>)));
-        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<2>)));
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
         CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
@@ -901,7 +915,8 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
     CU(cudaMemsetAsync(d_overflow, 0, 4, st));
     for (int qb0 = 0; qb0 < n_qblocks_total; qb0 += batch_qblocks) {
         const int nqb = std::min(batch_qblocks, n_qblocks_total - qb0);
-        const mcl_map::ChunkSet* cs = pick_chunks(gen4 ? m->chunk_sets : m->chunk_sets2, nqb, c->sm_count);   // 128- / 64-row tiles
+        const mcl_map::ChunkSet* cs = gen4 ? pick_chunks(m->chunk_sets, nqb, c->sm_count, m->padded_rows / 128)   // 128-row tiles
+                                           : pick_chunks(m->chunk_sets2, nqb, c->sm_count);                     // 64-row tiles
         if (cs->n == 0) break;
         CU(cudaMemsetAsync(d_cand_count, 0, 4, st));
         Params p;
@@ -918,7 +933,7 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         p.cand_cap = (unsigned)cap;
         p.overflow = d_overflow;
         p.q_row_base = qb0 * QBLK;
-        p.meta_cap = c->opt[1] == 1 ? 0 : META_CAP;   // option 1 = 1: always read the tile metadata from global memory
+        p.meta_cap = c->opt[1] == 1 ? 0 : (gen4 ? mcl::sifttc4::META_CAP : META_CAP);   // option 1 = 1: always read the tile metadata from global memory
         // CTAs of a cluster share the map tiles (multicast): worth it for long launches (less L2 traffic -> less power); a
         // query-block count that is not a multiple of the cluster size idles CTAs for one item.
         // option 5: 0 = automatic (pairs), 1 = never, 2 / 4 = always that cluster size
@@ -967,7 +982,6 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
                     else CU(cudaLaunchKernelEx(&cfg, sift_tc4_kernel<0, 0, 4>, p));
                 }
                 else if (ss_tiles == 1) sift_tc4_kernel<0, 1><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
-                else if (ss_tiles == 2) sift_tc4_kernel<0, 2><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
                 else sift_tc4_kernel<0><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
             } else if (c->opt[0] == 3) sift_tc3_kernel<3><<<grid, THREADS, smem, st>>>(p);
             else if (c->opt[0] == 4) sift_tc3_kernel<4><<<grid, THREADS, smem, st>>>(p);

@@ -34,7 +34,7 @@ constexpr int B_STAGES = 8;
 constexpr int EPI_WARPS = ATILES * 4;
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr int TMEM_COLS = 512;
-constexpr int META_CAP = sifttc3::META_CAP;  // 64-row records staged per chunk
+constexpr int META_CAP = 1024;               // 64-row records staged per chunk (48 KB): chunks of up to 512 tiles
 
 constexpr int A_TILE_BYTES = QTILE * 128;    // 16 KB
 
