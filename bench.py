@@ -329,7 +329,7 @@ def main():
             "algorithmic_ops_per_unit": OPS_PER_UNIT, "units_per_step_per_gpu": n_frames * n_images,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default configuration, from the ncu --set full
             # capture summarised in profiles/r1_sift_tc4_ncu_full.md (tensor-bound kernel: 0.2 % of the HBM peak)
-            "traffic": 310.0e6 if (n_frames == FRAMES and n_images == LOC_PER_GPU * IMG_PER_LOC and args.algo == 1) else None,
+            "traffic": 290.0e6 if (n_frames == FRAMES and n_images == LOC_PER_GPU * IMG_PER_LOC and args.algo == 1) else None,
             "traffic_unit": "bytes per launch (ncu, profiles/r1_sift_tc4_ncu_full.md)",
         }
         cpu = None
