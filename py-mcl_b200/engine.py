@@ -8,6 +8,9 @@ other data-path collective.
 """
 from __future__ import annotations
 
+import os
+import sys
+
 import numpy as np
 
 from . import _lib
@@ -30,6 +33,9 @@ def shard_bounds(rows_per_image, world):
 
 
 def _dist():
+    # a process that never imported torch cannot have initialised torch.distributed: do not pay the import (seconds) for it
+    if "torch" not in sys.modules and "WORLD_SIZE" not in os.environ:
+        return None
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
