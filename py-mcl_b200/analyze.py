@@ -510,7 +510,8 @@ class analyzer(object):
     #############################
 
     def _laplacians(self, paths):
-        imgs = [cv2.imread(pth, 0) for pth in paths]
+        # decode on the thread pool (cv2.imread releases the GIL; at 800x600 the PNG decode is most of processRaw)
+        imgs = self._per_frame(lambda pth: cv2.imread(pth, 0), list(paths))
         if not imgs:
             return []
         return [np.float64(v) for v in self._context().laplacian_var(imgs)]
