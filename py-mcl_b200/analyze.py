@@ -279,7 +279,7 @@ class analyzer(object):
         Dynamically Optimized Retrieval (reference analyze.py:148-232): after the first frame only locations
         within +-2 of the best location are matched, and inside them only angles within +-30 degrees; every
         other particle gets a small non-zero weight.  Frame t+1's window depends on frame t's best guess, so
-        this is one masked GPU call per frame.
+        this is one masked GPU call per frame (the frames' descriptors and blur weights are prepared up front).
         """
         if self.method != 'BOW':
             print('Creating indices...')
@@ -300,7 +300,22 @@ class analyzer(object):
         resident = None if color else self._resident_map()
         n_img = self.numLocations * 25
 
-        for imagePath in glob.glob('cam1_img' + '/*' + extension):
+        # Which images a frame is matched against depends on the previous frame's best guess, but its descriptors
+        # (histogram) and its blur weight do not: extract / decode every frame up front on the thread pool (cv2 extraction
+        # is the sequential cost of this driver otherwise), then run the dependent chain of masked GPU calls.
+        frames = glob.glob('cam1_img' + '/*' + extension)
+        if color:
+            def hist(path):
+                m = Matcher(self.method, width=self.w, height=self.h)
+                m.setQuery(path)
+                return m.createHistogram(m.image)
+
+            features = self._per_frame(hist, frames)
+        else:
+            features = self._extract_many(frames)
+        blurs = self._laplacians(frames)
+
+        for imagePath, feature, blurFactor in zip(frames, features, blurs):
             if bestCircleIndex is None:
                 locs = list(range(self.numLocations))
             else:
@@ -309,10 +324,9 @@ class analyzer(object):
                 locs = [i for i in range(self.numLocations) if i >= lower and i <= upper]
             if color:
                 # the colour branch of optRun ignores the angle window (reference Matcher.py:377-385)
-                matcher.setQuery(imagePath)
-                p = self._color_locations(matcher, [matcher.createHistogram(matcher.image)], locs)[0]
+                p = self._color_locations(matcher, [feature], locs)[0]
             else:
-                des = self._extract(matcher, imagePath)
+                des = feature
                 window = angle_window(bestAngleIndex) if bestAngleIndex is not None else [True] * 25
                 mask = np.zeros((1, n_img), dtype=np.uint8)
                 for i in locs:
@@ -327,7 +341,6 @@ class analyzer(object):
             print('\t' + imagePath)
 
             command = self.commands[imagePath.replace('cam1_img/', '').replace(extension, '')]
-            blurFactor = self.Laplacian(imagePath)
             adjusted, best = self._filter(command, previousProbs, p, blurFactor)
             bestCircleIndex, bestAngleIndex = best
             self.bestGuess.extend([[bestCircleIndex, bestAngleIndex]])

@@ -26,6 +26,10 @@ with contextlib.redirect_stdout(io.StringIO()):
     a.createRawP = a.createRawP  # (createRawP re-runs createIndex like the reference; timed as a whole below)
     t2 = time.perf_counter(); a.createRawP(); t3 = time.perf_counter()
     a.processRaw(); t4 = time.perf_counter()
+with contextlib.redirect_stdout(io.StringIO()):
+    b = analyzer("SIFT", w, h)
+    t5 = time.perf_counter(); b.optP(); t6 = time.perf_counter()
+res["optP_s(incl. index)"] = t6 - t5
 res.update({"createIndex_s": t1 - t0, "createRawP_s(incl. index)": t3 - t2, "processRaw_s": t4 - t3,
             "image_matches": n_frames * 175, "image_matches_per_s_createRawP": n_frames * 175 / (t3 - t2)})
 # oracle pipeline on the host for the first few frames (cv2 extraction + cv2 brute force + numpy filter)
