@@ -462,6 +462,12 @@ class BowIndex:
         except Exception:
             pass
 
+    def score_device(self, queries, d_scores_ptr, d_words_ptr=None, stream=None):
+        """Asynchronous: resident queries (QueryBatch of kind BOWQ), raw device pointers (e.g. torch tensor .data_ptr()):
+        scores (n_queries, total_images) float32, optional words (n_loc, total rows) int32."""
+        _check(self.ctx._lib.mcl_bow_score_device(self._h, queries._h, _p(d_words_ptr) if d_words_ptr else None,
+                                                  _p(d_scores_ptr), _p(stream) if stream else None), "mcl_bow_score_device")
+
     def score(self, q_descs, want_words=False):
         """-> (scores (n_queries, total_images) f32, words (n_loc, total rows) int32 or None)."""
         off, cat, code = pack_descriptors(BOWQ, q_descs)
