@@ -90,6 +90,40 @@ def test_sidecar_round_trips_what_readprob_parses(tmp_path, monkeypatch):
     assert a.readSidecar("rawP.txt") is None
 
 
+def test_large_batches_are_staged_without_changing_the_bytes():
+    """pack_descriptors concatenates big batches into a reusable staging buffer (pinned when a CUDA runtime is there), on a
+    few threads: the result must equal np.concatenate, for mixed dtypes too, and stay valid until the next call."""
+    rng = np.random.default_rng(3)
+    frames = [rng.integers(0, 256, size=(int(n), 128)).astype(np.float32) for n in rng.integers(1500, 2500, size=24)]
+    frames[5] = None
+    frames[7] = frames[7].astype(np.uint8)          # mixed dtypes are converted to float32
+    off, cat, code = _lib.pack_descriptors(_lib.SIFT, frames)
+    real = [f for f in frames if f is not None]
+    assert code == _lib.F32 and cat.dtype == np.float32 and cat.flags.c_contiguous
+    assert cat.nbytes >= (8 << 20)                   # the threaded path
+    assert np.array_equal(cat, np.concatenate([f.astype(np.float32) for f in real]))
+    assert list(off) == list(np.cumsum([0] + [0 if f is None else len(f) for f in frames]))
+    first = cat.copy()
+    off2, cat2, _ = _lib.pack_descriptors(_lib.SIFT, frames[:12])   # reuses the buffer: only the latest result is valid
+    assert np.array_equal(cat2, first[:off2[-1]])
+    small = _lib.pack_descriptors(_lib.ORB, [np.zeros((3, 32), np.uint8), np.ones((2, 32), np.uint8)])[1]
+    assert small.shape == (5, 32) and small[3:].min() == 1
+
+
+def test_typed_lists_round_trip_through_the_filter_packing():
+    """analyzer._pack/_unpack: the scalar-type tags (Python number / np.float64 / np.float32) survive the trip to the
+    (L, 1+I) float64 matrix the typed filter kernel works on, with exact values."""
+    from pymcl_b200.analyze import analyzer
+    lists = [[1, [1 / 75] * 25], [np.float32(21.411722), [np.float32(0.1)] * 25], [np.float64(3.5), [np.float64(0.25)] * 25],
+             [np.float32(7.0), [0.5] * 25]]
+    values, tags = analyzer._pack(lists)
+    assert values.shape == (4, 26) and tags.tolist() == [[0, 0], [2, 2], [1, 1], [2, 0]]
+    back = analyzer._unpack(values, tags)
+    assert type(back[0][0]) is float and type(back[0][1][0]) is float and back[0][1][0] == 1 / 75
+    assert type(back[1][0]) is np.float32 and back[1][0] == np.float32(21.411722) and type(back[1][1][3]) is np.float32
+    assert type(back[2][0]) is np.float64 and type(back[3][0]) is np.float32 and type(back[3][1][0]) is float
+
+
 def test_pack_descriptors():
     rng = np.random.default_rng(0)
     a, b = synth.sift_like(rng, 5), synth.sift_like(rng, 3)
