@@ -181,6 +181,22 @@ def test_sift_candidate_overflow_is_repaired_on_the_device(ctx):
     m.close()
 
 
+def test_sift_tile_records_from_global_memory_path(ctx):
+    """sift_tc3 / sift_tc4 stage a chunk's 64-row records in shared memory; chunks longer than the staging area (a single
+    image of > 65 536 rows for tc4) read them from global memory instead.  Option 1 forces that path on ordinary sizes."""
+    map_des, frames = synth.sift_map_and_frames(21, 9, 700, 4, 500)
+    m = _lib.MapIndex(ctx, "SIFT", map_des)
+    want = m.match_counts(frames, algo=_lib.ALGO_SIMT)
+    assert want.sum() > 100
+    ctx.set_option(1, 1)
+    try:
+        for algo in (_lib.ALGO_TENSOR, _lib.ALGO_TENSOR_V3):
+            assert np.array_equal(m.match_counts(frames, algo=algo), want), algo
+    finally:
+        ctx.set_option(1, 0)
+    m.close()
+
+
 def test_sift_ratio_known_answers(ctx, golden_dir):
     """The cv2 ratio semantics float(sqrtf(d0^2)) < 0.7*float(sqrtf(d1^2)) on the survey's integer pairs:
     build 1 query row and 2 map rows with exactly those squared distances."""
