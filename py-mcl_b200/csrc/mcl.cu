@@ -206,7 +206,8 @@ size_t row_bytes(int kind, int dtype) {
 int ingest_rows128(mcl_ctx* c, cudaStream_t st, const void* h_src, int dtype, int64_t n_rows, int n_seg,
                    const int64_t* d_src_off, const int64_t* d_dst_off, int64_t padded_rows, uint8_t* d_desc,
                    int32_t* d_norm, int32_t* d_seg, uint8_t* d_stage = nullptr /* null: the context's staging buffer */,
-                   bool check_now = true, const int32_t* d_perm = nullptr) {
+                   bool check_now = true, const int32_t* d_perm = nullptr, cudaStream_t copy_st = nullptr,
+                   cudaEvent_t copied = nullptr) {
     CU(cudaMemsetAsync(d_desc, 0, (size_t)padded_rows * 128, st));
     CU(cudaMemsetAsync(d_norm, 0xFF, (size_t)padded_rows * 4, st));
     CU(cudaMemsetAsync(d_seg, 0xFF, (size_t)padded_rows * 4, st));
@@ -216,7 +217,15 @@ int ingest_rows128(mcl_ctx* c, cudaStream_t st, const void* h_src, int dtype, in
         CU(c->stage.ensure(bytes));
         d_stage = c->stage.as<uint8_t>();
     }
-    CU(cudaMemcpyAsync(d_stage, h_src, bytes, cudaMemcpyHostToDevice, st));
+    if (copy_st) {
+        // the H2D copy goes on a stream that carries nothing but copies: a memset or conversion kernel queued in front of
+        // it would wait for SMs behind the persistent matching kernel and hold the copy back with it
+        CU(cudaMemcpyAsync(d_stage, h_src, bytes, cudaMemcpyHostToDevice, copy_st));
+        CU(cudaEventRecord(copied, copy_st));
+        CU(cudaStreamWaitEvent(st, copied, 0));
+    } else {
+        CU(cudaMemcpyAsync(d_stage, h_src, bytes, cudaMemcpyHostToDevice, st));
+    }
     int* bad = c->flags.as<int>() + 2;
     if (check_now) CU(cudaMemsetAsync(bad, 0, 4, st));
     {
@@ -1131,8 +1140,13 @@ int match_counts_sift_pipelined(mcl_map* m, int n_queries, const int64_t* offs, 
                                 double ratio, const uint8_t* mask, int32_t fill_value, int algo, int32_t* out_counts) {
     mcl_ctx* c = m->ctx;
     const int64_t total_rows = offs[n_queries];
-    // Two or three parts with growing sizes (1/16, 3/16, 3/4 of the rows): only the first, small part's copy is exposed;
-    // the later, large parts keep the tensor-core launches long (short launches lose a few % to tails and A reloads).
+    // Two or three parts with growing sizes (1/16, 3/16, 3/4 of the rows): only the first, small part's copy is exposed,
+    // and the later, large parts keep the tensor-core launches long (short launches lose a few % to tails and A reloads).
+    // All copies are queued at once on a stream that carries only copies (55 GB/s: the whole 210 MB batch of config 3 is
+    // on the device after 4 ms, well before the second part's matching ends); each part's memsets and conversion kernel
+    // run on the main stream in front of its matching.  (With the conversion kernels on the copy stream every copy
+    // waited, in stream order, behind a kernel that could not get an SM while the persistent matching kernel was
+    // running: 2.5 ms of gaps per call.)
     int P = total_rows >= 8 * 32768 ? 3 : (total_rows >= 2 * 32768 ? 2 : 1);
     P = std::min(P, n_queries);
     if (P <= 1 || m->n_images == 0) return 1;
@@ -1175,9 +1189,20 @@ int match_counts_sift_pipelined(mcl_map* m, int n_queries, const int64_t* offs, 
         d_mask = c->tmp_mask.as<uint8_t>();
     }
     int* bad = c->flags.as<int>() + 2;
-    CU(cudaMemsetAsync(bad, 0, 4, cs));
+    CU(cudaMemsetAsync(bad, 0, 4, st));
     std::vector<mcl_queries> parts(P);
     int rc = MCL_OK;
+    // MCL_DEBUG: device timeline of the parts (events on both streams), printed after the call
+    const bool dbg = getenv("MCL_DEBUG") != nullptr;
+    std::vector<cudaEvent_t> tl;
+    auto mark = [&](cudaStream_t s_) {
+        if (!dbg) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s_);
+        tl.push_back(e);
+    };
+    mark(cs);
     for (int p = 0; p < P && rc == MCL_OK; ++p) {
         mcl_queries& q = parts[p];
         const int f0 = fb[p], f1 = fb[p + 1];
@@ -1194,15 +1219,18 @@ int match_counts_sift_pipelined(mcl_map* m, int n_queries, const int64_t* offs, 
         q.d_norm = c->tq_norm.as<int32_t>() + region[p];
         q.d_frame = c->tq_frame.as<int32_t>() + region[p];
         if (q.n_queries == 0) continue;
+        // copies on the copy stream (all parts' copies are queued at once and run back to back); the memsets and the
+        // conversion kernel of a part on the main stream, right in front of its matching
         CU(cudaMemcpyAsync(q.d_off, q.h_off.data(), (size_t)(q.n_queries + 1) * 8, cudaMemcpyHostToDevice, cs));
-        rc = ingest_rows128(c, cs, (const uint8_t*)q_desc + (size_t)offs[f0] * row_b, q_dtype, q.rows, q.n_queries, q.d_off,
+        rc = ingest_rows128(c, st, (const uint8_t*)q_desc + (size_t)offs[f0] * row_b, q_dtype, q.rows, q.n_queries, q.d_off,
                             q.d_off, q.padded_rows, (uint8_t*)q.d_desc, q.d_norm, q.d_frame,
-                            c->stage.as<uint8_t>() + (size_t)offs[f0] * row_b, false);
+                            c->stage.as<uint8_t>() + (size_t)offs[f0] * row_b, false, nullptr, cs, c->part_events[p]);
         if (rc) break;
-        CU(cudaEventRecord(c->part_events[p], cs));
-        CU(cudaStreamWaitEvent(st, c->part_events[p], 0));
+        mark(cs);
+        mark(st);
         rc = match_device(m, &q, mode, ratio, d_mask ? d_mask + (size_t)f0 * ni : nullptr, fill_value, algo,
                           c->tmp_counts.as<int32_t>() + (size_t)f0 * ni, st);
+        mark(st);
     }
     if (rc == MCL_OK) {
         cudaError_t e = cudaMemcpyAsync(out_counts, c->tmp_counts.p, n_out * 4, cudaMemcpyDeviceToHost, st);
@@ -1211,6 +1239,16 @@ int match_counts_sift_pipelined(mcl_map* m, int n_queries, const int64_t* offs, 
     int h_bad = 0;
     cudaStreamSynchronize(cs);
     cudaError_t e1 = cudaStreamSynchronize(st);
+    if (dbg && tl.size() == (size_t)(1 + 3 * P)) {
+        for (int p = 0; p < P; ++p) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, tl[0], tl[1 + 3 * p]);       // copy + ingest of the part done (copy stream)
+            cudaEventElapsedTime(&b, tl[0], tl[2 + 3 * p]);       // matching of the part may start (main stream)
+            cudaEventElapsedTime(&d, tl[0], tl[3 + 3 * p]);       // matching done
+            fprintf(stderr, "[mcl] part %d (%d frames): ingested at %.2f ms, matching %.2f -> %.2f ms\n", p, fb[p + 1] - fb[p], a, b, d);
+        }
+        for (auto e : tl) cudaEventDestroy(e);
+    }
     if (rc == MCL_OK && e1 != cudaSuccess) rc = fail(MCL_ECUDA, "stream sync failed: %s", cudaGetErrorString(e1));
     if (rc == MCL_OK && q_dtype == MCL_F32) {
         CU(cudaMemcpy(&h_bad, bad, 4, cudaMemcpyDeviceToHost));
