@@ -10,6 +10,16 @@
 // tensor pipe works on the other two (2 x 268 cycles), which covers the drain (two 64-column loads + hand-back).
 // Everything else (norm-sorted rows, bracketed pre-filter, candidate list, exact fix-up, metadata records per 64 rows)
 // is sift_tc3's; the candidate format and sift_fixup3_kernel are shared.
+//
+// What measurements added on top (DESIGN.md section 4.1 has the numbers):
+//  * the epilogue was the limiter (3 warps per SMSP, ALU pipe at half rate): tile records are prefetched with ld.shared
+//    before the accumulator wait, a 128-row tile that lies in one image with close norms gets ONE bracket update
+//    (TileMeta::merge), and the exact image-end ratio test sits behind an inline conservative gate (finalize_gate);
+//  * every work item starts with a pipeline refill (the query tiles in tensor memory are single buffered), so chunks are
+//    long: up to 448 tiles, their records staged in 48 KB of shared memory, the chunk set picked by a makespan estimate;
+//  * CTA pairs (clusters of 2, template parameter CL) fetch every map tile once and multicast it: half the L2 -> SM traffic;
+//  * MODE 5 stamps clock64 around the waits of one epilogue warp and of the MMA warp (how the above was found);
+//    SS > 0 reads A tiles from shared memory instead (measured: no gain, kept as an experiment).
 #pragma once
 #include "common.cuh"
 #include "sift_tc3.cuh"
