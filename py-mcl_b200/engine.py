@@ -98,6 +98,22 @@ class ShardedMap(object):
         return gather_columns(local, self.bounds, self.group)
 
 
+_pinned_cache = {}
+
+
+def _pinned(shape, dtype):
+    """A reusable pinned host tensor (NCCL path): pageable .cuda() / .cpu() copies of a few MB cost more than the
+    all-gather itself."""
+    import torch
+    key = (tuple(shape), dtype)
+    t = _pinned_cache.get(key)
+    if t is None:
+        if len(_pinned_cache) > 16:
+            _pinned_cache.clear()
+        t = _pinned_cache[key] = torch.empty(shape, dtype=dtype).pin_memory()
+    return t
+
+
 def gather_columns(local, bounds, group=None):
     """The one data-path collective: every rank holds columns [lo, hi) = bounds[rank] of an (F, n) result; one
     all_gather_into_tensor of the zero-padded slices gives every rank the full matrix (NCCL on the GPU, gloo in tests)."""
@@ -108,14 +124,27 @@ def gather_columns(local, bounds, group=None):
     import torch
     F = local.shape[0]
     maxw = max(h - l for l, h in bounds)
-    pad = np.zeros((F, maxw), dtype=local.dtype)
-    pad[:, :local.shape[1]] = local
-    t = torch.from_numpy(pad)
-    if d.get_backend(group) == "nccl":
-        t = t.cuda()
+    nccl = d.get_backend(group) == "nccl"
+    tdt = torch.from_numpy(np.empty(0, dtype=local.dtype)).dtype
+    if nccl:
+        stage = _pinned((F, maxw), tdt)
+        sv = stage.numpy()
+        sv[:, :local.shape[1]] = local
+        sv[:, local.shape[1]:] = 0
+        t = stage.cuda(non_blocking=True)
+    else:
+        pad = np.zeros((F, maxw), dtype=local.dtype)
+        pad[:, :local.shape[1]] = local
+        t = torch.from_numpy(pad)
     out = torch.empty((world * F, maxw), dtype=t.dtype, device=t.device)   # concatenation along dim 0
     d.all_gather_into_tensor(out, t, group=group)
-    out = out.cpu().numpy().reshape(world, F, maxw)
+    if nccl:
+        host = _pinned((world * F, maxw), tdt)
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out = host.numpy().reshape(world, F, maxw)
+    else:
+        out = out.numpy().reshape(world, F, maxw)
     full = np.empty((F, bounds[-1][1]), dtype=local.dtype)
     for r, (l, h) in enumerate(bounds):
         full[:, l:h] = out[r][:, :h - l]
