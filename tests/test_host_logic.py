@@ -294,3 +294,89 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["value"] == line["value"] and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and "workload" in line["config"]
     assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+class FakeContext:
+    """Stands in for _lib.Context on CPU: every GPU entry point the colour drivers use, answered by the oracle.  Lets the
+    CPU suite run analyzer('Color') end to end (host logic, text formats, typed hand-over to the filter) against the files
+    the unmodified reference wrote."""
+
+    def chi2(self, q, m, eps=1e-10):
+        return oracle.chi2_matrix(q, m, eps)
+
+    def laplacian_var(self, imgs):
+        return np.array([oracle.laplacian_var(i) for i in imgs], dtype=np.float64)
+
+    @staticmethod
+    def _lists(values, tags):
+        conv = {_lib.T_PY: float, _lib.T_F64: np.float64, _lib.T_F32: np.float32}
+        return [[conv[int(t0)](row[0]), [conv[int(t1)](v) for v in row[1:]]] for row, (t0, t1) in zip(values, tags)]
+
+    def filter_step(self, stages, cmd, blur, prev, cur):
+        assert stages == _lib.F_ALL
+        z = np.zeros((len(prev), 2), np.int8)
+        p2, out, _, best = self.filter_step_typed(stages, cmd, blur, _lib.T_PY, prev, z, cur, z)
+        return p2, out, best
+
+    def filter_step_typed(self, stages, cmd, blur, blur_type, prev, prev_type, cur, cur_type):
+        assert stages == _lib.F_ALL
+        p, c = self._lists(prev, prev_type), self._lists(cur, cur_type)
+        adj, best = oracle.filter_step(cmd, p, c, np.float64(blur) if blur_type == _lib.T_F64 else float(blur))
+        tag = lambda x: _lib.T_F32 if isinstance(x, np.float32) else (_lib.T_F64 if isinstance(x, np.float64) else _lib.T_PY)
+        pack = lambda rows: np.array([[r[0]] + list(r[1]) for r in rows], dtype=np.float64)
+        return pack(p), pack(adj), np.array([[tag(r[0]), tag(r[1][0])] for r in adj], np.int8), tuple(best)
+
+
+def test_analyzer_color_drivers_on_a_fake_context(tmp_path, monkeypatch, golden_dir):
+    import glob
+    import json
+    import cv2
+    if json.load(open(os.path.join(golden_dir, "desc_hash.json")))["cv2"] != cv2.__version__:
+        pytest.skip("different OpenCV build than the golden run")
+    from pymcl_b200.analyze import analyzer
+    root = str(tmp_path / "ds")
+    synth.make_dataset(root, seed=0, n_locations=7, n_images=25, n_frames=6, view=(160, 120))
+    monkeypatch.chdir(root)
+    orig = glob.glob
+    monkeypatch.setattr(glob, "glob", lambda *a, **k: sorted(orig(*a, **k)))
+    monkeypatch.setattr(_lib, "default_context", lambda: FakeContext())
+    read = lambda name: open(name).read()
+    gold = lambda name: open(os.path.join(golden_dir, name)).read()
+    a = analyzer("Color", 160, 120)
+    a.createRawP()
+    assert read("rawP.txt") == gold("color_rawP.txt")
+    a.processRaw()
+    assert read("out.txt") == gold("color_out.txt") and read("bestGuess.txt") == gold("color_bestGuess.txt")
+    b = analyzer("Color", 160, 120)
+    b.optP()
+    assert read("out.txt") == gold("color_dor_out.txt") and read("bestGuess.txt") == gold("color_dor_bestGuess.txt")
+
+
+def test_analyzer_sift_drivers_on_a_fake_context(tmp_path, monkeypatch, golden_dir):
+    """analyzer('SIFT') end to end on CPU: cv2 extraction on the thread pool, batched createRawP, the DOR masks of optP,
+    the particle filter hand-over and the text writers -- with the GPU entry points answered by the oracle -- against the
+    files the unmodified reference wrote."""
+    import glob
+    import json
+    import cv2
+    if json.load(open(os.path.join(golden_dir, "desc_hash.json")))["cv2"] != cv2.__version__:
+        pytest.skip("different OpenCV build than the golden run")
+    from pymcl_b200.analyze import analyzer
+    root = str(tmp_path / "ds")
+    synth.make_dataset(root, seed=0, n_locations=7, n_images=25, n_frames=6, view=(160, 120))
+    monkeypatch.chdir(root)
+    orig = glob.glob
+    monkeypatch.setattr(glob, "glob", lambda *a, **k: sorted(orig(*a, **k)))
+    monkeypatch.setattr(_lib, "default_context", lambda: FakeContext())
+    monkeypatch.setattr(_lib, "MapIndex", lambda ctx, kind, descs: OracleLocal(descs))
+    read = lambda name: open(name).read()
+    gold = lambda name: open(os.path.join(golden_dir, name)).read()
+    a = analyzer("SIFT", 160, 120)
+    a.sidecar = True
+    a.createRawP()
+    assert read("rawP.txt") == gold("sift_rawP.txt")
+    a.processRaw()          # through the binary side-car
+    assert read("out.txt") == gold("sift_out.txt") and read("bestGuess.txt") == gold("sift_bestGuess.txt")
+    b = analyzer("SIFT", 160, 120)
+    b.optP()
+    assert read("out.txt") == gold("sift_dor_out.txt") and read("bestGuess.txt") == gold("sift_dor_bestGuess.txt")
