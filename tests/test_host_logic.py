@@ -380,3 +380,42 @@ def test_analyzer_sift_drivers_on_a_fake_context(tmp_path, monkeypatch, golden_d
     b = analyzer("SIFT", 160, 120)
     b.optP()
     assert read("out.txt") == gold("sift_dor_out.txt") and read("bestGuess.txt") == gold("sift_dor_bestGuess.txt")
+
+
+class OracleMap(object):
+    """_lib.MapIndex(ctx, kind, descs) answered by the oracle, any kind and mode."""
+
+    def __init__(self, ctx, kind, descs):
+        self.kind, self.descs, self.n_images = kind, descs, len(descs)
+
+    def match_counts(self, q_descs, mode=0, ratio=0.7, mask=None, fill_value=1, algo=0):
+        if self.kind == "ORB":
+            pair = oracle.orb_pair_count_crosscheck if mode == _lib.CROSSCHECK else (lambda q, m: oracle.orb_pair_count_knn(q, m, ratio))
+        else:
+            pair = lambda q, m: oracle.sift_pair_count(q, m, ratio)
+        out = np.zeros((len(q_descs), len(self.descs)), dtype=np.int32)
+        for f, q in enumerate(q_descs):
+            for i, m in enumerate(self.descs):
+                out[f, i] = fill_value if (mask is not None and not mask[f, i]) else pair(q, m)
+        return out
+
+
+@pytest.mark.parametrize("mode,tag", [("knn", "orb_knn"), ("crosscheck", "orb_cc")])
+def test_analyzer_orb_driver_on_a_fake_context(tmp_path, monkeypatch, golden_dir, mode, tag):
+    import glob
+    import json
+    import cv2
+    if json.load(open(os.path.join(golden_dir, "desc_hash.json")))["cv2"] != cv2.__version__:
+        pytest.skip("different OpenCV build than the golden run")
+    from pymcl_b200.analyze import analyzer
+    root = str(tmp_path / "ds")
+    synth.make_dataset(root, seed=0, n_locations=7, n_images=25, n_frames=6, view=(160, 120))
+    monkeypatch.chdir(root)
+    orig = glob.glob
+    monkeypatch.setattr(glob, "glob", lambda *a, **k: sorted(orig(*a, **k)))
+    monkeypatch.setattr(_lib, "default_context", lambda: FakeContext())
+    monkeypatch.setattr(_lib, "MapIndex", OracleMap)
+    a = analyzer("ORB", 160, 120)
+    a.orb_mode = mode
+    a.createRawP()
+    assert open("rawP.txt").read() == open(os.path.join(golden_dir, tag + "_rawP.txt")).read()
