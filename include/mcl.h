@@ -8,6 +8,9 @@
  * Conventions
  *   - every function returns 0 on success and a negative MCL_E* code on error; mcl_last_error() returns a
  *     thread-local message for the last failure on the calling thread.
+ *   - *_device functions use the context's scratch buffers (candidate lists, staging): calls on one context must be
+ *     issued from one host thread and are ordered like their streams; do not run two of them concurrently on
+ *     different streams of the same context.
  *   - host buffers are caller-owned and only read/written during the call; device memory is owned by handles.
  *   - one host thread per handle.  Functions without a `stream` argument are synchronous on return;
  *     *_device functions only enqueue work on `stream` (a cudaStream_t, NULL = the context's own stream).
@@ -37,10 +40,9 @@ enum { MCL_U8 = 0, MCL_F32 = 1 };
 enum { MCL_KNN2_RATIO = 0 /* knnMatch(k=2) + ratio lambda, Matcher.py:218-219,279-280 */,
        MCL_CROSSCHECK = 1 /* ORB only: BFMatcher(NORM_HAMMING, crossCheck=True).match, Matcher.py:180-182 */ };
 /* algorithm selector for SIFT (testing / profiling) */
-enum { MCL_ALGO_AUTO = 0, MCL_ALGO_TENSOR = 1 /* tcgen05, A in tensor memory, norm-sorted groups, N = 128 (sift_tc4): the product path */,
-       MCL_ALGO_SIMT = 2 /* dp4a, exact top-2 */, MCL_ALGO_TENSOR_V1 = 3 /* tcgen05, operands in shared memory (sift_tc) */,
-       MCL_ALGO_TENSOR_V2 = 4 /* tcgen05, A in tensor memory + K extension 128->160 (sift_tc2) */,
-       MCL_ALGO_TENSOR_V3 = 5 /* as the product path with N = 64 tiles and double-buffered accumulators (sift_tc3) */ };
+enum { MCL_ALGO_AUTO = 0, MCL_ALGO_TENSOR = 1 /* tcgen05: SIFT sift_tc4 (A in tensor memory, norm-sorted groups, N = 128); ORB knn on
+                                                 the tensor cores (tc9, +-1 rows) */,
+       MCL_ALGO_SIMT = 2 /* SIFT dp4a / ORB xor+popc, exact top-2 per thread */ };
 
 /* ---- context ---------------------------------------------------------------------------------------- */
 int mcl_init(int device_id, mcl_ctx** out);
@@ -50,15 +52,20 @@ const char* mcl_last_error(void);
  * [7]=whole-image exact rescans done by the SIFT fix-up kernels so far (statistics) */
 int mcl_device_info(mcl_ctx* ctx, int64_t info[8]);
 int mcl_sync(mcl_ctx* ctx);
+/* statistics since mcl_init (synchronises): out[0] = SIFT candidates resolved by the exact fix-up, [1] = SIFT whole-image exact
+ * rescans, [2] = SIFT/ORB (frame, image) pairs recomputed by the SIMT kernel because a candidate list was full, [3] = BOW
+ * rows rescanned over a whole code book in the last call, [4] = ORB candidates resolved exactly, [5..7] reserved.
+ * No reference counterpart (bench.py reports them per input distribution). */
+int mcl_stats(mcl_ctx* ctx, int64_t out[8]);
 /* pinned host memory for the end-to-end path (cudaHostAlloc) */
 int mcl_host_alloc(size_t bytes, void** out);
 void mcl_host_free(void* p);
 /* tuning / diagnostic switches (development aid, no reference counterpart).  option 0: SIFT tensor-core kernel
- * epilogue variant, 0 = product, other values = profiling variants with meaningless counts; option 1 = 1: tile metadata from
- * global memory; option 2 = 1: BOW word assignment on the float32 SIMT kernel only; option 3 = n > 0: cap the SIFT candidate
- * list at n entries (tests: forces the overflow -> exact SIMT repair path); option 4 = n: sift_tc4 reads n (0..1) query tiles
- * from shared instead of tensor memory; option 5: sift_tc4 thread-block clusters of 2 sharing the map tiles by multicast,
- * 0 = automatic, 1 = never, 2 = always. */
+ * epilogue variant, 0 = product, other values = profiling variants with meaningless counts; option 1 = 1: tile records from
+ * global memory; option 2 = 1: BOW word assignment on the float32 SIMT kernel only; option 3 = n > 0: cap the SIFT / ORB
+ * candidate list at n entries (tests: forces the dirty-pair -> exact SIMT repair path); option 5: thread-block clusters of 2
+ * sharing the map tiles by multicast, 0 = automatic, 1 = never, 2 = always; option 6 = n > 0: degrees between neighbouring map
+ * images for mcl_filter_step's forward-command rule (the reference's 15, analyze.py:331-335). */
 int mcl_set_option(mcl_ctx* ctx, int option, int value);
 /* number of kernels this library launched since mcl_init (bench.py's gpu_launches) */
 int64_t mcl_launch_count(mcl_ctx* ctx);
@@ -85,6 +92,14 @@ int mcl_map_info(mcl_map* map, int64_t info[4]);
  * n_queries frames; q_row_offsets has n_queries+1 entries. */
 int mcl_queries_create(mcl_ctx* ctx, int kind, int n_queries, const int64_t* q_row_offsets, const void* q_desc,
                        int q_dtype, mcl_queries** out);
+/* The same batch built from rows that are ALREADY in device memory (d_desc: rows x 128|32|64 of q_dtype, row-major;
+ * q_row_offsets stays a host array).  Only enqueues work on `stream` (NULL = the context's stream); the multi-GPU driver
+ * uploads each frame on ONE rank and all-gathers the rows over NVLink, so every rank builds its batch from device memory
+ * (replaces the same des1 as above).  Integer-valuedness of float32 SIFT rows is recorded on the device:
+ * mcl_queries_validate synchronises and returns MCL_EDATA if the ingest saw a non-integer value. */
+int mcl_queries_create_device(mcl_ctx* ctx, int kind, int n_queries, const int64_t* q_row_offsets, const void* d_desc,
+                              int q_dtype, void* stream, mcl_queries** out);
+int mcl_queries_validate(mcl_queries* q);
 void mcl_queries_destroy(mcl_queries* q);
 
 /* ---- matching ------------------------------------------------------------------------------------------

@@ -8,7 +8,7 @@ the reference lives in third-party wheels that are not vendored under /root/refe
 requirements file, so no pinned versions): OpenCV (``cv2.BFMatcher`` / ``FlannBasedMatcher`` /
 ``Laplacian``; 4.13.0 in this image), SciPy (``scipy.cluster.vq.vq``; 1.18.1), scikit-learn
 (``preprocessing.normalize``; 1.9.0) and NumPy (2.3.5).  Their published algorithms are restated
-here in plain numpy; ``oracle/pin_oracle.py`` + ``tests/test_oracle.py`` pin every restatement
+here in plain numpy; ``oracle/make_golden.py`` + ``tests/test_oracle.py`` pin every restatement
 against (a) the third-party routine itself on seeded inputs, (b) the unmodified reference modules
 run through import shims in the build container (``oracle/ref_shims.py``; outputs committed under
 ``tests/golden/``) and (c) the known-answer vectors in SURVEY.md §8(c).
@@ -50,7 +50,10 @@ def l2sq_int(des1, des2):
     b = _as_int_desc(des2)
     na = (a * a).sum(1)[:, None]
     nb = (b * b).sum(1)[None, :]
-    return na + nb - 2 * (a @ b.T)
+    # the dot products through float64 BLAS: entries are integers <= 255, so every product and partial sum (<= 128 * 255^2)
+    # is an integer far below 2^53 and the result is exact whatever the summation order
+    dots = (a.astype(np.float64) @ b.astype(np.float64).T)
+    return na + nb - 2 * np.rint(dots).astype(np.int64)
 
 
 def ratio_pass_from_d2(d0sq, d1sq, ratio=RATIO):
@@ -263,35 +266,81 @@ def color_run(results, data_dir, ext=".png"):
 # --------------------------------------------------------------------------------------------
 # Laplacian variance (analyze.py:441-445)
 # --------------------------------------------------------------------------------------------
-def laplacian_var(img):
-    """cv2.Laplacian(img, CV_64F) with ksize=1 is the 4-neighbour kernel [0 1 0;1 -4 1;0 1 0] with
-    BORDER_REFLECT_101; .var() is the population variance.  Integer formulation with exact sums."""
+def laplacian_int(img):
+    """cv2.Laplacian(img, CV_64F) with ksize=1 is the 4-neighbour kernel [0 1 0;1 -4 1;0 1 0] with BORDER_REFLECT_101:
+    integer valued in [-1020, 1020]."""
     a = np.asarray(img)
     assert a.ndim == 2
     p = np.pad(a.astype(np.int64), 1, mode="reflect")
-    lap = p[:-2, 1:-1] + p[2:, 1:-1] + p[1:-1, :-2] + p[1:-1, 2:] - 4 * p[1:-1, 1:-1]
-    n = lap.size
-    s1 = int(lap.sum())
-    s2 = int((lap * lap).sum())
+    return p[:-2, 1:-1] + p[2:, 1:-1] + p[1:-1, :-2] + p[1:-1, 2:] - 4 * p[1:-1, 1:-1]
+
+
+def pairwise_sum_f64(x):
+    """numpy's pairwise summation of a contiguous float64 vector spelled out (numpy/_core/src/umath/loops_utils.h.src,
+    DOUBLE_pairwise_sum): halve recursively (left part rounded down to a multiple of 8) until <= 128 elements; a piece is
+    summed with 8 interleaved accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), leftovers one by one.
+    Iterative (explicit stack) so that 480 000-element images do not recurse in Python; the accumulators are vectorised."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+
+    def leaf(lo, n):
+        v = x[lo:lo + n]
+        if n < 8:
+            r = np.float64(0.0)
+            for e in v:
+                r = r + e
+            return r
+        m = n - n % 8
+        r = v[:8].copy()
+        for i in range(8, m, 8):
+            r = r + v[i:i + 8]
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+        for e in v[m:]:
+            res = res + e
+        return res
+
+    def rec(lo, n):
+        if n <= 128:
+            return leaf(lo, n)
+        n2 = n // 2
+        n2 -= n2 % 8
+        return rec(lo, n2) + rec(lo + n2, n - n2)   # depth is log2(n / 128): fine for any image
+
+    return rec(0, len(x))
+
+
+def laplacian_var(img):
+    """analyze.py:441-445: cv2.Laplacian(img, cv2.CV_64F).var().  ndarray.var() is numpy's TWO-PASS variance,
+    mean = sum(x) / N then sum((x - mean)^2) / N, both sums pairwise (pairwise_sum_f64).  The Laplacian is integer valued, so
+    the first sum is exact; the second rounds at every addition and must be reproduced addition for addition, because the
+    blur weight blur/200*0.85 (analyze.py:245-248) carries every bit of it into out.txt."""
+    lap = laplacian_int(img)
+    x = lap.astype(np.float64).ravel()
+    n = np.float64(x.size)
+    mean = np.float64(int(lap.sum())) / n
+    d = x - mean
+    return pairwise_sum_f64(d * d) / n
+
+
+def laplacian_var_from_sums(img):
+    """(sum L^2 - (sum L)^2 / N) / N on exact integer sums: within 1 ulp or so of laplacian_var, NOT bit-identical to it."""
+    s1, s2, n = laplacian_sums(img)
     return (s2 - s1 * s1 / n) / n
 
 
 def laplacian_sums(img):
     """(sum L, sum L^2, N) as exact Python ints: what the CUDA kernel must reproduce bit-exactly."""
-    a = np.asarray(img)
-    p = np.pad(a.astype(np.int64), 1, mode="reflect")
-    lap = p[:-2, 1:-1] + p[2:, 1:-1] + p[1:-1, :-2] + p[1:-1, 2:] - 4 * p[1:-1, 1:-1]
+    lap = laplacian_int(img)
     return int(lap.sum()), int((lap * lap).sum()), int(lap.size)
 
 
 # --------------------------------------------------------------------------------------------
 # particle filter update (analyze.py:239-336), generalised from 7x25 to L x I
 # --------------------------------------------------------------------------------------------
-def forward_factor(best_angle_index):
-    return 0.05 * abs(math.sin(best_angle_index * 15 * 180 / math.pi))  # analyze.py:331 (sic)
+def forward_factor(best_angle_index, step=15):
+    return 0.05 * abs(math.sin(best_angle_index * step * 180 / math.pi))  # analyze.py:331 (sic); step = 15 in the reference
 
 
-def account_command(command, previous):
+def account_command(command, previous, step=15):
     """analyze.py:312-336.  ``previous`` is a list of [total, [p...]]; like the reference this
     mutates the inner lists of ``previous`` (shallow copy at :317)."""
     copy = previous[:]
@@ -305,10 +354,10 @@ def account_command(command, previous):
     elif command == "f":
         bc = previous.index(max(previous))
         ba = previous[bc][1].index(max(previous[bc][1]))
-        factor = forward_factor(ba)
-        if bc < n_loc - 1 and ba * 15 < 180 and ba > 0:
+        factor = forward_factor(ba, step)
+        if bc < n_loc - 1 and ba * step < 180 and ba > 0:
             copy[bc + 1][0] *= (1 + factor)
-        elif bc > 0 and ba * 15 > 180 and ba * 15 < 360:
+        elif bc > 0 and ba * step > 180 and ba * step < 360:
             copy[bc - 1][0] *= (1 + factor)
     return copy
 
@@ -337,16 +386,16 @@ def best_guess(adjusted):
     return bc, ba
 
 
-def filter_step(command, previous, current, blur):
+def filter_step(command, previous, current, blur, step=15):
     """One frame of processRaw (analyze.py:119-138).  Returns (adjusted, (bestCircle, bestAngle))."""
-    acc = account_command(command, previous)
+    acc = account_command(command, previous, step)
     adj = prev_weight(acc, current)
     adj = prob_update(acc, adj, blur)
     return adj, best_guess(adj)
 
 
 def initial_probs(n_loc=7, n_img=25):
-    return [[1, [1 / 75] * n_img] for _ in range(n_loc)]  # analyze.py:106-107 (1/75 kept verbatim)
+    return [[1, [1 / (3 * n_img)] * n_img] for _ in range(n_loc)]  # analyze.py:106-107: [1/75]*25, i.e. 1/(3 I)
 
 
 # --------------------------------------------------------------------------------------------

@@ -26,12 +26,12 @@ def extractor(kind):
     return cv2.SIFT_create() if kind == "SIFT" else cv2.ORB_create()
 
 
-def map_descriptors(root, kind, n_locations=7):
+def map_descriptors(root, kind, n_locations=7, n_images=25, step=15):
     """Matcher.createFeatureIndex (Matcher.py:147-163): raw imread, no preprocessing."""
     ex = extractor(kind)
     out = []
     for loc in range(n_locations):
-        out.append([ex.detectAndCompute(cv2.imread(p), None)[1] for p in angle_paths(root, loc)])
+        out.append([ex.detectAndCompute(cv2.imread(p), None)[1] for p in angle_paths(root, loc, n_images, step)])
     return out
 
 
@@ -62,9 +62,10 @@ def read_commands(root):
     return d
 
 
-def create_raw_p(root, kind, w, h, orb_mode="knn", n_locations=7):
-    """analyzer.createRawP (analyze.py:64-96) -> list of [total, [p...]] (frames x locations)."""
-    mdes = map_descriptors(root, kind, n_locations)
+def create_raw_p(root, kind, w, h, orb_mode="knn", n_locations=7, n_images=25, step=15):
+    """analyzer.createRawP (analyze.py:64-96) -> list of [total, [p...]] (frames x locations).  n_locations / n_images / step
+    generalise the reference's 7 / 25 / 15 (analyze.py:35, Matcher.py:309)."""
+    mdes = map_descriptors(root, kind, n_locations, n_images, step)
     p = []
     for fp in frame_paths(root):
         q = query_descriptors(fp, kind, w, h)
@@ -75,33 +76,33 @@ def create_raw_p(root, kind, w, h, orb_mode="knn", n_locations=7):
     return p
 
 
-def process_raw(root, raw_p_file, n_locations=7):
+def process_raw(root, raw_p_file, n_locations=7, n_images=25, step=15):
     """analyzer.processRaw (analyze.py:98-146) -> (blurP, bestGuess).  Keeps the reference's aliasing: accountCommand
     of frame t+1 mutates the inner lists already appended to blurP for frame t."""
     commands = read_commands(root)
     prob = oracle.read_prob(raw_p_file, n_locations)
-    previous = oracle.initial_probs(n_locations)
+    previous = oracle.initial_probs(n_locations, n_images)
     blur_p, best = [], []
     for fp in frame_paths(root):
         stem = os.path.basename(fp).replace(EXT, "")
         blur = oracle.laplacian_var(cv2.imread(fp, 0))
-        adjusted, bg = oracle.filter_step(commands[stem], previous, prob[stem], blur)
+        adjusted, bg = oracle.filter_step(commands[stem], previous, prob[stem], blur, step)
         best.append([bg[0], bg[1]])
         blur_p.extend(adjusted)
         previous = adjusted
     return blur_p, best
 
 
-def opt_p(root, kind, w, h, orb_mode="knn", n_locations=7):
+def opt_p(root, kind, w, h, orb_mode="knn", n_locations=7, n_images=25, step=15):
     """analyzer.optP (analyze.py:148-232): DOR location window +-2 and angle window +-30 degrees."""
     commands = read_commands(root)
-    mdes = map_descriptors(root, kind, n_locations)
-    previous = oracle.initial_probs(n_locations)
+    mdes = map_descriptors(root, kind, n_locations, n_images, step)
+    previous = oracle.initial_probs(n_locations, n_images)
     best_angle = best_circle = None
     blur_p, best = [], []
     for fp in frame_paths(root):
         q = query_descriptors(fp, kind, w, h)
-        window = oracle.opt_window(best_angle)
+        window = oracle.opt_window(best_angle, n_images, step)
         p = []
         for loc in range(n_locations):
             if best_circle is None or (best_circle - 2 <= loc <= best_circle + 2):
@@ -109,10 +110,10 @@ def opt_p(root, kind, w, h, orb_mode="knn", n_locations=7):
                 total, probs = oracle.run_from_counts(counts)
                 p.append([total, probs])
             else:
-                p.append([1, [1 / 75] * 25])
+                p.append([1, [1 / (3 * n_images)] * n_images])
         stem = os.path.basename(fp).replace(EXT, "")
         blur = oracle.laplacian_var(cv2.imread(fp, 0))
-        adjusted, bg = oracle.filter_step(commands[stem], previous, p, blur)
+        adjusted, bg = oracle.filter_step(commands[stem], previous, p, blur, step)
         best_circle, best_angle = bg
         best.append([bg[0], bg[1]])
         blur_p.extend(adjusted)

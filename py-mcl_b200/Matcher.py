@@ -55,23 +55,33 @@ def _make_extractor(alg):
 
 
 class _ResidentCache(object):
-    """id(index dict) -> resident MapIndex.  Holds a reference to the dict so the id stays valid."""
+    """id(index dict) -> resident MapIndex.  Holds a reference to the dict so the id stays valid, and a fingerprint of its
+    content -- the paths in order and the identity + shape of every descriptor array -- so that an index changed in place
+    (index[path] = (kp, other_des), a path added or removed) gets a fresh HBM copy instead of a stale one."""
 
     def __init__(self, capacity=64):
         self.capacity = capacity
         self.entries = {}
         self.order = []
 
+    @staticmethod
+    def _fingerprint(index):
+        return tuple((p, id(v[1]), None if v[1] is None else v[1].shape) for p, v in index.items())
+
     def get(self, ctx, kind, index):
         key = (id(index), kind)
+        fp = self._fingerprint(index)
         ent = self.entries.get(key)
-        if ent is not None and ent[0] is index and ent[3] == len(index):
+        if ent is not None and ent[0] is index and ent[3] == fp:
             return ent[1], ent[2]
+        if ent is not None:          # same dict object, different content: release the stale resident copy
+            ent[1].close()
+            self.order.remove(key)
         paths = list(index.keys())
         descs = [index[p][1] for p in paths]
         resident = _lib.MapIndex(ctx, kind, descs)
         col = dict((p, i) for i, p in enumerate(paths))
-        self.entries[key] = (index, resident, col, len(index))
+        self.entries[key] = (index, resident, col, fp)
         self.order.append(key)
         while len(self.order) > self.capacity:
             old = self.order.pop(0)
@@ -81,8 +91,30 @@ class _ResidentCache(object):
         return resident, col
 
 
+class _BowCache(object):
+    """(index path, mtime, size) -> resident BowIndex, least recently used first out: a 10 000-word index keeps ~9 MB in
+    HBM (code book + planes + tf-idf rows), and the reference's loop visits every location's .pkl for every frame."""
+
+    def __init__(self, capacity=512):
+        from collections import OrderedDict
+        self.capacity = capacity
+        self.entries = OrderedDict()
+
+    def get(self, key):
+        ent = self.entries.get(key)
+        if ent is not None:
+            self.entries.move_to_end(key)
+        return ent
+
+    def put(self, key, ent):
+        self.entries[key] = ent
+        while len(self.entries) > self.capacity:
+            _, old = self.entries.popitem(last=False)
+            old.close()
+
+
 _resident_cache = _ResidentCache()
-_bow_cache = {}
+_bow_cache = _BowCache()
 
 
 class Matcher(object):
@@ -91,11 +123,15 @@ class Matcher(object):
     ### Initialization ###
     ######################
 
-    def __init__(self, algorithm, index=None, width=800, height=600):
+    def __init__(self, algorithm, index=None, width=800, height=600, *, imagesPerLocation=25, angleStep=15):
+        """Reference signature (Matcher.py:41) plus two keyword-only generalisations of its hard-coded map shape
+        (`range(0, 375, 15)`, Matcher.py:309,325,348): images per location and degrees between them."""
         self.w = width
         self.h = height
         self.alg = algorithm
         self.index = index
+        self.imagesPerLocation = int(imagesPerLocation)
+        self.angleStep = int(angleStep)
         self.numWords = 10000
         self.orb_mode = 'knn'
         self.ratio = 0.7
@@ -282,7 +318,7 @@ class Matcher(object):
         resident, col = _resident_cache.get(ctx, kind, self.index)
         des = self._query_descriptors(kind)
         if only_paths is None:
-            key = (id(self.index), kind, self._mode(kind))
+            key = (id(self.index), kind, self._mode(kind), float(self.ratio), id(resident))
             if self._counts is not None and self._counts[0] == key:
                 return self._counts[1], col
             counts = resident.match_counts([des], mode=self._mode(kind), ratio=self.ratio)[0]
@@ -330,7 +366,7 @@ class Matcher(object):
             # the reference sizes the query histogram with self.numWords (Matcher.py:237); it must equal the index width
             W = int(np.asarray(im_features).shape[1])
             ent = _lib.BowIndex(self._context(), [(im_features, idf, voc)], W)
-            _bow_cache[key] = ent
+            _bow_cache.put(key, ent)
         des = self._query_descriptors('SIFT')
         scores, _ = ent.score([des])
         return scores
@@ -342,7 +378,8 @@ class Matcher(object):
         return self._single('SIFT', imagePath)
 
     def _angle_paths(self):
-        return [self.data + '/angle' + str(i).zfill(3) + extension for i in range(0, 375, 15)]
+        return [self.data + '/angle' + str(i).zfill(3) + extension
+                for i in range(0, self.imagesPerLocation * self.angleStep, self.angleStep)]
 
     def _finish(self, numbers):
         totalMatches = sum(numbers)
@@ -367,7 +404,7 @@ class Matcher(object):
             # the reference takes the colour branch for both here (Matcher.py:377-385)
             return self._color_finish(self.colorSearch())
         kind = self.alg if self.alg in ('SIFT', 'SURF') else 'ORB'
-        window = angle_window(bestAngleIndex)
+        window = angle_window(bestAngleIndex, self.imagesPerLocation, self.angleStep)
         paths = self._angle_paths()
         counts, col = self._match_index(kind, only_paths=[p for p, w in zip(paths, window) if w])
         return self._finish([int(counts[col[p]]) if w else 1 for p, w in zip(paths, window)])

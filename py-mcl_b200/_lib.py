@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libmcl.so")
 SIFT, ORB, SURF, BOWQ = 0, 1, 2, 3
 U8, F32 = 0, 1
 KNN2_RATIO, CROSSCHECK = 0, 1
-ALGO_AUTO, ALGO_TENSOR, ALGO_SIMT, ALGO_TENSOR_V1, ALGO_TENSOR_V2, ALGO_TENSOR_V3 = 0, 1, 2, 3, 4, 5
+ALGO_AUTO, ALGO_TENSOR, ALGO_SIMT = 0, 1, 2
 F_COMMAND, F_PREV, F_BLUR, F_BEST, F_ALL = 1, 2, 4, 8, 15
 T_PY, T_F64, T_F32 = 0, 1, 2
 KIND_BY_NAME = {"SIFT": SIFT, "ORB": ORB, "SURF": SURF}
@@ -43,6 +43,7 @@ SIGNATURES = {
     "mcl_last_error": (C.c_char_p, []),
     "mcl_device_info": (C.c_int, [_p, _i64p]),
     "mcl_sync": (C.c_int, [_p]),
+    "mcl_stats": (C.c_int, [_p, _i64p]),
     "mcl_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_p)]),
     "mcl_host_free": (None, [_p]),
     "mcl_launch_count": (C.c_int64, [_p]),
@@ -53,6 +54,8 @@ SIGNATURES = {
     "mcl_map_destroy": (None, [_p]),
     "mcl_map_info": (C.c_int, [_p, _i64p]),
     "mcl_queries_create": (C.c_int, [_p, C.c_int, C.c_int, _i64p, _p, C.c_int, C.POINTER(_p)]),
+    "mcl_queries_create_device": (C.c_int, [_p, C.c_int, C.c_int, _i64p, _p, C.c_int, _p, C.POINTER(_p)]),
+    "mcl_queries_validate": (C.c_int, [_p]),
     "mcl_queries_destroy": (None, [_p]),
     "mcl_match_counts": (C.c_int, [_p, C.c_int, _i64p, _p, C.c_int, C.c_int, C.c_double, _p, C.c_int32, C.c_int, _p]),
     "mcl_match_counts_device": (C.c_int, [_p, _p, C.c_int, C.c_double, _p, C.c_int32, C.c_int, _p, _p]),
@@ -223,6 +226,12 @@ class Context:
     def sync(self):
         _check(self._lib.mcl_sync(self._h), "mcl_sync")
 
+    def stats(self):
+        a = (C.c_int64 * 8)()
+        _check(self._lib.mcl_stats(self._h, a), "mcl_stats")
+        return {"sift_candidates": a[0], "sift_rescans": a[1], "repaired_pairs": a[2], "bow_rescanned_rows": a[3],
+                "orb_candidates": a[4]}
+
     def set_option(self, option, value):
         _check(self._lib.mcl_set_option(self._h, int(option), int(value)), "mcl_set_option")
 
@@ -287,8 +296,9 @@ class Context:
             _check(self._lib.mcl_laplacian_var(self._h, n, ptrs, hs, ws, st, _ptr(out)), "mcl_laplacian_var")
         return out
 
-    def filter_step(self, stages, cmd, blur, prev, cur):
+    def filter_step(self, stages, cmd, blur, prev, cur, angle_step=15):
         """prev, cur: (L, 1+I) float64.  Returns (prev after the command shift, out, (bestCircle, bestAngle))."""
+        self.set_option(6, int(angle_step))
         prev = np.ascontiguousarray(prev, dtype=np.float64).copy()
         cur = np.ascontiguousarray(cur, dtype=np.float64)
         if prev.shape != cur.shape or prev.ndim != 2:
@@ -300,9 +310,10 @@ class Context:
                                          _ptr(prev), _ptr(cur), _ptr(out), _ptr(best)), "mcl_filter_step")
         return prev, out, (int(best[0]), int(best[1]))
 
-    def filter_step_typed(self, stages, cmd, blur, blur_type, prev, prev_type, cur, cur_type):
+    def filter_step_typed(self, stages, cmd, blur, blur_type, prev, prev_type, cur, cur_type, angle_step=15):
         """filter_step on lists that hold numpy scalars (include/mcl.h: mcl_filter_step_typed).  *_type: (L, 2) int8 tags
         [total, probabilities] per row (T_PY / T_F64 / T_F32).  Returns (prev, out, out_type, best)."""
+        self.set_option(6, int(angle_step))
         prev = np.ascontiguousarray(prev, dtype=np.float64).copy()
         cur = np.ascontiguousarray(cur, dtype=np.float64)
         if prev.shape != cur.shape or prev.ndim != 2:
@@ -402,16 +413,28 @@ class MapIndex:
 class QueryBatch:
     """Resident query descriptors of a batch of frames (mcl_queries)."""
 
-    def __init__(self, ctx, kind, descs=None, packed=None):
+    def __init__(self, ctx, kind, descs=None, packed=None, device=None):
+        """descs / packed: host descriptors.  device = (row offsets int64 host array, device pointer of the concatenated
+        rows, dtype code, stream or None): the rows are already in device memory (mcl_queries_create_device; asynchronous)."""
         self.ctx = ctx
         self.kind = (KIND_BY_NAME.get(kind, BOWQ) if isinstance(kind, str) else int(kind))
-        off, cat, code = packed if packed is not None else pack_descriptors(self.kind, descs)
+        h = _p()
+        if device is not None:
+            off, d_ptr, code, stream = device
+            off = np.ascontiguousarray(off, dtype=np.int64)
+            _check(ctx._lib.mcl_queries_create_device(ctx._h, self.kind, len(off) - 1, off.ctypes.data_as(_i64p), _p(d_ptr), code,
+                                                      _p(stream) if stream else None, C.byref(h)), "mcl_queries_create_device")
+        else:
+            off, cat, code = packed if packed is not None else pack_descriptors(self.kind, descs)
+            _check(ctx._lib.mcl_queries_create(ctx._h, self.kind, len(off) - 1, off.ctypes.data_as(_i64p), _ptr(cat), code,
+                                               C.byref(h)), "mcl_queries_create")
         self.n_queries = len(off) - 1
         self.row_offsets = off
-        h = _p()
-        _check(ctx._lib.mcl_queries_create(ctx._h, self.kind, self.n_queries, off.ctypes.data_as(_i64p), _ptr(cat), code,
-                                           C.byref(h)), "mcl_queries_create")
         self._h = h
+
+    def validate(self):
+        """Device-built batches: raises if the ingest saw a float32 SIFT value that is not an integer in [0, 255]."""
+        _check(self.ctx._lib.mcl_queries_validate(self._h), "mcl_queries_validate")
 
     def close(self):
         if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):

@@ -30,8 +30,14 @@ extension = '.png'
 
 class analyzer(object):
 
-    def __init__(self, method, width, height, numLocations=7):
+    def __init__(self, method, width, height, numLocations=7, *, imagesPerLocation=25, angleStep=15, framesPerCall=256):
+        """Reference signature (analyze.py:34) plus keyword-only generalisations of its hard-coded map shape: numLocations
+        (7, analyze.py:35), images per location (25) and degrees between them (15) (`range(0, 375, 15)`, Matcher.py:309;
+        `[1/75]*25`, analyze.py:107).  framesPerCall bounds how many frames createRawP extracts and matches at a time."""
         self.numLocations = numLocations
+        self.I = int(imagesPerLocation)
+        self.angleStep = int(angleStep)
+        self.framesPerCall = max(1, int(framesPerCall))
         self.indices = [None] * self.numLocations
         self.method = method
         self.w = width
@@ -55,7 +61,7 @@ class analyzer(object):
         """
         Create the feature indices (reference analyze.py:45-58).
         """
-        matcher = Matcher(self.method, width=self.w, height=self.h)
+        matcher = self._matcher()
         if self.method != 'BOW':
             for i in range(self.numLocations):
                 matcher.setDirectory('map/' + str(i))
@@ -71,6 +77,13 @@ class analyzer(object):
     ### Main Methods ###
     ####################
 
+    def _matcher(self):
+        return Matcher(self.method, width=self.w, height=self.h, imagesPerLocation=self.I, angleStep=self.angleStep)
+
+    def _prior(self):
+        # the reference's [1, [1/75]*25] (analyze.py:107,166,204): 1/(3 I) per image
+        return [1, [1 / (3 * self.I)] * self.I]
+
     def _kind(self):
         return self.method if self.method in ('SIFT', 'SURF') else 'ORB'
 
@@ -78,7 +91,7 @@ class analyzer(object):
         return _lib.CROSSCHECK if (self._kind() == 'ORB' and self.orb_mode == 'crosscheck') else _lib.KNN2_RATIO
 
     def _angle_paths(self, loc):
-        return ['map/' + str(loc) + '/angle' + str(i).zfill(3) + extension for i in range(0, 375, 15)]
+        return ['map/' + str(loc) + '/angle' + str(i).zfill(3) + extension for i in range(0, self.I * self.angleStep, self.angleStep)]
 
     def _resident_map(self):
         """All locations x 25 angle images as one sharded, HBM-resident map (run()'s image order)."""
@@ -102,7 +115,7 @@ class analyzer(object):
         kind = kind or self._kind()
 
         def one(path):
-            m = Matcher(self.method, width=self.w, height=self.h)
+            m = self._matcher()
             m.setQuery(path)
             return m._query_descriptors(kind)
 
@@ -152,14 +165,15 @@ class analyzer(object):
 
         start = time.time()
         p = []
-        matcher = Matcher(self.method, width=self.w, height=self.h)
+        matcher = self._matcher()
         print('Matching...')
         frames = glob.glob('cam1_img' + '/*' + extension)
+        I = self.I
 
         if self.method == 'Color':
             # every frame's histogram against every location's colour index: one chi-squared call
             def hist(path):
-                m = Matcher(self.method, width=self.w, height=self.h)
+                m = self._matcher()
                 m.setQuery(path)
                 return m.createHistogram(m.image)
 
@@ -170,11 +184,17 @@ class analyzer(object):
                 p.extend(results)
                 print('\t' + imagePath)
         elif self.method != 'BOW':
-            qdes = self._extract_many(frames)
-            counts = self._resident_map().match_counts(qdes, mode=self._mode())
+            # frames in bounded chunks (the reference streams frame by frame; one call per chunk keeps the batching win
+            # while host memory, the pinned staging copy and the device buffers stop growing with the run length)
+            resident = self._resident_map()
+            chunks = []
+            for c0 in range(0, len(frames), self.framesPerCall):
+                qdes = self._extract_many(frames[c0:c0 + self.framesPerCall])
+                chunks.append(resident.match_counts(qdes, mode=self._mode()))
+            counts = np.concatenate(chunks, axis=0) if chunks else np.zeros((0, self.numLocations * I), np.int32)
             for f, imagePath in enumerate(frames):
                 for i in range(self.numLocations):
-                    p.append(self._run_result(counts[f, i * 25:(i + 1) * 25]))
+                    p.append(self._run_result(counts[f, i * I:(i + 1) * I]))
                 print('\t' + imagePath)
         else:
             import joblib
@@ -185,8 +205,10 @@ class analyzer(object):
 
             # locations (code book + index) are the unit of sharding; the float32 scores are all-gathered
             bow = ShardedBow(self.numLocations, load, ctx=self._context())
-            qdes = self._extract_many(frames, 'SIFT')
-            scores = bow.score(qdes)
+            parts = []
+            for c0 in range(0, len(frames), self.framesPerCall):
+                parts.append(bow.score(self._extract_many(frames[c0:c0 + self.framesPerCall], 'SIFT')))
+            scores = np.concatenate(parts, axis=0) if parts else np.zeros((0, bow.total_images), np.float32)
             for f, imagePath in enumerate(frames):
                 for i in range(self.numLocations):
                     s = scores[f:f + 1, bow.img_off[i]:bow.img_off[i + 1]]
@@ -212,7 +234,7 @@ class analyzer(object):
             results, col = [], 0
             for i in range(self.numLocations):
                 if i not in names:
-                    results.append([1, [1/75] * 25])
+                    results.append(self._prior())
                     continue
                 matcher.setDirectory('map/' + str(i))
                 d = chi[f, col:col + len(names[i])]
@@ -247,7 +269,7 @@ class analyzer(object):
         """
         previousProbs = []
         for i in range(self.numLocations):
-            previousProbs.append([1, [1/75] * 25])
+            previousProbs.append(self._prior())
 
         start = time.time()
         probDict = self.readSidecar('rawP.txt') if self.sidecar else None
@@ -291,14 +313,15 @@ class analyzer(object):
         bestCircleIndex = None
 
         for i in range(self.numLocations):
-            previousProbs.append([1, [1/75] * 25])
+            previousProbs.append(self._prior())
 
-        matcher = Matcher(self.method, width=self.w, height=self.h)
+        matcher = self._matcher()
         start = time.time()
         print('Matching...')
         color = self.method == 'Color'
         resident = None if color else self._resident_map()
-        n_img = self.numLocations * 25
+        I = self.I
+        n_img = self.numLocations * I
 
         # Which images a frame is matched against depends on the previous frame's best guess, but its descriptors
         # (histogram) and its blur weight do not: extract / decode every frame up front on the thread pool (cv2 extraction
@@ -306,7 +329,7 @@ class analyzer(object):
         frames = glob.glob('cam1_img' + '/*' + extension)
         if color:
             def hist(path):
-                m = Matcher(self.method, width=self.w, height=self.h)
+                m = self._matcher()
                 m.setQuery(path)
                 return m.createHistogram(m.image)
 
@@ -327,17 +350,17 @@ class analyzer(object):
                 p = self._color_locations(matcher, [feature], locs)[0]
             else:
                 des = feature
-                window = angle_window(bestAngleIndex) if bestAngleIndex is not None else [True] * 25
+                window = angle_window(bestAngleIndex, I, self.angleStep) if bestAngleIndex is not None else [True] * I
                 mask = np.zeros((1, n_img), dtype=np.uint8)
                 for i in locs:
-                    mask[0, i * 25:(i + 1) * 25] = window
+                    mask[0, i * I:(i + 1) * I] = window
                 counts = resident.match_counts([des], mode=self._mode(), mask=mask, fill_value=1)[0]
                 p = []
                 for i in range(self.numLocations):
                     if i in locs:
-                        p.append(self._run_result(counts[i * 25:(i + 1) * 25]))
+                        p.append(self._run_result(counts[i * I:(i + 1) * I]))
                     else:
-                        p.append([1, [1/75] * 25])
+                        p.append(self._prior())
             print('\t' + imagePath)
 
             command = self.commands[imagePath.replace('cam1_img/', '').replace(extension, '')]
@@ -395,10 +418,10 @@ class analyzer(object):
         prev, pt = self._pack(previousP)
         cur, ct = self._pack(currentP)
         if not (pt == _lib.T_F32).any() and not (ct == _lib.T_F32).any():
-            prev2, out, best = self._context().filter_step(stages, command, float(blurFactor), prev, cur)
+            prev2, out, best = self._context().filter_step(stages, command, float(blurFactor), prev, cur, angle_step=self.angleStep)
             return self._unpack(prev2, pt), [[float(r[0]), r[1:].tolist()] for r in out], best
         prev2, out, ot, best = self._context().filter_step_typed(stages, command, float(blurFactor), self._tag(blurFactor),
-                                                                  prev, pt, cur, ct)
+                                                                  prev, pt, cur, ct, angle_step=self.angleStep)
         return self._unpack(prev2, pt), self._unpack(out, ot), best
 
     def probUpdate(self, previousP, currentP, blurFactor):
@@ -452,10 +475,11 @@ class analyzer(object):
         L = self.numLocations
         with np.printoptions(legacy='1.25'):
             total = np.array([float(str(c[0])) for c in prob], dtype=np.float64).reshape(-1, L)
-            probs = np.array([[float(str(x)) for x in c[1]] for c in prob], dtype=np.float64)
-        probs = probs.reshape(total.shape[0], L, -1)
+            flat = np.array([float(str(x)) for c in prob for x in c[1]], dtype=np.float64)
+        # per (frame, location) list lengths: equal for the feature methods, ragged for BOW (locations own different image counts)
+        lengths = np.array([len(c[1]) for c in prob], dtype=np.int64).reshape(-1, L)
         extra = {} if counts is None else {'counts': np.asarray(counts, dtype=np.int32)}
-        np.savez(filename[:filename.rfind('.')] + '.npz', total=total, probs=probs,
+        np.savez(filename[:filename.rfind('.')] + '.npz', total=total, probs=flat, lengths=lengths,
                  text_sha256=np.array(self._text_digest(filename)), **extra)
 
     def readSidecar(self, filename):
@@ -467,10 +491,16 @@ class analyzer(object):
         with np.load(path) as z:
             if str(z['text_sha256']) != self._text_digest(filename) or z['total'].shape[1] != self.numLocations:
                 return None
-            total, probs = z['total'], z['probs']
+            total, flat, lengths = z['total'], z['probs'], z['lengths']
         probD = {}
+        pos = 0
         for f in range(total.shape[0]):
-            probD[str(f).zfill(4)] = [[float(total[f, l]), probs[f, l].tolist()] for l in range(total.shape[1])]
+            row = []
+            for l in range(total.shape[1]):
+                n = int(lengths[f, l])
+                row.append([float(total[f, l]), flat[pos:pos + n].tolist()])
+                pos += n
+            probD[str(f).zfill(4)] = row
         return probD
 
     def readCommand(self, filename):

@@ -398,7 +398,7 @@ __device__ __forceinline__ TV t_add(TV a, TV b) {
     return r;
 }
 
-__global__ void filter_step_kernel(int L, int I, int stages, int cmd, double blur, int blur_t, double* __restrict__ prev,
+__global__ void filter_step_kernel(int L, int I, int step_deg, int stages, int cmd, double blur, int blur_t, double* __restrict__ prev,
                                    const signed char* __restrict__ prev_t, const double* __restrict__ cur,
                                    const signed char* __restrict__ cur_t, const double* __restrict__ fwd_factor,
                                    double* __restrict__ out, signed char* __restrict__ out_t, int* __restrict__ best /* 2 */,
@@ -426,8 +426,8 @@ __global__ void filter_step_kernel(int L, int I, int stages, int cmd, double blu
                 const int ba = first_argmax(prev + (size_t)bc * S + 1, I);
                 const TV onep = {__dadd_rn(1.0, fwd_factor[ba]), T_PY};
                 int row = -1;
-                if (bc < L - 1 && ba * 15 < 180 && ba > 0) row = bc + 1;
-                else if (bc > 0 && ba * 15 > 180 && ba * 15 < 360) row = bc - 1;
+                if (bc < L - 1 && ba * step_deg < 180 && ba > 0) row = bc + 1;              // analyze.py:332-335 (15 = the angle step)
+                else if (bc > 0 && ba * step_deg > 180 && ba * step_deg < 360) row = bc - 1;
                 if (row >= 0) {
                     const TV tot = {prev[(size_t)row * S], prev_t ? prev_t[2 * row] : T_PY};
                     prev[(size_t)row * S] = t_mul(tot, onep).v;   // `*=` with a Python float keeps the row's type

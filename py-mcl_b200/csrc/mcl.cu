@@ -10,18 +10,18 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "common.cuh"
 #include "prep.cuh"
-#include "sift_tc.cuh"
-#include "sift_tc2.cuh"
 #include "sift_tc3.cuh"
 #include "sift_tc4.cuh"
 #include "simt_match.cuh"
 #include "bow_lap_filter.cuh"
+#include "lap_var.cuh"
 #include "bow_tc.cuh"
 #include "kmeans.cuh"
 #include "color.cuh"
@@ -49,7 +49,7 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 enum { PROF_SIFT_TC = 0, PROF_SIFT_FIX, PROF_ORB, PROF_SURF, PROF_VQ, PROF_SCORE, PROF_LAP, PROF_PREP, PROF_SIFT_SIMT, PROF_VQ_TC, PROF_VQ_RESOLVE, PROF_CHI2, PROF_N };
-constexpr int QROW_PAD = 768;  // lcm of the two tensor-core kernels' query blocks (256, 384)
+constexpr int QROW_PAD = 384;  // sift_tc4's query block
 
 // growable device scratch buffer (never shrinks; avoids cudaMalloc on the per-frame path)
 struct DevBuf {
@@ -77,6 +77,12 @@ struct DevBuf {
 
 }  // namespace
 
+// numpy's pairwise summation of N elements as tables (lap_var.cuh): the leaves and, level by level, the internal nodes
+struct LapPlan {
+    int n_leaves = 0, n_nodes = 0, n_levels = 0;
+    int* d_tab = nullptr;   // leaf_lo[n_leaves] | leaf_n[n_leaves] | node_l[n_nodes] | node_r[n_nodes] | level_off[n_levels + 1]
+};
+
 struct mcl_ctx {
     int device = 0;
     int sm_count = 0;
@@ -88,14 +94,22 @@ struct mcl_ctx {
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[PROF_N];
     // scratch
-    DevBuf stage, cand, flags /* [0]=cand_count [1]=overflow [2]=bad [3]=rescans [4]=norm min [5]=norm max */, row_arg, bow_best, lap_pix, lap_meta, filt, tmp_counts,
+    DevBuf stage, cand, dirty, flags /* ints: [0]=cand_count [1]=overflow [2]=bad [3]=rescans [6]=bow bad [8..10]=bow state; bytes 64..: statistics */, row_arg, bow_best, lap_pix, lap_meta, filt, tmp_counts,
         tmp_mask, tmp_words, tmp_scores, chi2, tq_off, tq_desc, tq_norm, tq_frame, bow_q8, bow_qaux, bow_tc_out;
     bool bowtc_attr = false;
     size_t cand_cap_entries = 0;
-    bool tc_attr_set = false, tc2_attr_set = false;
-    int opt[8] = {0};  // mcl_set_option: [0] = sift_tc diagnostic mode
-    int max_clusters[2] = {0, 0};   // co-resident sift_tc4 clusters of 2 / of 4 CTAs
+    bool tc4_attr = false;
+    int opt[8] = {0};  // mcl_set_option: [0] = sift_tc4 diagnostic mode
+    int max_clusters2 = 0;          // co-resident sift_tc4 clusters of 2 CTAs
     int bow_max_clusters = 0;       // co-resident bow_vq_tc clusters of 2 CTAs
+    int bow_score_smem = 0;         // dynamic shared memory opt-in of bow_score_kernel so far
+    std::map<int64_t, LapPlan> lap_plans;   // by pixel count
+    // free list of device blocks for the query batches of mcl_queries_create_device: the per-step batches of the multi-GPU
+    // driver come and go with the same few sizes, and cudaMalloc / cudaFree (which synchronises the device) cost more than
+    // the ingest itself
+    std::vector<std::pair<void*, size_t>> pool;
+    size_t pool_bytes = 0;
+    DevBuf lap_vals, lap_list;
 };
 
 struct mcl_queries {
@@ -108,6 +122,10 @@ struct mcl_queries {
     void* d_desc = nullptr;        // SIFT: SW128 atoms; ORB: (rows,32) u8; SURF: (rows,64) f32; BOWQ: (rows,128) f32
     int32_t* d_norm = nullptr;     // SIFT
     int32_t* d_frame = nullptr;    // SIFT: frame of each resident row
+    int* d_bad = nullptr;          // device-built batches: set by the ingest kernel when a float row is not integer valued (mcl_queries_validate)
+    cudaStream_t built_on = nullptr;
+    bool pooled = false;           // device blocks come from / go back to the context's free list
+    size_t sz_off = 0, sz_desc = 0, sz_norm = 0, sz_frame = 0;
     bool borrowed = false;         // buffers belong to ctx scratch (temporary batch of mcl_match_counts)
 };
 
@@ -123,18 +141,12 @@ struct mcl_map {
     void* d_desc = nullptr;
     int32_t* d_norm = nullptr;
     int32_t* d_img_of = nullptr;
-    mcl::sifttc::TileMeta* d_meta = nullptr;
-    int n_tiles = 0;
-    // chunk tables for a few granularities (tiles per chunk), picked per call from the query batch size
-    struct ChunkSet { int target = 0; int n = 0; mcl::sifttc::Chunk* d = nullptr; };
-    std::vector<ChunkSet> chunk_sets;    // sift_tc  (128-row tiles)
-    std::vector<ChunkSet> chunk_sets2;   // sift_tc2 (64-row tiles)
-    uint8_t* d_ext2 = nullptr;           // sift_tc2: per 64-row tile, extension bytes + metadata
-    int n_tiles2 = 0;
-    int key_c = 0;                       // sift_tc2: true key = 2*acc - key_c (+ parity)
-    bool ext_ok = false;                 // the norms' range fits the extension encoding
-    mcl::sifttc3::TileMeta* d_meta3 = nullptr;   // sift_tc3: per 64-row tile
-    bool tc3_attr = false, tc4_attr = false;
+    int n_tiles = 0;                     // 128-row tiles
+    // chunk tables for a few granularities (128-row tiles per chunk), picked per call from the query batch size
+    struct ChunkSet { int target = 0; int n = 0; mcl::sifttc3::Chunk* d = nullptr; };
+    std::vector<ChunkSet> chunk_sets;
+    mcl::sifttc3::TileMeta* d_meta3 = nullptr;   // per 64-row unit: image ids, descriptor counts, norm brackets
+    int n_units = 0;                             // 64-row units
     int max_rows_per_image = 0;
 };
 
@@ -157,6 +169,27 @@ struct mcl_bow {
 };
 
 namespace {
+
+cudaError_t pool_alloc(mcl_ctx* c, void** out, size_t bytes) {
+    bytes = (std::max<size_t>(bytes, 256) + 255) & ~(size_t)255;
+    int best = -1;
+    for (int i = 0; i < (int)c->pool.size(); ++i)
+        if (c->pool[i].second >= bytes && c->pool[i].second <= 2 * bytes + (1 << 20) && (best < 0 || c->pool[i].second < c->pool[best].second)) best = i;
+    if (best >= 0) {
+        *out = c->pool[best].first;
+        c->pool_bytes -= c->pool[best].second;
+        c->pool.erase(c->pool.begin() + best);
+        return cudaSuccess;
+    }
+    return cudaMalloc(out, bytes);
+}
+void pool_free(mcl_ctx* c, void* p, size_t bytes) {
+    if (!p) return;
+    bytes = (std::max<size_t>(bytes, 256) + 255) & ~(size_t)255;
+    if (c->pool.size() >= 64 || c->pool_bytes + bytes > ((size_t)4 << 30)) { cudaFree(p); return; }
+    c->pool.push_back({p, bytes});
+    c->pool_bytes += bytes;
+}
 
 struct ProfScope {
     mcl_ctx* c;
@@ -207,17 +240,20 @@ int ingest_rows128(mcl_ctx* c, cudaStream_t st, const void* h_src, int dtype, in
                    const int64_t* d_src_off, const int64_t* d_dst_off, int64_t padded_rows, uint8_t* d_desc,
                    int32_t* d_norm, int32_t* d_seg, uint8_t* d_stage = nullptr /* null: the context's staging buffer */,
                    bool check_now = true, const int32_t* d_perm = nullptr, cudaStream_t copy_st = nullptr,
-                   cudaEvent_t copied = nullptr) {
+                   cudaEvent_t copied = nullptr, bool src_on_device = false, int* d_bad = nullptr) {
     CU(cudaMemsetAsync(d_desc, 0, (size_t)padded_rows * 128, st));
     CU(cudaMemsetAsync(d_norm, 0xFF, (size_t)padded_rows * 4, st));
     CU(cudaMemsetAsync(d_seg, 0xFF, (size_t)padded_rows * 4, st));
     if (n_rows == 0) return MCL_OK;
     const size_t bytes = (size_t)n_rows * (dtype == MCL_F32 ? 512 : 128);
-    if (!d_stage) {
+    if (src_on_device) {
+        d_stage = (uint8_t*)const_cast<void*>(h_src);   // rows are device memory already: ingest straight from them
+    } else if (!d_stage) {
         CU(c->stage.ensure(bytes));
         d_stage = c->stage.as<uint8_t>();
     }
-    if (copy_st) {
+    if (src_on_device) {
+    } else if (copy_st) {
         // the H2D copy goes on a stream that carries nothing but copies: a memset or conversion kernel queued in front of
         // it would wait for SMs behind the persistent matching kernel and hold the copy back with it
         CU(cudaMemcpyAsync(d_stage, h_src, bytes, cudaMemcpyHostToDevice, copy_st));
@@ -226,7 +262,7 @@ int ingest_rows128(mcl_ctx* c, cudaStream_t st, const void* h_src, int dtype, in
     } else {
         CU(cudaMemcpyAsync(d_stage, h_src, bytes, cudaMemcpyHostToDevice, st));
     }
-    int* bad = c->flags.as<int>() + 2;
+    int* bad = d_bad ? d_bad : c->flags.as<int>() + 2;
     if (check_now) CU(cudaMemsetAsync(bad, 0, 4, st));
     {
         ProfScope ps(c, PROF_PREP, st);
@@ -246,14 +282,14 @@ int ingest_rows128(mcl_ctx* c, cudaStream_t st, const void* h_src, int dtype, in
     return MCL_OK;
 }
 
-void build_chunks(const mcl_map* m, int TILE_N, int target_tiles, std::vector<mcl::sifttc::Chunk>& out) {
+void build_chunks(const mcl_map* m, int TILE_N, int target_tiles, std::vector<mcl::sifttc3::Chunk>& out) {
     out.clear();
     int i = 0;
     const int n = m->n_images;
     while (i < n) {
         // skip empty images (they never get a group; their count stays 0)
         if (m->h_dst_off[i + 1] == m->h_dst_off[i]) { ++i; continue; }
-        mcl::sifttc::Chunk ch;
+        mcl::sifttc3::Chunk ch;
         ch.img_begin = i;
         ch.tile_begin = (int)(m->h_dst_off[i] / TILE_N);
         int j = i;
@@ -270,18 +306,9 @@ void build_chunks(const mcl_map* m, int TILE_N, int target_tiles, std::vector<mc
     }
 }
 
-const mcl_map::ChunkSet* pick_chunks(const std::vector<mcl_map::ChunkSet>& sets, int n_qblocks, int sm_count, int64_t total_tiles = 0) {
-    if (total_tiles <= 0) {
-        // want >= ~3 waves of work items (qblocks x chunks), chunks as long as possible beyond that
-        const mcl_map::ChunkSet* best = &sets.back();
-        for (const auto& cs : sets) {  // sorted by decreasing target
-            best = &cs;
-            if ((int64_t)cs.n * n_qblocks >= (int64_t)3 * sm_count) break;
-        }
-        return best;
-    }
-    // sift_tc4: every work item pays a pipeline refill (the query tiles in tensor memory are single buffered: ~2.5 tile
-    // times), and the last round of items is only partly filled: take the set with the smallest estimated makespan
+const mcl_map::ChunkSet* pick_chunks(const std::vector<mcl_map::ChunkSet>& sets, int n_qblocks, int sm_count, int64_t total_tiles) {
+    // every work item pays a pipeline refill (the query tiles in tensor memory are single buffered: ~2.5 tile times), and
+    // the last round of items is only partly filled: take the set with the smallest estimated makespan
     const mcl_map::ChunkSet* best = &sets.front();
     double best_cost = 1e300;
     for (const auto& cs : sets) {
@@ -323,9 +350,9 @@ extern "C" int mcl_init(int device_id, mcl_ctx** out) {
     c->sm_count = c->prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return fail(MCL_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
-    e = c->flags.ensure(64);
+    e = c->flags.ensure(256);
     if (e != cudaSuccess) { delete c; return fail(MCL_ECUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
-    cudaMemset(c->flags.p, 0, 64);
+    cudaMemset(c->flags.p, 0, 256);
     *out = c;
     return MCL_OK;
 }
@@ -336,10 +363,15 @@ extern "C" void mcl_shutdown(mcl_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& v : c->prof)
         for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-    DevBuf* bufs[] = {&c->stage, &c->cand, &c->flags, &c->row_arg, &c->bow_best, &c->lap_pix, &c->lap_meta, &c->filt,
+    DevBuf* bufs[] = {&c->stage, &c->cand, &c->dirty, &c->flags, &c->row_arg, &c->bow_best, &c->lap_pix, &c->lap_meta, &c->filt,
                       &c->tmp_counts, &c->tmp_mask, &c->tmp_words, &c->tmp_scores, &c->tq_off, &c->tq_desc, &c->tq_norm,
                       &c->tq_frame, &c->bow_q8, &c->bow_qaux, &c->bow_tc_out};
     for (DevBuf* b : bufs) b->release();
+    for (auto& kv : c->lap_plans) cudaFree(kv.second.d_tab);
+    for (auto& b : c->pool) cudaFree(b.first);
+    c->pool.clear();
+    c->lap_vals.release();
+    c->lap_list.release();
     for (cudaEvent_t e : c->part_events) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
@@ -363,6 +395,24 @@ extern "C" int mcl_device_info(mcl_ctx* c, int64_t info[8]) {
         cudaMemcpy(&r, c->flags.as<unsigned int>() + 3, 4, cudaMemcpyDeviceToHost);
         info[7] = r;
     }
+    return MCL_OK;
+}
+
+extern "C" int mcl_stats(mcl_ctx* c, int64_t out[8]) {
+    if (!c || !out) return fail(MCL_EINVAL, "mcl_stats: NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    unsigned int f[16];
+    unsigned long long st[4];
+    CU(cudaMemcpy(f, c->flags.p, sizeof f, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(st, c->flags.as<unsigned long long>() + 8, sizeof st, cudaMemcpyDeviceToHost));
+    out[0] = (int64_t)st[0];   // SIFT candidates resolved by the exact fix-up
+    out[1] = f[3];             // SIFT whole-image exact rescans
+    out[2] = (int64_t)st[1];   // SIFT (frame, image) pairs recomputed by the SIMT kernel after a full candidate list
+    out[3] = f[10];            // BOW rows rescanned over the whole code book (last call)
+    out[4] = (int64_t)st[2];   // ORB candidates resolved exactly
+    out[5] = (int64_t)st[3];
+    out[6] = out[7] = 0;
     return MCL_OK;
 }
 
@@ -426,10 +476,7 @@ extern "C" void mcl_map_destroy(mcl_map* m) {
     cudaFree(m->d_desc);
     cudaFree(m->d_norm);
     cudaFree(m->d_img_of);
-    cudaFree(m->d_meta);
     for (auto& cs : m->chunk_sets) cudaFree(cs.d);
-    for (auto& cs : m->chunk_sets2) cudaFree(cs.d);
-    cudaFree(m->d_ext2);
     cudaFree(m->d_meta3);
     delete m;
 }
@@ -470,7 +517,8 @@ extern "C" int mcl_map_create(mcl_ctx* c, int kind, int n_images, const int64_t*
     MCU(cudaMalloc(&m->d_src_off, (size_t)(n_images + 1) * 8));
     MCU(cudaMemcpyAsync(m->d_src_off, m->h_src_off.data(), (size_t)(n_images + 1) * 8, cudaMemcpyHostToDevice, st));
     if (kind == MCL_SIFT) {
-        using namespace mcl::sifttc;
+        using namespace mcl::sifttc3;
+        constexpr int TILE_ROWS = mcl::sifttc4::TILE_N;   // 128-row tiles
         m->h_dst_off.resize(n_images + 1);
         int64_t acc = 0;
         for (int i = 0; i < n_images; ++i) {
@@ -479,15 +527,15 @@ extern "C" int mcl_map_create(mcl_ctx* c, int kind, int n_images, const int64_t*
             acc += (r + GROUP - 1) / GROUP * GROUP;
         }
         m->h_dst_off[n_images] = acc;
-        m->padded_rows = std::max<int64_t>(TILE_N, (acc + TILE_N - 1) / TILE_N * TILE_N);
-        m->n_tiles = (int)(m->padded_rows / TILE_N);
+        m->padded_rows = std::max<int64_t>(TILE_ROWS, (acc + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS);
+        m->n_tiles = (int)(m->padded_rows / TILE_ROWS);
+        m->n_units = (int)(m->padded_rows / TILE_N);
         MCU(cudaMalloc(&m->d_dst_off, (size_t)(n_images + 1) * 8));
         MCU(cudaMemcpyAsync(m->d_dst_off, m->h_dst_off.data(), (size_t)(n_images + 1) * 8, cudaMemcpyHostToDevice, st));
         MCU(cudaMalloc(&m->d_desc, (size_t)m->padded_rows * 128));
         MCU(cudaMalloc(&m->d_norm, (size_t)m->padded_rows * 4));
         MCU(cudaMalloc(&m->d_img_of, (size_t)m->padded_rows * 4));
-        MCU(cudaMalloc(&m->d_meta, (size_t)m->n_tiles * sizeof(TileMeta)));
-        // rows of every image are stored sorted by |m|^2 (sift_tc3: a 32-row group then has one norm, up to a few units)
+        // rows of every image are stored sorted by |m|^2 (a 32-row group then has one norm, up to a few units)
         int32_t* d_perm = nullptr;
         if (rows > 0) {
             std::vector<int64_t> nrm((size_t)rows);
@@ -519,67 +567,32 @@ extern "C" int mcl_map_create(mcl_ctx* c, int kind, int n_images, const int64_t*
         cudaStreamSynchronize(st);
         cudaFree(d_perm);
         if (rc) { mcl_map_destroy(m); return rc; }
-        {
-            ProfScope ps(c, PROF_PREP, st);
-            build_meta_kernel<<<m->n_tiles, TILE_N, 0, st>>>(m->d_norm, m->d_img_of, m->d_src_off, m->n_tiles, m->d_meta);
-        }
-        MCU(cudaGetLastError());
         std::vector<Chunk> ch;
-        auto make_sets = [&](std::vector<mcl_map::ChunkSet>& sets, int tile_rows, std::initializer_list<int> targets) -> cudaError_t {
-            int last_n = -1;
-            for (int target : targets) {
-                build_chunks(m, tile_rows, target, ch);
-                if ((int)ch.size() == last_n) continue;
-                last_n = (int)ch.size();
-                mcl_map::ChunkSet cs;
-                cs.target = target;
-                cs.n = (int)ch.size();
-                if (cs.n) {
-                    cudaError_t e = cudaMalloc(&cs.d, ch.size() * sizeof(Chunk));
-                    if (e != cudaSuccess) return e;
-                    e = cudaMemcpy(cs.d, ch.data(), ch.size() * sizeof(Chunk), cudaMemcpyHostToDevice);
-                    if (e != cudaSuccess) return e;
-                }
-                sets.push_back(cs);
-            }
-            return cudaSuccess;
-        };
+        int last_n = -1;
         // long chunks amortise sift_tc4's per-item pipeline refill; (448 + one image) x 2 records stay within its staged metadata
-        MCU(make_sets(m->chunk_sets, TILE_N, {448, 144, 64, 32, 16, 8, 4, 2, 1}));
-        MCU(make_sets(m->chunk_sets2, mcl::sifttc2::TILE_N, {256, 128, 64, 32, 16, 8, 4, 2, 1}));
-        // ---- second-generation kernel: norm range -> C, extension bytes + metadata per 64-row tile
-        {
-            int* mm = c->flags.as<int>() + 4;
-            const int init[2] = {INT_MAX, -1};
-            MCU(cudaMemcpyAsync(mm, init, 8, cudaMemcpyHostToDevice, st));
-            c->launches++;
-            mcl::sifttc2::norm_minmax_kernel<<<c->sm_count * 4, 256, 0, st>>>(m->d_norm, m->padded_rows, mm);
-            int h_mm[2];
-            MCU(cudaMemcpyAsync(h_mm, mm, 8, cudaMemcpyDeviceToHost, st));
-            MCU(cudaStreamSynchronize(st));
-            m->n_tiles2 = (int)(m->padded_rows / mcl::sifttc2::TILE_N);
-            if (h_mm[1] >= 0) {
-                m->key_c = h_mm[1] + 3;
-                m->ext_ok = (m->key_c - h_mm[0]) / 2 <= mcl::sifttc2::EXT_CAP;
+        for (int target : {448, 144, 64, 32, 16, 8, 4, 2, 1}) {
+            build_chunks(m, TILE_ROWS, target, ch);
+            if ((int)ch.size() == last_n) continue;
+            last_n = (int)ch.size();
+            mcl_map::ChunkSet cs;
+            cs.target = target;
+            cs.n = (int)ch.size();
+            if (cs.n) {
+                MCU(cudaMalloc(&cs.d, ch.size() * sizeof(Chunk)));
+                m->chunk_sets.push_back(cs);   // owned by the map from here on (freed by mcl_map_destroy on a later failure)
+                MCU(cudaMemcpy(cs.d, ch.data(), ch.size() * sizeof(Chunk), cudaMemcpyHostToDevice));
+            } else {
+                m->chunk_sets.push_back(cs);
             }
-            if (m->ext_ok) {
-                MCU(cudaMalloc(&m->d_ext2, (size_t)m->n_tiles2 * mcl::sifttc2::EXT_META_BYTES));
-                ProfScope ps(c, PROF_PREP, st);
-                mcl::sifttc2::build_ext_kernel<<<m->n_tiles2, mcl::sifttc2::TILE_N, 0, st>>>(
-                    m->d_norm, m->d_img_of, m->d_src_off, m->n_tiles2, m->key_c, m->d_ext2);
-            }
-            MCU(cudaGetLastError());
         }
-        // ---- third-generation kernel: per 64-row tile metadata with the groups' norm brackets
-        MCU(cudaMalloc(&m->d_meta3, (size_t)m->n_tiles2 * sizeof(mcl::sifttc3::TileMeta)));
+        // per 64-row unit: image ids, descriptor counts and the groups' norm brackets
+        MCU(cudaMalloc(&m->d_meta3, (size_t)m->n_units * sizeof(TileMeta)));
         {
             ProfScope ps(c, PROF_PREP, st);
-            mcl::sifttc3::build_meta_kernel<<<(m->n_tiles2 + 127) / 128, 128, 0, st>>>(m->d_norm, m->d_img_of, m->d_src_off,
-                                                                                   m->n_tiles2, m->d_meta3);
+            build_meta_kernel<<<(m->n_units + 127) / 128, 128, 0, st>>>(m->d_norm, m->d_img_of, m->d_src_off, m->n_units, m->d_meta3);
         }
         MCU(cudaGetLastError());
-        m->resident_bytes = (size_t)m->padded_rows * (128 + 8) + (size_t)m->n_tiles * sizeof(TileMeta) +
-                            (m->d_ext2 ? (size_t)m->n_tiles2 * mcl::sifttc2::EXT_META_BYTES : 0);
+        m->resident_bytes = (size_t)m->padded_rows * (128 + 8) + (size_t)m->n_units * sizeof(TileMeta);
     } else {
         const size_t rb = row_bytes(kind, desc_dtype);
         m->padded_rows = rows;
@@ -607,13 +620,23 @@ extern "C" int mcl_map_info(mcl_map* m, int64_t info[4]) {
 // ================================================================================================
 extern "C" void mcl_queries_destroy(mcl_queries* q) {
     if (!q) return;
-    if (!q->borrowed) {
+    if (q->pooled) {
+        cudaSetDevice(q->ctx->device);
+        cudaStreamSynchronize(q->built_on);
+        cudaStreamSynchronize(q->ctx->stream);
+        pool_free(q->ctx, q->d_off, q->sz_off);
+        pool_free(q->ctx, q->d_desc, q->sz_desc);
+        pool_free(q->ctx, q->d_norm, q->sz_norm);
+        pool_free(q->ctx, q->d_frame, q->sz_frame);
+        pool_free(q->ctx, q->d_bad, 256);
+    } else if (!q->borrowed) {
         cudaSetDevice(q->ctx->device);
         cudaStreamSynchronize(q->ctx->stream);
         cudaFree(q->d_off);
         cudaFree(q->d_desc);
         cudaFree(q->d_norm);
         cudaFree(q->d_frame);
+        cudaFree(q->d_bad);
     }
     delete q;
 }
@@ -622,7 +645,7 @@ namespace {
 // borrowed = true: device buffers come from the context's growable scratch (the per-call batch of mcl_match_counts /
 // mcl_bow_score: no cudaMalloc / cudaFree on the per-frame path); false: owned allocations (resident batch).
 int queries_build(mcl_ctx* c, int kind, int n_queries, const int64_t* q_row_offsets, const void* q_desc, int q_dtype,
-                  bool borrowed, mcl_queries** out) {
+                  bool borrowed, mcl_queries** out, bool src_on_device = false, cudaStream_t on_stream = nullptr) {
     *out = nullptr;
     if (kind < MCL_SIFT || kind > MCL_BOWQ) return fail(MCL_EINVAL, "queries: bad kind %d", kind);
     if (n_queries < 0) return fail(MCL_EINVAL, "queries: n_queries < 0");
@@ -643,7 +666,9 @@ int queries_build(mcl_ctx* c, int kind, int n_queries, const int64_t* q_row_offs
     q->rows = rows;
     q->borrowed = borrowed;
     q->h_off.assign(q_row_offsets, q_row_offsets + n_queries + 1);
-    cudaStream_t st = c->stream;
+    cudaStream_t st = src_on_device && on_stream ? on_stream : c->stream;
+    q->built_on = st;
+    const cudaMemcpyKind h2d = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
 #define QCU(expr)                                                                                                 \
     do {                                                                                                          \
         cudaError_t e_ = (expr);                                                                                  \
@@ -652,6 +677,7 @@ int queries_build(mcl_ctx* c, int kind, int n_queries, const int64_t* q_row_offs
             return fail(MCL_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);   \
         }                                                                                                         \
     } while (0)
+    q->pooled = src_on_device;
     auto get = [&](DevBuf& scratch, void** dst, size_t bytes) -> cudaError_t {
         bytes = std::max<size_t>(bytes, 256);
         if (borrowed) {
@@ -659,28 +685,36 @@ int queries_build(mcl_ctx* c, int kind, int n_queries, const int64_t* q_row_offs
             *dst = scratch.p;
             return e;
         }
+        if (q->pooled) {
+            (dst == (void**)&q->d_off ? q->sz_off : dst == &q->d_desc ? q->sz_desc : dst == (void**)&q->d_norm ? q->sz_norm : q->sz_frame) = bytes;
+            return pool_alloc(c, dst, bytes);
+        }
         return cudaMalloc(dst, bytes);
     };
     QCU(get(c->tq_off, (void**)&q->d_off, (size_t)(n_queries + 1) * 8));
     QCU(cudaMemcpyAsync(q->d_off, q->h_off.data(), (size_t)(n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
     if (kind == MCL_SIFT) {
-        using namespace mcl::sifttc;
         q->padded_rows = std::max<int64_t>(QROW_PAD, (rows + QROW_PAD - 1) / QROW_PAD * QROW_PAD);
         QCU(get(c->tq_desc, &q->d_desc, (size_t)q->padded_rows * 128));
         QCU(get(c->tq_norm, (void**)&q->d_norm, (size_t)q->padded_rows * 4));
         QCU(get(c->tq_frame, (void**)&q->d_frame, (size_t)q->padded_rows * 4));
+        if (src_on_device) {
+            QCU(pool_alloc(c, (void**)&q->d_bad, 256));
+            QCU(cudaMemsetAsync(q->d_bad, 0, 4, st));
+        }
         rc = ingest_rows128(c, st, q_desc, q_dtype, rows, n_queries, q->d_off, q->d_off, q->padded_rows,
-                            (uint8_t*)q->d_desc, q->d_norm, q->d_frame);
+                            (uint8_t*)q->d_desc, q->d_norm, q->d_frame, nullptr, !src_on_device, nullptr, nullptr, nullptr,
+                            src_on_device, q->d_bad);
         if (rc) { mcl_queries_destroy(q); return rc; }
     } else if (kind == MCL_BOWQ) {
         q->padded_rows = rows;
         QCU(get(c->tq_desc, &q->d_desc, (size_t)rows * 512));
         if (rows) {
             if (q_dtype == MCL_F32) {
-                QCU(cudaMemcpyAsync(q->d_desc, q_desc, (size_t)rows * 512, cudaMemcpyHostToDevice, st));
+                QCU(cudaMemcpyAsync(q->d_desc, q_desc, (size_t)rows * 512, h2d, st));
             } else {
                 QCU(c->stage.ensure((size_t)rows * 128));
-                QCU(cudaMemcpyAsync(c->stage.p, q_desc, (size_t)rows * 128, cudaMemcpyHostToDevice, st));
+                QCU(cudaMemcpyAsync(c->stage.p, q_desc, (size_t)rows * 128, h2d, st));
                 ProfScope ps(c, PROF_PREP, st);
                 mcl::u8_to_f32_kernel<<<grid_for(rows * 128, 256, c->sm_count * 8), 256, 0, st>>>(
                     c->stage.as<uint8_t>(), (float*)q->d_desc, rows * 128);
@@ -690,10 +724,11 @@ int queries_build(mcl_ctx* c, int kind, int n_queries, const int64_t* q_row_offs
         const size_t rb = row_bytes(kind, q_dtype);
         q->padded_rows = rows;
         QCU(get(c->tq_desc, &q->d_desc, (size_t)rows * rb));
-        if (rows) QCU(cudaMemcpyAsync(q->d_desc, q_desc, (size_t)rows * rb, cudaMemcpyHostToDevice, st));
+        if (rows) QCU(cudaMemcpyAsync(q->d_desc, q_desc, (size_t)rows * rb, h2d, st));
     }
-    // the host offsets/descriptors are caller-owned: the copies must have been consumed before we return
-    QCU(cudaStreamSynchronize(st));
+    // the host offsets/descriptors are caller-owned: the copies must have been consumed before we return (a device-built
+    // batch only enqueues: its offsets live in q->h_off, which outlives the copy)
+    if (!src_on_device) QCU(cudaStreamSynchronize(st));
 #undef QCU
     *out = q;
     return MCL_OK;
@@ -706,231 +741,112 @@ extern "C" int mcl_queries_create(mcl_ctx* c, int kind, int n_queries, const int
     return queries_build(c, kind, n_queries, q_row_offsets, q_desc, q_dtype, false, out);
 }
 
+extern "C" int mcl_queries_create_device(mcl_ctx* c, int kind, int n_queries, const int64_t* q_row_offsets, const void* d_desc,
+                                         int q_dtype, void* stream, mcl_queries** out) {
+    if (!c || !out) return fail(MCL_EINVAL, "mcl_queries_create_device: NULL argument");
+    return queries_build(c, kind, n_queries, q_row_offsets, d_desc, q_dtype, false, out, true, (cudaStream_t)stream);
+}
+
+extern "C" int mcl_queries_validate(mcl_queries* q) {
+    if (!q) return fail(MCL_EINVAL, "mcl_queries_validate: NULL argument");
+    if (!q->d_bad) return MCL_OK;   // host-built batches were checked when they were created
+    int h_bad = 0;
+    CU(cudaSetDevice(q->ctx->device));
+    CU(cudaMemcpyAsync(&h_bad, q->d_bad, 4, cudaMemcpyDeviceToHost, q->built_on));
+    CU(cudaStreamSynchronize(q->built_on));
+    if (h_bad) return fail(MCL_EDATA, "SIFT descriptors must be integer valued in [0,255]");
+    return MCL_OK;
+}
+
 // ================================================================================================
 // matching
 // ================================================================================================
 namespace {
 
-int launch_sift_tc(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, cudaStream_t st) {
-    using namespace mcl::sifttc;
-    mcl_ctx* c = m->ctx;
-    const size_t smem = sizeof(Smem) + 1024;
-    if (!c->tc_attr_set) {
-        CU(cudaFuncSetAttribute(sift_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(sift_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(sift_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(sift_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(sift_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        c->tc_attr_set = true;
-    }
-    const int n_qblocks_total = (int)(q->padded_rows / QBLK);
-    // candidate buffer: sized for 1/4 of all (query row, image) pairs of a batch being candidates; an overflow is
-    // detected on the device and repaired by the exact SIMT kernel (see below), so this is only a performance knob.
-    const int64_t pairs_total = q->padded_rows * (int64_t)std::max(1, m->n_images);
-    const int64_t want = std::min<int64_t>(std::max<int64_t>(pairs_total / 4, 1 << 16), (int64_t)48 << 20);
-    if ((size_t)want > c->cand_cap_entries) {
-        CU(c->cand.ensure((size_t)want * sizeof(int4)));
-        c->cand_cap_entries = (size_t)want;
-    }
-    // option 3 (tests): cap the candidate list to force the overflow -> exact SIMT repair path
-    const int64_t cap = c->opt[3] > 0 ? std::min<int64_t>(c->opt[3], (int64_t)c->cand_cap_entries) : (int64_t)c->cand_cap_entries;
-    int batch_qblocks = (int)std::max<int64_t>(1, cap * 4 / ((int64_t)std::max(1, m->n_images) * QBLK));
-    batch_qblocks = std::min(batch_qblocks, n_qblocks_total);
-    unsigned int* d_cand_count = c->flags.as<unsigned int>();
-    int* d_overflow = c->flags.as<int>() + 1;
-    CU(cudaMemsetAsync(d_overflow, 0, 4, st));
-    for (int qb0 = 0; qb0 < n_qblocks_total; qb0 += batch_qblocks) {
-        const int nqb = std::min(batch_qblocks, n_qblocks_total - qb0);
-        const mcl_map::ChunkSet* cs = pick_chunks(m->chunk_sets, nqb, c->sm_count);
-        if (cs->n == 0) break;
-        CU(cudaMemsetAsync(d_cand_count, 0, 4, st));
-        Params p;
-        p.q_desc = (const uint8_t*)q->d_desc + (size_t)qb0 * QBLK_BYTES;
-        p.q_norm = q->d_norm + (size_t)qb0 * QBLK;
-        p.m_desc = (const uint8_t*)m->d_desc;
-        p.m_meta = m->d_meta;
-        p.chunks = cs->d;
-        p.n_qblocks = nqb;
-        p.n_chunks = cs->n;
-        p.ratio = ratio;
-        p.cand = c->cand.as<int4>();
-        p.cand_count = d_cand_count;
-        p.cand_cap = (unsigned)cap;
-        p.overflow = d_overflow;
-        p.q_row_base = qb0 * QBLK;
-        const int64_t n_items = (int64_t)nqb * cs->n;
-        const int grid = (int)std::min<int64_t>(n_items, c->sm_count);
-        {
-            ProfScope ps(c, PROF_SIFT_TC, st);
-            if (c->opt[0] == 1) sift_tc_kernel<1><<<grid, THREADS, smem, st>>>(p);
-            else if (c->opt[0] == 2) sift_tc_kernel<2><<<grid, THREADS, smem, st>>>(p);
-            else if (c->opt[0] == 3) sift_tc_kernel<3><<<grid, THREADS, smem, st>>>(p);
-            else if (c->opt[0] == 4) sift_tc_kernel<4><<<grid, THREADS, smem, st>>>(p);
-            else sift_tc_kernel<0><<<grid, THREADS, smem, st>>>(p);
-        }
-        CU(cudaGetLastError());
-        {
-            ProfScope ps(c, PROF_SIFT_FIX, st);
-            sift_fixup_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->cand.as<int4>(), d_cand_count, (unsigned)cap,
-                                                              (const uint8_t*)q->d_desc, q->d_norm, q->d_frame,
-                                                              (const uint8_t*)m->d_desc, m->d_norm, ratio, m->n_images,
-                                                              d_counts);
-        }
-        CU(cudaGetLastError());
-    }
-    // exact repair if (and only if) a candidate list overflowed: the SIMT kernel overwrites every count
-    {
-        ProfScope ps(c, PROF_SIFT_SIMT, st);
-        dim3 grid(std::max(1, m->n_images), std::max(1, q->n_queries));
-        mcl::sift_simt_kernel<<<grid, 128, 0, st>>>((const uint8_t*)q->d_desc, q->d_norm, q->d_off, (const uint8_t*)m->d_desc,
-                                                    m->d_norm, m->d_dst_off, m->d_src_off, m->n_images, ratio, nullptr,
-                                                    d_overflow, d_counts);
-    }
-    CU(cudaGetLastError());
-    return MCL_OK;
+// cluster launch helper
+template <typename K, typename P>
+cudaError_t launch_cluster(K kernel, int grid, int threads, size_t smem, cudaStream_t st, int cl, const P& p) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+template <typename K>
+int max_active_clusters(K kernel, int sm_count, int threads, size_t smem, int cl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((sm_count / cl) * cl);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+    return n;
 }
 
-int launch_sift_tc2(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, cudaStream_t st) {
-    using namespace mcl::sifttc2;
+// SIFT on the tensor cores: sift_tc4_kernel (bracketed pre-filter, candidates) + sift_fixup3_kernel (exact resolution) per
+// batch of query blocks, then the exact SIMT kernel on the (frame, image) pairs that lost a candidate to a full list.
+int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, cudaStream_t st) {
+    using mcl::sifttc3::Params;
+    using mcl::sifttc3::sift_fixup3_kernel;
+    using namespace mcl::sifttc4;
     mcl_ctx* c = m->ctx;
-    const size_t smem = sizeof(Smem);
-    if (!c->tc2_attr_set) {
-        CU(cudaFuncSetAttribute(sift_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(sift_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(sift_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        c->tc2_attr_set = true;
+    constexpr size_t smem = sizeof(SmemT<0>);
+    if (!c->tc4_attr) {
+        CU(cudaFuncSetAttribute(sift_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc4_kernel<0, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(sift_tc4_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // how many CTA pairs are co-resident (GPC boundaries may strand SMs)
+        c->max_clusters2 = max_active_clusters(sift_tc4_kernel<0, 0, 2>, c->sm_count, mcl::sifttc4::THREADS, smem, 2);
+        if (getenv("MCL_DEBUG")) fprintf(stderr, "[mcl] co-resident sift_tc4 clusters of 2 CTAs: %d (%d SMs)\n", c->max_clusters2, c->sm_count);
+        c->tc4_attr = true;
     }
     const int n_qblocks_total = (int)(q->padded_rows / QBLK);
+    // candidate list: sized for 1/4 of all (query row, image) pairs of a batch being candidates.  A candidate that does not fit
+    // marks its (frame, image) pair dirty; dirty pairs are recomputed by the exact SIMT kernel at the end of the call, so
+    // the size is only a performance knob (an adversarial batch degrades pair by pair, not as a whole).
     const int64_t pairs_total = q->padded_rows * (int64_t)std::max(1, m->n_images);
     const int64_t want = std::min<int64_t>(std::max<int64_t>(pairs_total / 4, 1 << 16), (int64_t)48 << 20);
     if ((size_t)want > c->cand_cap_entries) {
         CU(c->cand.ensure((size_t)want * sizeof(int4)));
         c->cand_cap_entries = (size_t)want;
     }
-    // option 3 (tests): cap the candidate list to force the overflow -> exact SIMT repair path
+    // option 3 (tests): cap the candidate list to force the dirty-pair repair path
     const int64_t cap = c->opt[3] > 0 ? std::min<int64_t>(c->opt[3], (int64_t)c->cand_cap_entries) : (int64_t)c->cand_cap_entries;
     int batch_qblocks = (int)std::max<int64_t>(1, cap * 4 / ((int64_t)std::max(1, m->n_images) * QBLK));
     batch_qblocks = std::min(batch_qblocks, n_qblocks_total);
     unsigned int* d_cand_count = c->flags.as<unsigned int>();
     int* d_overflow = c->flags.as<int>() + 1;
     unsigned int* d_rescans = c->flags.as<unsigned int>() + 3;
+    unsigned long long* d_stats = c->flags.as<unsigned long long>() + 8;   // [0] candidates, [1] dirty pairs (bytes 64..79)
+    const size_t n_pairs = (size_t)std::max(1, q->n_queries) * std::max(1, m->n_images);
+    CU(c->dirty.ensure(n_pairs));
     CU(cudaMemsetAsync(d_overflow, 0, 4, st));
     for (int qb0 = 0; qb0 < n_qblocks_total; qb0 += batch_qblocks) {
         const int nqb = std::min(batch_qblocks, n_qblocks_total - qb0);
-        const mcl_map::ChunkSet* cs = pick_chunks(m->chunk_sets2, nqb, c->sm_count);
+        const mcl_map::ChunkSet* cs = pick_chunks(m->chunk_sets, nqb, c->sm_count, m->n_tiles);
         if (cs->n == 0) break;
         CU(cudaMemsetAsync(d_cand_count, 0, 4, st));
         Params p;
         p.q_desc = (const uint8_t*)q->d_desc + (size_t)qb0 * QBLK * 128;
         p.q_norm = q->d_norm + (size_t)qb0 * QBLK;
-        p.m_desc = (const uint8_t*)m->d_desc;
-        p.m_ext = m->d_ext2;
-        p.chunks = cs->d;
-        p.n_qblocks = nqb;
-        p.n_chunks = cs->n;
-        p.key_c = m->key_c;
-        p.ratio = ratio;
-        p.cand = c->cand.as<int4>();
-        p.cand_count = d_cand_count;
-        p.cand_cap = (unsigned)cap;
-        p.overflow = d_overflow;
-        p.q_row_base = qb0 * QBLK;
-        const int64_t n_items = (int64_t)nqb * cs->n;
-        const int grid = (int)std::min<int64_t>(n_items, c->sm_count);
-        {
-            ProfScope ps(c, PROF_SIFT_TC, st);
-            if (c->opt[0] == 3) sift_tc2_kernel<3><<<grid, THREADS, smem, st>>>(p);
-            else if (c->opt[0] == 4) sift_tc2_kernel<4><<<grid, THREADS, smem, st>>>(p);
-            else sift_tc2_kernel<0><<<grid, THREADS, smem, st>>>(p);
-        }
-        CU(cudaGetLastError());
-        {
-            ProfScope ps(c, PROF_SIFT_FIX, st);
-            sift_fixup2_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->cand.as<int4>(), d_cand_count, (unsigned)cap,
-                                                               (const uint8_t*)q->d_desc, q->d_norm, q->d_frame,
-                                                               (const uint8_t*)m->d_desc, m->d_norm, m->d_dst_off, m->key_c,
-                                                               ratio, m->n_images, d_counts, d_rescans);
-        }
-        CU(cudaGetLastError());
-    }
-    {
-        ProfScope ps(c, PROF_SIFT_SIMT, st);
-        dim3 grid(std::max(1, m->n_images), std::max(1, q->n_queries));
-        mcl::sift_simt_kernel<<<grid, 128, 0, st>>>((const uint8_t*)q->d_desc, q->d_norm, q->d_off, (const uint8_t*)m->d_desc,
-                                                    m->d_norm, m->d_dst_off, m->d_src_off, m->n_images, ratio, nullptr,
-                                                    d_overflow, d_counts);
-    }
-    CU(cudaGetLastError());
-    return MCL_OK;
-}
-
-int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, cudaStream_t st, bool gen4 = false) {
-    using namespace mcl::sifttc3;
-    mcl_ctx* c = m->ctx;
-    const size_t smem = sizeof(Smem);
-    if (!m->tc3_attr) {
-        CU(cudaFuncSetAttribute(sift_tc3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(sift_tc3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(sift_tc3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(sift_tc3_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaFuncSetAttribute(sift_tc3_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        m->tc3_attr = true;
-    }
-    const int ss_tiles = std::max(0, std::min(c->opt[4], 1));   // option 4: A tiles the MMAs read from shared memory (2 no longer fit beside the staged metadata)
-    const size_t smem4 = ss_tiles == 0 ? sizeof(mcl::sifttc4::SmemT<0>) : sizeof(mcl::sifttc4::SmemT<1>);
-    if (gen4 && !m->tc4_attr) {
-        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<1>)));
-        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
-        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
-        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<0, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
-        for (int cl = 2; cl <= 4; cl += 2) {   // how many clusters of this size are co-resident (GPC boundaries may strand SMs)
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((c->sm_count / cl) * cl);
-            cfg.blockDim = dim3(mcl::sifttc4::THREADS);
-            cfg.dynamicSmemBytes = sizeof(mcl::sifttc4::SmemT<0>);
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = cl;
-            at[0].val.clusterDim.y = 1;
-            at[0].val.clusterDim.z = 1;
-            cfg.attrs = at;
-            cfg.numAttrs = 1;
-            int n = 0;
-            cudaError_t e = cl == 2 ? cudaOccupancyMaxActiveClusters(&n, mcl::sifttc4::sift_tc4_kernel<0, 0, 2>, &cfg)
-                                    : cudaOccupancyMaxActiveClusters(&n, mcl::sifttc4::sift_tc4_kernel<0, 0, 4>, &cfg);
-            if (e != cudaSuccess) { n = 0; cudaGetLastError(); }
-            c->max_clusters[cl / 2 - 1] = n;
-            if (getenv("MCL_DEBUG")) fprintf(stderr, "[mcl] co-resident sift_tc4 clusters of %d CTAs: %d (%d SMs)\n", cl, n, c->sm_count);
-        }
-        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
-        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
-        CU(cudaFuncSetAttribute(mcl::sifttc4::sift_tc4_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mcl::sifttc4::SmemT<0>)));
-        m->tc4_attr = true;
-    }
-    const int n_qblocks_total = (int)(q->padded_rows / QBLK);
-    const int64_t pairs_total = q->padded_rows * (int64_t)std::max(1, m->n_images);
-    const int64_t want = std::min<int64_t>(std::max<int64_t>(pairs_total / 4, 1 << 16), (int64_t)48 << 20);
-    if ((size_t)want > c->cand_cap_entries) {
-        CU(c->cand.ensure((size_t)want * sizeof(int4)));
-        c->cand_cap_entries = (size_t)want;
-    }
-    // option 3 (tests): cap the candidate list to force the overflow -> exact SIMT repair path
-    const int64_t cap = c->opt[3] > 0 ? std::min<int64_t>(c->opt[3], (int64_t)c->cand_cap_entries) : (int64_t)c->cand_cap_entries;
-    int batch_qblocks = (int)std::max<int64_t>(1, cap * 4 / ((int64_t)std::max(1, m->n_images) * QBLK));
-    batch_qblocks = std::min(batch_qblocks, n_qblocks_total);
-    unsigned int* d_cand_count = c->flags.as<unsigned int>();
-    int* d_overflow = c->flags.as<int>() + 1;
-    unsigned int* d_rescans = c->flags.as<unsigned int>() + 3;
-    CU(cudaMemsetAsync(d_overflow, 0, 4, st));
-    for (int qb0 = 0; qb0 < n_qblocks_total; qb0 += batch_qblocks) {
-        const int nqb = std::min(batch_qblocks, n_qblocks_total - qb0);
-        const mcl_map::ChunkSet* cs = gen4 ? pick_chunks(m->chunk_sets, nqb, c->sm_count, m->padded_rows / 128)   // 128-row tiles
-                                           : pick_chunks(m->chunk_sets2, nqb, c->sm_count);                     // 64-row tiles
-        if (cs->n == 0) break;
-        CU(cudaMemsetAsync(d_cand_count, 0, 4, st));
-        Params p;
-        p.q_desc = (const uint8_t*)q->d_desc + (size_t)qb0 * QBLK * 128;
-        p.q_norm = q->d_norm + (size_t)qb0 * QBLK;
+        p.q_frame = q->d_frame + (size_t)qb0 * QBLK;
         p.m_desc = (const uint8_t*)m->d_desc;
         p.m_meta = m->d_meta3;
         p.chunks = cs->d;
@@ -941,71 +857,41 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         p.cand_count = d_cand_count;
         p.cand_cap = (unsigned)cap;
         p.overflow = d_overflow;
+        p.dirty = c->dirty.as<uint8_t>();
+        p.n_images = m->n_images;
         p.q_row_base = qb0 * QBLK;
-        p.meta_cap = c->opt[1] == 1 ? 0 : (gen4 ? mcl::sifttc4::META_CAP : META_CAP);   // option 1 = 1: always read the tile metadata from global memory
-        // CTAs of a cluster share the map tiles (multicast): worth it for long launches (less L2 traffic -> less power); a
-        // query-block count that is not a multiple of the cluster size idles CTAs for one item.
-        // option 5: 0 = automatic (pairs), 1 = never, 2 / 4 = always that cluster size
+        p.meta_cap = c->opt[1] == 1 ? 0 : META_CAP;   // option 1 = 1: always read the tile records from global memory
+        // CTAs of a cluster share the map tiles (multicast): less L2 traffic -> less power; a query-block count that is not
+        // a multiple of the cluster size idles one CTA for one item per chunk, so small odd batches launch plain CTAs.
+        // option 5: 0 = automatic, 1 = never, 2 = always pairs
         int cl = 1;
-        if (gen4 && c->opt[0] == 0 && ss_tiles == 0) {
-            if (c->opt[5] == 2 || c->opt[5] == 4) cl = c->opt[5];
+        if (c->opt[0] == 0) {
+            if (c->opt[5] == 2) cl = 2;
             else if (c->opt[5] == 0 && ((nqb % 2 == 0 && nqb >= 2) || nqb >= 32)) cl = 2;
-            if (cl > 1 && c->max_clusters[cl / 2 - 1] < 1) cl = 1;
+            if (cl > 1 && c->max_clusters2 < 1) cl = 1;
         }
-        const bool cl2 = cl > 1;
         const int64_t n_items = (int64_t)((nqb + cl - 1) / cl) * cs->n;
-        const int grid = cl > 1 ? cl * (int)std::min<int64_t>(n_items, c->max_clusters[cl / 2 - 1]) : (int)std::min<int64_t>(n_items, c->sm_count);
+        const int grid = cl > 1 ? cl * (int)std::min<int64_t>(n_items, c->max_clusters2) : (int)std::min<int64_t>(n_items, c->sm_count);
         {
             ProfScope ps(c, PROF_SIFT_TC, st);
-            if (gen4) {
-                using namespace mcl::sifttc4;
-                if (c->opt[0] == 3) sift_tc4_kernel<3><<<grid, mcl::sifttc4::THREADS, sizeof(SmemT<0>), st>>>(p);
-                else if (c->opt[0] == 4) sift_tc4_kernel<4><<<grid, mcl::sifttc4::THREADS, sizeof(SmemT<0>), st>>>(p);
-                else if (c->opt[0] == 5) {   // timeline of 64 consecutive tiles: epilogue warp 5 and the MMA warp of CTA 0
-                    sift_tc4_kernel<5><<<grid, mcl::sifttc4::THREADS, sizeof(SmemT<0>), st>>>(p);
-                    long long tl[64 * 5], tm[64 * 6];
-                    cudaStreamSynchronize(st);
-                    cudaMemcpy(tl, reinterpret_cast<long long*>(c->cand.as<int4>() + (cap - 1024)), sizeof tl, cudaMemcpyDeviceToHost);
-                    cudaMemcpy(tm, reinterpret_cast<long long*>(c->cand.as<int4>() + (cap - 1024)) + 1024, sizeof tm, cudaMemcpyDeviceToHost);
-                    for (int i = 0; i < 64; ++i)
-                        fprintf(stderr, "tile %2d epi: wait_full %5lld ld1 %5lld max+ld2+arrive %5lld compute %5lld period %5lld | mma: wait_b %5lld wait_e0 %5lld e1 %5lld e2 %5lld rest %5lld period %5lld | full->empty %5lld\n", i,
-                                tl[i * 5 + 1] - tl[i * 5], tl[i * 5 + 2] - tl[i * 5 + 1], tl[i * 5 + 3] - tl[i * 5 + 2], tl[i * 5 + 4] - tl[i * 5 + 3],
-                                i ? tl[i * 5] - tl[i * 5 - 5] : 0, tm[i * 6 + 1] - tm[i * 6], tm[i * 6 + 2] - tm[i * 6 + 1], tm[i * 6 + 3] - tm[i * 6 + 2],
-                                tm[i * 6 + 4] - tm[i * 6 + 3], tm[i * 6 + 5] - tm[i * 6 + 4], i ? tm[i * 6] - tm[i * 6 - 6] : 0,
-                                tl[i * 5 + 3] - tl[i * 5 + 1]);
-                }
-                else if (cl2) {
-                    cudaLaunchConfig_t cfg = {};
-                    cfg.gridDim = dim3(grid);
-                    cfg.blockDim = dim3(mcl::sifttc4::THREADS);
-                    cfg.dynamicSmemBytes = sizeof(SmemT<0>);
-                    cfg.stream = st;
-                    cudaLaunchAttribute at[1];
-                    at[0].id = cudaLaunchAttributeClusterDimension;
-                    at[0].val.clusterDim.x = cl;
-                    at[0].val.clusterDim.y = 1;
-                    at[0].val.clusterDim.z = 1;
-                    cfg.attrs = at;
-                    cfg.numAttrs = 1;
-                    if (cl == 2) CU(cudaLaunchKernelEx(&cfg, sift_tc4_kernel<0, 0, 2>, p));
-                    else CU(cudaLaunchKernelEx(&cfg, sift_tc4_kernel<0, 0, 4>, p));
-                }
-                else if (ss_tiles == 1) sift_tc4_kernel<0, 1><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
-                else sift_tc4_kernel<0><<<grid, mcl::sifttc4::THREADS, smem4, st>>>(p);
-            } else if (c->opt[0] == 3) sift_tc3_kernel<3><<<grid, THREADS, smem, st>>>(p);
-            else if (c->opt[0] == 4) sift_tc3_kernel<4><<<grid, THREADS, smem, st>>>(p);
-            else if (c->opt[0] == 6) sift_tc3_kernel<6><<<grid, THREADS, smem, st>>>(p);
-            else if (c->opt[0] == 5) {
-                sift_tc3_kernel<5><<<grid, THREADS, smem, st>>>(p);
-                long long tl[64 * 5];
+            const int T = mcl::sifttc4::THREADS;
+            if (c->opt[0] == 3) sift_tc4_kernel<3><<<grid, T, smem, st>>>(p);
+            else if (c->opt[0] == 4) sift_tc4_kernel<4><<<grid, T, smem, st>>>(p);
+            else if (c->opt[0] == 5) {   // timeline of 64 consecutive tiles: epilogue warp 5 and the MMA warp of CTA 0
+                sift_tc4_kernel<5><<<grid, T, smem, st>>>(p);
+                long long tl[64 * 5], tm[64 * 6];
                 cudaStreamSynchronize(st);
-                cudaMemcpy(tl, reinterpret_cast<long long*>(c->cand.p) + (size_t)(1 << 20), sizeof tl, cudaMemcpyDeviceToHost);
+                cudaMemcpy(tl, reinterpret_cast<long long*>(c->cand.as<int4>() + (cap - 1024)), sizeof tl, cudaMemcpyDeviceToHost);
+                cudaMemcpy(tm, reinterpret_cast<long long*>(c->cand.as<int4>() + (cap - 1024)) + 1024, sizeof tm, cudaMemcpyDeviceToHost);
                 for (int i = 0; i < 64; ++i)
-                    fprintf(stderr, "tile %2d: wait_full %5lld  ldtm %5lld  release %5lld  compute %5lld  | period %5lld\n", i, tl[i * 5 + 1] - tl[i * 5],
-                            tl[i * 5 + 2] - tl[i * 5 + 1], tl[i * 5 + 3] - tl[i * 5 + 2], tl[i * 5 + 4] - tl[i * 5 + 3],
-                            i ? tl[i * 5] - tl[i * 5 - 5] : 0);
+                    fprintf(stderr, "tile %2d epi: wait_full %5lld ld1 %5lld max+ld2+arrive %5lld compute %5lld period %5lld | mma: wait_b %5lld wait_e0 %5lld e1 %5lld e2 %5lld rest %5lld period %5lld | full->empty %5lld\n", i,
+                            tl[i * 5 + 1] - tl[i * 5], tl[i * 5 + 2] - tl[i * 5 + 1], tl[i * 5 + 3] - tl[i * 5 + 2], tl[i * 5 + 4] - tl[i * 5 + 3],
+                            i ? tl[i * 5] - tl[i * 5 - 5] : 0, tm[i * 6 + 1] - tm[i * 6], tm[i * 6 + 2] - tm[i * 6 + 1], tm[i * 6 + 3] - tm[i * 6 + 2],
+                            tm[i * 6 + 4] - tm[i * 6 + 3], tm[i * 6 + 5] - tm[i * 6 + 4], i ? tm[i * 6] - tm[i * 6 - 6] : 0,
+                            tl[i * 5 + 3] - tl[i * 5 + 1]);
             }
-            else sift_tc3_kernel<0><<<grid, THREADS, smem, st>>>(p);
+            else if (cl == 2) CU(launch_cluster(sift_tc4_kernel<0, 0, 2>, grid, T, smem, st, 2, p));
+            else sift_tc4_kernel<0><<<grid, T, smem, st>>>(p);
         }
         CU(cudaGetLastError());
         {
@@ -1013,16 +899,17 @@ int launch_sift_tc3(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
             sift_fixup3_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->cand.as<int4>(), d_cand_count, (unsigned)cap,
                                                                (const uint8_t*)q->d_desc, q->d_norm, q->d_frame,
                                                                (const uint8_t*)m->d_desc, m->d_norm, m->d_img_of, m->d_dst_off,
-                                                               ratio, m->n_images, d_counts, d_rescans);
+                                                               ratio, m->n_images, d_counts, d_rescans, d_stats);
         }
         CU(cudaGetLastError());
     }
+    // exact repair of the dirty (frame, image) pairs, if any: the SIMT kernel overwrites their counts
     {
         ProfScope ps(c, PROF_SIFT_SIMT, st);
         dim3 grid(std::max(1, m->n_images), std::max(1, q->n_queries));
         mcl::sift_simt_kernel<<<grid, 128, 0, st>>>((const uint8_t*)q->d_desc, q->d_norm, q->d_off, (const uint8_t*)m->d_desc,
-                                                    m->d_norm, m->d_dst_off, m->d_src_off, m->n_images, ratio, nullptr,
-                                                    d_overflow, d_counts);
+                                                    m->d_norm, m->d_dst_off, m->d_src_off, m->n_images, ratio, c->dirty.as<uint8_t>(),
+                                                    d_overflow, d_counts, d_stats + 1);
     }
     CU(cudaGetLastError());
     return MCL_OK;
@@ -1047,25 +934,15 @@ int match_device(mcl_map* m, mcl_queries* q, int mode, double ratio, const uint8
                 const double pairs = (double)q->rows * (double)m->rows;
                 use = (d_mask && pairs < 2.0e7) ? MCL_ALGO_SIMT : MCL_ALGO_TENSOR;
             }
-            if (use == MCL_ALGO_TENSOR_V2 && !m->ext_ok) use = MCL_ALGO_TENSOR_V1;  // norm range too wide for the K extension
             if (use == MCL_ALGO_TENSOR) {
-                int rc = launch_sift_tc3(m, q, ratio, d_counts, st, true);
-                if (rc) return rc;
-            } else if (use == MCL_ALGO_TENSOR_V3) {
-                int rc = launch_sift_tc3(m, q, ratio, d_counts, st, false);
-                if (rc) return rc;
-            } else if (use == MCL_ALGO_TENSOR_V2) {
-                int rc = launch_sift_tc2(m, q, ratio, d_counts, st);
-                if (rc) return rc;
-            } else if (use == MCL_ALGO_TENSOR_V1) {
-                int rc = launch_sift_tc(m, q, ratio, d_counts, st);
+                int rc = launch_sift_tc4(m, q, ratio, d_counts, st);
                 if (rc) return rc;
             } else {
                 ProfScope ps(c, PROF_SIFT_SIMT, st);
                 dim3 grid(ni, nf);
                 mcl::sift_simt_kernel<<<grid, 128, 0, st>>>((const uint8_t*)q->d_desc, q->d_norm, q->d_off,
                                                             (const uint8_t*)m->d_desc, m->d_norm, m->d_dst_off, m->d_src_off,
-                                                            ni, ratio, d_mask, nullptr, d_counts);
+                                                            ni, ratio, d_mask, nullptr, d_counts, nullptr);
             }
             CU(cudaGetLastError());
         } else {
@@ -1359,7 +1236,10 @@ extern "C" int mcl_bow_create(mcl_ctx* c, int n_locations, const int64_t* voc_ro
         BCU(cudaMemcpyAsync(b->d_imf, im_features, (size_t)b->total_images * W * 4, cudaMemcpyHostToDevice, st));
     BCU(cudaMemcpyAsync(b->d_voc_off, b->h_voc_off.data(), (size_t)(n_locations + 1) * 8, cudaMemcpyHostToDevice, st));
     BCU(cudaMemcpyAsync(b->d_img_off, b->h_img_off.data(), (size_t)(n_locations + 1) * 8, cudaMemcpyHostToDevice, st));
-    BCU(cudaFuncSetAttribute(mcl::bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W * 12));
+    if (W * 12 > c->bow_score_smem) {   // only ever raised: a smaller index created later must not lower it under a live larger one
+        BCU(cudaFuncSetAttribute(mcl::bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W * 12));
+        c->bow_score_smem = W * 12;
+    }
     // codebook planes for the tensor-core word assignment
     {
         b->h_tile_off.resize(n_locations + 1);
@@ -1576,7 +1456,7 @@ extern "C" int mcl_kmeans(mcl_ctx* c, int64_t n, const void* obs, int obs_dtype,
     if (!c || !obs || !guess || !out_voc || !out_k) return fail(MCL_EINVAL, "mcl_kmeans: NULL argument");
     if (n <= 0 || k <= 0 || n > ((int64_t)1 << 30)) return fail(MCL_EINVAL, "mcl_kmeans: bad n or k");
     if (obs_dtype != MCL_U8 && obs_dtype != MCL_F32) return fail(MCL_EINVAL, "mcl_kmeans: bad dtype");
-    if (max_iter <= 0) max_iter = 1000;
+    if (max_iter <= 0) max_iter = INT_MAX;   // scipy's loop has no iteration cap
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     using namespace mcl::bowtc;
@@ -1589,10 +1469,11 @@ extern "C" int mcl_kmeans(mcl_ctx* c, int64_t n, const void* obs, int obs_dtype,
     int32_t* d_tile_off = nullptr;
     uint8_t* d_tiles = nullptr;
     double* d_sum = nullptr;   // [0] distortion sum; the following int is k_new
-    auto cleanup = [&]() {
+    auto cleanup = [&]() {   // idempotent: an error inside assign_and_distort frees here and the caller frees again
         cudaStreamSynchronize(st);
-        cudaFree(d_obs); cudaFree(d_voc[0]); cudaFree(d_voc[1]); cudaFree(d_sums); cudaFree(d_counts);
-        cudaFree(d_voc_off); cudaFree(d_tile_off); cudaFree(d_tiles); cudaFree(d_sum);
+        void** ptrs[] = {(void**)&d_obs, (void**)&d_voc[0], (void**)&d_voc[1], (void**)&d_sums, (void**)&d_counts,
+                         (void**)&d_voc_off, (void**)&d_tile_off, (void**)&d_tiles, (void**)&d_sum};
+        for (void** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
     };
 #define KCU(expr)                                                                                                \
     do {                                                                                                          \
@@ -1678,11 +1559,13 @@ extern "C" int mcl_kmeans(mcl_ctx* c, int64_t n, const void* obs, int obs_dtype,
         ++iters;
         if (k_cur <= 0) { rc = fail(MCL_EDATA, "mcl_kmeans: every cluster became empty"); break; }
     }
-    if (rc == MCL_OK) rc = assign_and_distort();   // final distortion of the returned code book
+    if (rc == MCL_OK && iters == 0) rc = assign_and_distort();   // thresh = inf: scipy would not iterate either; report the guess's distortion
     if (rc == MCL_OK) {
         KCU(cudaMemcpyAsync(out_voc, d_voc[cur], (size_t)k_cur * 512, cudaMemcpyDeviceToHost, st));
         KCU(cudaStreamSynchronize(st));
         *out_k = k_cur;
+        // scipy returns prev_avg_dists[1]: the average distortion of the LAST assignment, i.e. against the code book before
+        // its final update (scipy/cluster/vq/_vq_impl.py _kmeans)
         if (out_distortion) *out_distortion = avg;
         if (out_iters) *out_iters = iters;
     }
@@ -1696,6 +1579,64 @@ extern "C" int mcl_kmeans(mcl_ctx* c, int64_t n, const void* obs, int obs_dtype,
 // small stages
 // ================================================================================================
 namespace {
+// the recursion of numpy's pairwise sum over n elements starting at lo; returns a reference to the node holding the
+// range's sum: a leaf index (>= 0) or -1 - (index of an internal node in `nodes`)
+struct LapNode { int l, r, height; };
+int lap_build(int lo, int n, std::vector<int>& leaf_lo, std::vector<int>& leaf_n, std::vector<LapNode>& nodes, int& height) {
+    if (n <= 128) {
+        leaf_lo.push_back(lo);
+        leaf_n.push_back(n);
+        height = 0;
+        return (int)leaf_lo.size() - 1;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    int hl = 0, hr = 0;
+    const int l = lap_build(lo, n2, leaf_lo, leaf_n, nodes, hl);
+    const int r = lap_build(lo + n2, n - n2, leaf_lo, leaf_n, nodes, hr);
+    height = std::max(hl, hr) + 1;
+    nodes.push_back({l, r, height});
+    return -1 - ((int)nodes.size() - 1);
+}
+
+int lap_plan_get(mcl_ctx* c, int64_t N, const LapPlan** out) {
+    auto it = c->lap_plans.find(N);
+    if (it != c->lap_plans.end()) { *out = &it->second; return MCL_OK; }
+    if (c->lap_plans.size() >= 32) {   // sizes come and go: drop the tables rather than grow without bound
+        CU(cudaStreamSynchronize(c->stream));
+        for (auto& kv : c->lap_plans) cudaFree(kv.second.d_tab);
+        c->lap_plans.clear();
+    }
+    std::vector<int> leaf_lo, leaf_n;
+    std::vector<LapNode> nodes;
+    int height = 0;
+    lap_build(0, (int)N, leaf_lo, leaf_n, nodes, height);
+    // internal nodes ordered by height (children before parents; the root last), references remapped to value indices
+    std::vector<int> order(nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nodes[a].height < nodes[b].height; });
+    std::vector<int> pos(nodes.size());
+    for (size_t i = 0; i < order.size(); ++i) pos[order[i]] = (int)i;
+    LapPlan pl;
+    pl.n_leaves = (int)leaf_lo.size();
+    pl.n_nodes = (int)nodes.size();
+    pl.n_levels = height;
+    std::vector<int> tab;
+    tab.insert(tab.end(), leaf_lo.begin(), leaf_lo.end());
+    tab.insert(tab.end(), leaf_n.begin(), leaf_n.end());
+    auto ref = [&](int r) { return r >= 0 ? r : pl.n_leaves + pos[-1 - r]; };
+    for (int i : order) tab.push_back(ref(nodes[i].l));
+    for (int i : order) tab.push_back(ref(nodes[i].r));
+    std::vector<int> level_off(height + 1, 0);   // nodes of height h sit at [level_off[h - 1], level_off[h])
+    for (int i : order) level_off[nodes[i].height]++;
+    for (int h = 1; h <= height; ++h) level_off[h] += level_off[h - 1];
+    tab.insert(tab.end(), level_off.begin(), level_off.end());
+    CU(cudaMalloc((void**)&pl.d_tab, std::max<size_t>(tab.size() * 4, 16)));
+    CU(cudaMemcpy(pl.d_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    *out = &c->lap_plans.emplace(N, pl).first->second;
+    return MCL_OK;
+}
+
 int laplacian_common(mcl_ctx* c, int n, const uint8_t* const* imgs, const int* h, const int* w, const int* stride,
                      int64_t* sums_out, double* var_out) {
     if (!c || (n > 0 && (!imgs || !h || !w))) return fail(MCL_EINVAL, "mcl_laplacian: NULL argument");
@@ -1730,7 +1671,7 @@ int laplacian_common(mcl_ctx* c, int n, const uint8_t* const* imgs, const int* h
     CU(cudaMemcpyAsync(mb + o_w, w, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(mb + o_p, pitch.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(mb + o_s, 0, (size_t)n * 16, st));
-    {
+    if (sums_out) {   // sum Lb^2 (exact integers); the variance below needs only sum L, which the finish kernel gets from the border
         const int64_t threads = (int64_t)((max_w + mcl::LAP_PX - 1) / mcl::LAP_PX) * ((max_h + mcl::LAP_RY - 1) / mcl::LAP_RY);
         dim3 grid((unsigned)((threads + 255) / 256), n);
         ProfScope ps(c, PROF_LAP, st);
@@ -1744,7 +1685,47 @@ int laplacian_common(mcl_ctx* c, int n, const uint8_t* const* imgs, const int* h
                                                               (const int*)(mb + o_h), (const int*)(mb + o_w), n,
                                                               (long long*)(mb + o_s), (double*)(mb + o_v));
     CU(cudaGetLastError());
-    if (var_out) CU(cudaMemcpyAsync(var_out, mb + o_v, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (var_out) {
+        // numpy's two-pass variance, addition for addition (lap_var.cuh); images grouped by pixel count (one table each)
+        std::map<int64_t, std::vector<int>> groups;
+        for (int i = 0; i < n; ++i) {
+            if ((int64_t)h[i] * w[i] >= ((int64_t)1 << 31)) return fail(MCL_EINVAL, "image %d: too many pixels", i);
+            groups[(int64_t)h[i] * w[i]].push_back(i);
+        }
+        std::vector<int> list;
+        for (auto& g : groups) list.insert(list.end(), g.second.begin(), g.second.end());
+        CU(c->lap_list.ensure((size_t)n * 4));
+        CU(cudaMemcpyAsync(c->lap_list.p, list.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        size_t need = 0;
+        for (auto& g : groups) {
+            const LapPlan* pl = nullptr;
+            int r = lap_plan_get(c, g.first, &pl);
+            if (r) return r;
+            need = std::max(need, (size_t)(pl->n_leaves + pl->n_nodes) * g.second.size());
+        }
+        CU(c->lap_vals.ensure(need * 8));
+        int first = 0;
+        for (auto& g : groups) {
+            const LapPlan* pl = &c->lap_plans[g.first];
+            const int cnt = (int)g.second.size(), nl = pl->n_leaves, nn = pl->n_nodes, nv = nl + nn;
+            const int* t = pl->d_tab;
+            const int* lst = c->lap_list.as<int>() + first;
+            const int bx = std::max(1, std::min((nl + 31) / 32, std::max(1, 8 * c->sm_count / cnt)));
+            {
+                ProfScope ps(c, PROF_LAP, st);
+                mcl::lap_leaf_kernel<<<dim3(bx, cnt), 256, 0, st>>>(c->lap_pix.as<uint8_t>(), (const int64_t*)mb, (const int*)(mb + o_p),
+                                                                    (const int*)(mb + o_h), (const int*)(mb + o_w), lst,
+                                                                    (const long long*)(mb + o_s), t, t + nl, nl, nv, c->lap_vals.as<double>());
+            }
+            c->launches++;
+            mcl::lap_tree_kernel<<<cnt, 256, 0, st>>>(t + 2 * nl, t + 2 * nl + nn, t + 2 * nl + 2 * nn, pl->n_levels, nl, nv, lst,
+                                                      (const int*)(mb + o_h), (const int*)(mb + o_w), c->lap_vals.as<double>(),
+                                                      (double*)(mb + o_v));
+            CU(cudaGetLastError());
+            first += cnt;
+        }
+        CU(cudaMemcpyAsync(var_out, mb + o_v, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    }
     if (sums_out) CU(cudaMemcpyAsync(sums_out, mb + o_s, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return MCL_OK;
@@ -1785,14 +1766,15 @@ int filter_step_common(mcl_ctx* c, int L, int I, int stages, char cmd, double bl
     signed char* d_pt = reinterpret_cast<signed char*>(d_best + 4);
     signed char *d_ct = d_pt + 2 * L, *d_ot = d_ct + 2 * L;
     std::vector<double> fac(I);
-    for (int k = 0; k < I; ++k) fac[k] = 0.05 * std::fabs(std::sin((double)(k * 15 * 180) / M_PI));  // analyze.py:331 (sic)
+    const int step_deg = c->opt[6] > 0 ? c->opt[6] : 15;   // option 6: degrees between neighbouring map images (reference: 15)
+    for (int k = 0; k < I; ++k) fac[k] = 0.05 * std::fabs(std::sin((double)(k * step_deg * 180) / M_PI));  // analyze.py:331 (sic)
     CU(cudaMemcpyAsync(d_prev, prev, n * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_cur, cur, n * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_fac, fac.data(), (size_t)I * 8, cudaMemcpyHostToDevice, st));
     if (prev_type) CU(cudaMemcpyAsync(d_pt, prev_type, (size_t)2 * L, cudaMemcpyHostToDevice, st));
     if (cur_type) CU(cudaMemcpyAsync(d_ct, cur_type, (size_t)2 * L, cudaMemcpyHostToDevice, st));
     c->launches++;
-    mcl::filter_step_kernel<<<1, 256, 0, st>>>(L, I, stages, (int)cmd, blur, blur_type, d_prev, prev_type ? d_pt : nullptr, d_cur,
+    mcl::filter_step_kernel<<<1, 256, 0, st>>>(L, I, step_deg, stages, (int)cmd, blur, blur_type, d_prev, prev_type ? d_pt : nullptr, d_cur,
                                                cur_type ? d_ct : nullptr, d_fac, d_out, out_type ? d_ot : nullptr, d_best, d_scr);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(prev, d_prev, n * 8, cudaMemcpyDeviceToHost, st));

@@ -70,6 +70,12 @@ __global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restr
         dst[i] = (float)src[i];
 }
 
+// DOR: images a query was not matched against get the reference's stand-in count (optRun's "numMatches = 1", Matcher.py:359,369)
+__global__ void apply_mask_kernel(int32_t* __restrict__ counts, const uint8_t* __restrict__ mask, int64_t n, int32_t fill) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (!mask[i]) counts[i] = fill;
+}
+
 template <typename T>
 __global__ void fill_kernel(T* __restrict__ p, int64_t n, T v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;

@@ -1,52 +1,40 @@
-// SIFT / integer-L2 matching on 5th-gen tensor cores, third generation: the kernel the product path uses.
+// SIFT / integer-L2 matching on 5th-gen tensor cores: everything sift_tc4_kernel (sift_tc4.cuh, the product kernel) shares
+// with its exact fix-up -- the norm-sorted map layout, the per-64-row tile records, the bracketed pre-filter and the
+// candidate format.  (This file was the third kernel generation; its own main kernel, N = 64 tiles with double-buffered
+// accumulators, and the two generations before it were removed once sift_tc4 superseded them -- DESIGN.md section 4.1
+// keeps their measurements, git history keeps the code.)
 //
 //   replaces: Matcher.SIFTMatch (Matcher.py:262-291) looped by Matcher.run (Matcher.py:305-338) looped by
 //             analyzer.createRawP (analyze.py:78-90): knnMatch(k=2) + ratio lambda (Matcher.py:280) + len().
 //
-// sift_tc2 made the kernel tensor-bound (tensor pipe 94 % busy) but pays a 5th MMA per tile to carry the -|m|^2/2
-// term inside the contraction: 20 % of the tensor time is not algorithmic work.  This generation gets the norm term
-// for free instead: at map build the rows of every image are SORTED BY NORM, so the 32 rows of a group have nearly
-// the same |m|^2 (real SIFT: 512^2 +- a few hundred over an image, a few units inside a group).  The epilogue takes
-// the bare maximum of the accumulators A_ij = q_i.m_j over the group (3-input max tree, no per-element add, no
-// shared-memory bias) and brackets the group's best key 2 q.m - |m|^2 by
+// At map build the rows of every image are SORTED BY NORM, so the 32 rows of a group have nearly the same |m|^2 (real
+// SIFT: 512^2 +- a few hundred over an image, a few units inside a group).  The epilogue takes the bare maximum of the
+// accumulators A_ij = q_i.m_j over the group (3-input max tree, no per-element add, no shared-memory bias) and brackets
+// the group's best key 2 q.m - |m|^2 by
 //        lo_g = 2*max_j A - nmax_g   <=   best key in g   <=   2*max_j A - nmin_g = hi_g .
 // Per image it tracks the group with the largest hi (G1), and over all other groups max(hi) and max(lo).  A (query row,
 // image) pair is rejected for good when even the most favourable reading (best = hi_G1, second = max lo of the others)
 // fails the ratio test; survivors go to sift_fixup3_kernel, which recomputes G1 exactly (dp4a), evaluates the ratio test
 // at both ends of the bracket of the others and, only if the verdicts differ, rescans the image exactly.  Counts are
 // bit-exact whatever the norms are; the sort only decides how often the exact rescan runs (practically never).
-//
-// Everything else is sift_tc2's pipeline: query block (3 x 128 rows) stationary in TENSOR MEMORY (A-from-TMEM MMA, 64 B/clk
-// of shared-memory reads instead of 128), 64-row map tiles streamed by TMA bulk copies in the SWIZZLE_128B image, 2 x 3
-// accumulators of 64 columns with their own full/empty barriers, 12 epilogue warps, one TMA warp, two MMA issuing warps,
-// tcgen05.mma / commit / cp.async.bulk issued through elect.sync in warp-uniform code.
 #pragma once
 #include "common.cuh"
-#include "sift_tc.cuh"  // Chunk
 
 namespace mcl {
 namespace sifttc3 {
 
-using sifttc::Chunk;
+struct Chunk {  // a contiguous range of whole images handled by one work item
+    int32_t tile_begin, tile_end;  // tiles [begin,end)
+    int32_t img_begin, img_end;    // images [begin,end) whose results this chunk owns
+};
 
 constexpr int TILE_N = 64;
-constexpr int GROUP = sifttc::GROUP;   // 32
+constexpr int GROUP = 32;              // rows per group; images are padded to a multiple of GROUP rows
 constexpr int GROUPS = TILE_N / GROUP;
 constexpr int QTILE = 128;
 constexpr int ATILES = 3;
 constexpr int QBLK = ATILES * QTILE;   // 384 query rows per work item
-constexpr int A_COLS = 32;             // TMEM columns per A tile (128 bytes per row)
-constexpr int ACC_COL0 = 128;
-constexpr int ACC_STAGES = 2;
-constexpr int B_TILE_BYTES = TILE_N * 128;
 constexpr int META_BYTES = 48;
-constexpr int STAGE_BYTES = B_TILE_BYTES;          // 8 KB: every stage stays 1024-byte aligned
-constexpr int B_STAGES = 16;
-constexpr int EPI_WARPS = ATILES * 4;
-constexpr int MMA_WARPS = 2;
-constexpr int THREADS = (EPI_WARPS + 1 + MMA_WARPS) * 32;
-constexpr int TMEM_COLS = 512;
-constexpr int META_CAP = 352;          // tiles of a chunk whose metadata is staged in shared memory (longer chunks read it from L2)
 constexpr int NONE = INT_MIN / 2;      // "no group yet": Q - NONE still fits in int32
 constexpr int POS_WIDE = 1 << 24;      // flag in a group position / candidate row: G1 is a whole 128-row tile (sift_tc4)
 
@@ -64,16 +52,6 @@ struct TileMeta {
 constexpr int MERGE_WIDTH = 1024;
 static_assert(sizeof(TileMeta) == META_BYTES, "meta size");
 
-struct Smem {
-    alignas(1024) uint8_t stage[B_STAGES][STAGE_BYTES];
-    alignas(16) int4 meta[META_CAP * 3];   // the current chunk's TileMeta records
-    alignas(8) uint64_t b_full[B_STAGES];
-    uint64_t b_empty[B_STAGES];
-    uint64_t acc_full[ACC_STAGES][ATILES], acc_empty[ACC_STAGES][ATILES];
-    uint64_t a_full, a_free;
-    uint32_t tmem_base;
-};
-
 struct Params {
     const uint8_t* q_desc;    // SW128 atoms, n_qblocks*QBLK rows (batch base)
     const int32_t* q_norm;    // -1 for padding rows
@@ -85,7 +63,10 @@ struct Params {
     int4* cand;               // {q row, first map row of G1, max hi of the other groups, max lo of the other groups}
     unsigned int* cand_count;
     unsigned int cand_cap;
-    int* overflow;
+    int* overflow;            // set when a candidate did not fit the list
+    uint8_t* dirty;           // [n_frames][n_images]: pairs that lost a candidate (recomputed exactly after the fix-up)
+    const int32_t* q_frame;   // frame of every query row (batch base)
+    int n_images;
     int q_row_base;
     int meta_cap;             // chunks up to this many tiles stage their metadata in shared memory (<= META_CAP)
 };
@@ -155,8 +136,10 @@ __device__ __noinline__ void finalize_image(const Params& p, int lane, bool row_
             const unsigned idx = base + __popc(bal & ((1u << lane) - 1u));
             if (idx < p.cand_cap)
                 p.cand[idx] = make_int4(p.q_row_base + (int)qrow, (pos & (POS_WIDE - 1)) * GROUP | ((pos & POS_WIDE) << 6), H2, L2);
-            else
+            else {   // list full: this (frame, image) pair is recomputed by the exact SIMT kernel at the end of the call
+                p.dirty[(int64_t)p.q_frame[qrow] * p.n_images + img] = 1;
                 *p.overflow = 1;
+            }
         }
     }
 }
@@ -184,202 +167,6 @@ __device__ __forceinline__ int group_max(const uint32_t (&v)[32]) {
     l[10] = max((int)v[30], (int)v[31]);
     const int a0 = max3(l[0], l[1], l[2]), a1 = max3(l[3], l[4], l[5]), a2 = max3(l[6], l[7], l[8]);
     return max3(max3(a0, a1, a2), l[9], l[10]);
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(THREADS, 1) sift_tc3_kernel(const __grid_constant__ Params p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
-    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-    const int warp = warp_id_uniform();
-    const int lane = threadIdx.x & 31;
-    const uint32_t leader = lane == 0;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < B_STAGES; ++i) { mbar_init(&s.b_full[i], 1); mbar_init(&s.b_empty[i], 1); }
-        for (int i = 0; i < ACC_STAGES; ++i)
-            for (int a = 0; a < ATILES; ++a) { mbar_init(&s.acc_full[i][a], 1); mbar_init(&s.acc_empty[i][a], 4); }
-        mbar_init(&s.a_full, EPI_WARPS);
-        mbar_init(&s.a_free, MMA_WARPS);
-        mbar_fence_init();
-    }
-    if (warp == EPI_WARPS + 1) tmem_alloc<TMEM_COLS>(&s.tmem_base);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = s.tmem_base;
-    const int n_items = p.n_qblocks * p.n_chunks;
-
-    if (warp == EPI_WARPS) {
-        // ================= TMA producer: one 64-row map tile (8 KB) per stage ==========================================
-        uint32_t bn = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const Chunk ch = p.chunks[item / p.n_qblocks];
-            for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
-                const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
-                mbar_wait(&s.b_empty[bs], bph ^ 1);
-                mbar_arrive_expect_tx_if(leader, &s.b_full[bs], B_TILE_BYTES);
-                bulk_g2s_if(leader, s.stage[bs], p.m_desc + (size_t)t * B_TILE_BYTES, B_TILE_BYTES, &s.b_full[bs]);
-            }
-        }
-    } else if (warp > EPI_WARPS) {
-        // ================= MMA issuers (one per accumulator stage): A from tensor memory, B from shared memory ========
-        const uint32_t my_stage = warp - (EPI_WARPS + 1);
-        constexpr uint32_t idesc = umma_idesc(/*c=S32*/ 2, /*a=u8*/ 0, /*b=u8*/ 0, QTILE, TILE_N);
-        uint32_t bn = 0, item_n = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
-            const Chunk ch = p.chunks[item / p.n_qblocks];
-            mbar_wait(&s.a_full, item_n & 1);
-            tc_fence_after();
-            for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
-                const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
-                const uint32_t as = bn % ACC_STAGES, aph = (bn / ACC_STAGES) & 1;
-                if (as != my_stage) continue;
-                mbar_wait(&s.b_full[bs], bph);
-                const uint64_t b_desc = umma_desc_sw128(smem_u32(s.stage[bs]));
-                // The three accumulators of this stage are independent: issue each A tile's MMAs as soon as ITS accumulator
-                // has been handed back, in whatever order that happens (in-order issue lets the slowest of the 12 epilogue
-                // warps hold up the other two A tiles: a convoy).
-                uint32_t pending = (1u << ATILES) - 1u;
-                while (pending) {
-#pragma unroll
-                    for (int a = 0; a < ATILES; ++a) {
-                        if (!(pending & (1u << a))) continue;
-                        if (!mbar_test_wait(&s.acc_empty[as][a], aph ^ 1)) continue;
-                        pending &= ~(1u << a);
-                        tc_fence_after();
-                        const uint32_t d = tmem_base + ACC_COL0 + (as * ATILES + a) * TILE_N;
-                        const uint32_t ta = tmem_base + a * A_COLS;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_i8_ts_if(leader, d, ta + 8 * k, b_desc + 2 * k, idesc, k > 0);
-                        tc_commit_if(leader, &s.acc_full[as][a]);
-                    }
-                }
-                tc_commit_if(leader, &s.b_empty[bs]);
-                __syncwarp();
-            }
-            tc_commit_if(leader, &s.a_free);
-            __syncwarp();
-        }
-    } else {
-        // ================= epilogue warps ===========================================================================
-        const int atile = warp >> 2;
-        const int lane_base = (warp & 3) * 32;
-        const int row_in_blk = atile * QTILE + lane_base + lane;
-        const uint32_t t_lane = tmem_base + ((uint32_t)lane_base << 16);
-        uint32_t bn = 0, item_n = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
-            const int qb = item % p.n_qblocks;
-            const Chunk ch = p.chunks[item / p.n_qblocks];
-            const int64_t qrow = (int64_t)qb * QBLK + row_in_blk;
-            {   // this thread's query row -> tensor memory (row = TMEM lane, 4 K-bytes per column)
-                uint32_t w[32];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 x = *reinterpret_cast<const uint4*>(p.q_desc + sw128_chunk_offset(qrow, c));
-                    w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
-                }
-                mbar_wait(&s.a_free, (item_n & 1) ^ 1);   // every MMA of the previous item has read its A tiles
-                tc_fence_after();
-                tmem_st32(t_lane + atile * A_COLS, w);
-                tmem_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s.a_full);
-            }
-            const int Q = p.q_norm[qrow];
-            const bool row_valid = Q >= 0;
-            int H1 = NONE, L1 = NONE, H2 = NONE, L2 = NONE, pos = 0;
-            // one (hi, lo) bracket joins the running state: the loser of (bracket, current G1) joins "the others"
-            auto join = [&](int gm, int nmin, int nmax, int id) {
-                const int hi = 2 * gm - nmin, lo = 2 * gm - nmax;
-                const bool better = hi > H1;
-                H2 = max(H2, better ? H1 : hi);
-                L2 = max(L2, better ? L1 : lo);
-                pos = better ? id : pos;
-                L1 = better ? lo : L1;
-                H1 = max(H1, hi);
-            };
-            // the chunk's tile metadata (48 B per tile) is staged in shared memory once per work item by the 12 epilogue
-            // warps (named barrier 1); per-tile reads from global memory miss L1 whenever an SM sees a chunk only once
-            const int n_ct = ch.tile_end - ch.tile_begin;
-            const int4* mp = reinterpret_cast<const int4*>(p.m_meta + ch.tile_begin);
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");   // nobody still reads the previous chunk's records
-            if (n_ct <= p.meta_cap) {
-                for (int i = threadIdx.x; i < n_ct * 3; i += EPI_WARPS * 32) s.meta[i] = __ldg(mp + i);
-                mp = s.meta;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-            int4 m0 = mp[0], m1 = mp[1], m2 = mp[2];
-#pragma unroll 2   // halves the loop-head cost per tile (measured +1.5 %); deferring the scalar tail under the next load did not pay
-            for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
-                const uint32_t as = bn % ACC_STAGES, aph = (bn / ACC_STAGES) & 1;
-                // m0 = {img0, img1, nval0, nval1}, m1 = {nmin0, nmin1, nmax0, nmax1}, m2 = {end_mask, tnmin, tnmax, -}
-                const int4 c0 = m0, c1 = m1, c2 = m2;
-                if (t + 1 < ch.tile_end) {
-                    mp += 3;
-                    m0 = mp[0]; m1 = mp[1]; m2 = mp[2];
-                }
-                long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
-                if (MODE == 5) tk0 = clock64();
-                mbar_wait(&s.acc_full[as][atile], aph);
-                tc_fence_after();
-                if (MODE == 5) tk1 = clock64();
-                const uint32_t tcol = t_lane + ACC_COL0 + (as * ATILES + atile) * TILE_N;
-                uint32_t v[GROUPS][32];
-                if (MODE == 6) {   // diagnostic: half of the TMEM read volume (results meaningless)
-                    tmem_ld32(tcol, v[0]);
-                    tmem_wait_all();
-                    tmem_fence_regs(v[0]);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[1][i] = v[0][i];
-                } else if (MODE != 4) {
-                    tmem_ld64(tcol, reinterpret_cast<uint32_t(&)[64]>(v));
-                    tmem_wait_all();
-#pragma unroll
-                    for (int g = 0; g < GROUPS; ++g) tmem_fence_regs(v[g]);
-                } else {
-#pragma unroll
-                    for (int g = 0; g < GROUPS; ++g)
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[g][i] = 0;
-                }
-                if (MODE == 5) tk2 = clock64();
-                // tcgen05.wait::ld is warp-aligned and returns when every lane's columns are in registers: the accumulator
-                // can go back to the MMA warp right away (no further tcgen05 fence is needed for a completed load)
-                if (lane == 0) mbar_arrive(&s.acc_empty[as][atile]);
-                if (MODE == 5) tk3 = clock64();
-                const int end_mask = c2.x;
-                const int g0 = group_max<MODE>(v[0]), g1 = group_max<MODE>(v[1]);
-                if ((end_mask & 1) == 0) {
-                    // both groups belong to one image (the common case): one 64-row bracket
-                    join(max(g0, g1), c2.y, c2.z, t * GROUPS);
-                    if (end_mask & 2) {
-                        finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.y, c0.w, ch);
-                        H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
-                    }
-                } else {
-                    join(g0, c1.x, c1.z, t * GROUPS);
-                    finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.x, c0.z, ch);
-                    H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
-                    if (c0.y >= 0) {
-                        join(g1, c1.y, c1.w, t * GROUPS + 1);
-                        if (end_mask & 2) {
-                            finalize_image(p, lane, row_valid, Q, qrow, H1, L1, H2, L2, pos, c0.y, c0.w, ch);
-                            H1 = NONE; L1 = NONE; H2 = NONE; L2 = NONE;
-                        }
-                    }
-                }
-                if (MODE == 5 && blockIdx.x == 0 && warp == 5 && lane == 0 && bn >= 100 && bn < 164) {
-                    long long* tl = reinterpret_cast<long long*>(p.cand) + (size_t)(1 << 20) + (bn - 100) * 5;
-                    tl[0] = tk0; tl[1] = tk1; tl[2] = tk2; tl[3] = tk3; tl[4] = clock64();
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == EPI_WARPS + 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -415,9 +202,10 @@ __global__ void sift_fixup3_kernel(const int4* __restrict__ cand, const unsigned
                                    const uint8_t* __restrict__ m_desc, const int32_t* __restrict__ m_norm,
                                    const int32_t* __restrict__ m_img_of, const int64_t* __restrict__ m_dst_off,
                                    double ratio, int n_images, int32_t* __restrict__ counts,
-                                   unsigned int* __restrict__ n_rescans) {
+                                   unsigned int* __restrict__ n_rescans, unsigned long long* __restrict__ n_candidates) {
     const int lane = threadIdx.x & 31;
     const unsigned n = min(*cand_count, cand_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(n_candidates, (unsigned long long)n);   // statistics
     const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
     for (unsigned c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < n; c += n_warps) {
         const int4 cd = cand[c];

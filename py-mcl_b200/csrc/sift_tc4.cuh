@@ -27,7 +27,7 @@
 namespace mcl {
 namespace sifttc4 {
 
-using sifttc::Chunk;
+using sifttc3::Chunk;
 using sifttc3::Params;          // chunks / tile indices are in units of TILE_N = 128 rows here; m_meta stays per 64 rows
 using sifttc3::NONE;
 

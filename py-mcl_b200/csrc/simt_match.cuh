@@ -18,10 +18,11 @@ __global__ void __launch_bounds__(128) sift_simt_kernel(
     const uint8_t* __restrict__ m_desc, const int32_t* __restrict__ m_norm, const int64_t* __restrict__ m_dst_off,
     const int64_t* __restrict__ m_src_off, int n_images, double ratio, const uint8_t* __restrict__ mask,
     const int* __restrict__ only_if /* optional device flag: run only when *only_if != 0 */,
-    int32_t* __restrict__ counts) {
+    int32_t* __restrict__ counts, unsigned long long* __restrict__ n_blocks_run /* optional statistics */) {
     const int img = blockIdx.x, frame = blockIdx.y;
     if (only_if && *only_if == 0) return;
     if (mask && !mask[(int64_t)frame * n_images + img]) return;
+    if (n_blocks_run && threadIdx.x == 0) atomicAdd(n_blocks_run, 1ULL);
     __shared__ uint4 sm_rows[SIMT_STAGE_ROWS][8];
     __shared__ int sm_norm[SIMT_STAGE_ROWS];
     __shared__ int sm_count;

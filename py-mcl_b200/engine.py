@@ -63,39 +63,186 @@ def sharded_apply(fn, items, group=None):
 
 
 class ShardedMap(object):
-    """All map images of all locations, flattened, with this rank's slice resident on its GPU."""
+    """All map images of all locations, flattened, with this rank's slice resident on its GPU.
 
-    def __init__(self, kind, descs, ctx=None, local_factory=None, group=None):
+    One process per GPU.  With NCCL the whole call stays on the device: every query frame is uploaded by ONE rank and its
+    rows are all-gathered over NVLink (instead of every rank pulling the same batch through its own PCIe link), each rank
+    matches against its slice (mcl_match_counts_device), the int32 counts are all-gathered on the device, and ONE
+    device-to-host copy returns them.  Other backends (gloo in the CPU tests, or a custom local matcher) take the host path."""
+
+    # batches below this many descriptor rows are uploaded whole by every rank (the collective would cost more than the copy)
+    SHARED_UPLOAD_MIN_ROWS = 32768
+
+    def __init__(self, kind, descs, ctx=None, local_factory=None, group=None, local_only=False):
+        """descs: every map image's descriptors (each rank keeps its slice), or -- local_only=True -- just THIS rank's
+        images, in rank order (the slices' sizes are exchanged once)."""
         self.kind = kind
-        self.n_images = len(descs)
         self.group = group
         d = _dist()
         self.world = d.get_world_size(group) if d else 1
         self.rank = d.get_rank(group) if d else 0
-        rows = [0 if x is None else len(x) for x in descs]
-        self.bounds = shard_bounds(rows, self.world)
-        lo, hi = self.bounds[self.rank]
-        self.lo, self.hi = lo, hi
+        if local_only:
+            counts = [len(descs)]
+            if self.world > 1:
+                counts = [None] * self.world
+                d.all_gather_object(counts, len(descs), group=group)
+            edges = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+            self.bounds = [(int(edges[r]), int(edges[r + 1])) for r in range(self.world)]
+            self.n_images = int(edges[-1])
+            local = descs
+        else:
+            self.n_images = len(descs)
+            rows = [0 if x is None else len(x) for x in descs]
+            self.bounds = shard_bounds(rows, self.world)
+            lo, hi = self.bounds[self.rank]
+            local = descs[lo:hi]
+        self.lo, self.hi = self.bounds[self.rank]
         if local_factory is None:
             ctx = ctx or _lib.default_context()
-            self.local = _lib.MapIndex(ctx, kind, descs[lo:hi])
+            self.local = _lib.MapIndex(ctx, kind, local)
         else:
-            self.local = local_factory(descs[lo:hi])
+            self.local = local_factory(local)
+        self._ctx = ctx
+        self._bufs = {}
 
     def close(self):
         if hasattr(self.local, "close"):
             self.local.close()
+        self._bufs = {}
 
-    def match_counts(self, q_descs, mode=_lib.KNN2_RATIO, ratio=0.7, mask=None, fill_value=1, algo=_lib.ALGO_AUTO):
-        """(n_queries, n_images) int32 on every rank."""
+    # ---- host path (single process, gloo, custom local matcher) ---------------------------------------------------
+    def match_counts(self, q_descs, mode=_lib.KNN2_RATIO, ratio=0.7, mask=None, fill_value=1, algo=_lib.ALGO_AUTO, packed=None):
+        """(n_queries, n_images) int32 on every rank.  `packed` = (offsets, matrix, dtype code) skips the packing."""
+        if self._on_device():
+            return self._match_counts_nccl(q_descs, mode, ratio, mask, fill_value, algo, packed)
         lo, hi = self.lo, self.hi
         local_mask = None if mask is None else np.ascontiguousarray(np.asarray(mask)[:, lo:hi])
-        local = self.local.match_counts(q_descs, mode=mode, ratio=ratio, mask=local_mask, fill_value=fill_value, algo=algo)
+        kw = {} if packed is None else {"packed": packed}
+        local = self.local.match_counts(q_descs, mode=mode, ratio=ratio, mask=local_mask, fill_value=fill_value, algo=algo, **kw)
         return self.gather(local)
 
     def gather(self, local):
         """all-gather of the per-image counts: local (F, hi-lo) -> (F, n_images)."""
         return gather_columns(local, self.bounds, self.group)
+
+    # ---- device path (NCCL) -------------------------------------------------------------------------------------------
+    def _on_device(self):
+        d = _dist()
+        return (self.world > 1 and d is not None and d.get_backend(self.group) == "nccl" and isinstance(self.local, _lib.MapIndex))
+
+    def _buf(self, name, shape, dtype, pinned=False):
+        """grow-only cache of device / pinned host tensors (no allocation on the per-call path)."""
+        import torch
+        n = int(np.prod(shape))
+        t = self._bufs.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            cap = max(n, 1)
+            t = torch.empty(cap, dtype=dtype).pin_memory() if pinned else torch.empty(cap, dtype=dtype, device="cuda")
+            self._bufs[name] = t
+        return t[:n].view(*shape)
+
+    def match_counts_device(self, queries, mode=_lib.KNN2_RATIO, ratio=0.7, d_mask=None, fill_value=1, algo=_lib.ALGO_AUTO):
+        """Resident query batch (a _lib.QueryBatch on this rank's context) -> torch int32 tensor (n_queries, n_images) on the
+        device, valid on the current torch stream: this rank's counts + the device all-gather, nothing touches the host."""
+        import torch
+        d = _dist()
+        F, w = queries.n_queries, self.hi - self.lo
+        maxw = max(h - l for l, h in self.bounds)
+        stream = torch.cuda.current_stream()
+        mine = self._buf("counts_local", (F, maxw), torch.int32)
+        if w < maxw:
+            mine.zero_()
+        tight = mine if w == maxw else self._buf("counts_tight", (F, w), torch.int32)
+        if w:
+            self.local.match_counts_device(queries, tight.data_ptr(), mode=mode, ratio=ratio,
+                                           d_mask_ptr=d_mask.data_ptr() if d_mask is not None else None, fill_value=fill_value,
+                                           algo=algo, stream=stream.cuda_stream)
+            if tight is not mine:
+                mine[:, :w].copy_(tight)
+        if self.world == 1:
+            return mine
+        allc = self._buf("counts_all", (self.world, F, maxw), torch.int32)
+        d.all_gather_into_tensor(allc, mine, group=self.group)
+        if all(h - l == maxw for l, h in self.bounds):
+            return allc.permute(1, 0, 2).reshape(F, self.world * maxw)
+        full = self._buf("counts_full", (F, self.n_images), torch.int32)
+        for r, (l, h) in enumerate(self.bounds):
+            full[:, l:h].copy_(allc[r][:, :h - l])
+        return full
+
+    def _match_counts_nccl(self, q_descs, mode, ratio, mask, fill_value, algo, packed):
+        import torch
+        d = _dist()
+        off, cat, code = packed if packed is not None else _lib.pack_descriptors(self.local.kind, q_descs)
+        F = len(off) - 1
+        rows = int(off[-1])
+        row_elems = cat.shape[1] if cat.ndim == 2 else _lib.ROW_DIM[self.local.kind]
+        tdt = torch.from_numpy(np.empty(0, dtype=cat.dtype)).dtype
+        main = torch.cuda.current_stream()
+        d_mask = None
+        if mask is not None:
+            m = np.ascontiguousarray(np.asarray(mask)[:, self.lo:self.hi], dtype=np.uint8)
+            d_mask = self._buf("mask", m.shape, torch.uint8)
+            d_mask.copy_(torch.from_numpy(m), non_blocking=False)
+        dq = self._buf("q_rows", (rows, row_elems), tdt)
+        src = torch.from_numpy(cat) if rows else None
+        plan = None
+        if rows >= self.SHARED_UPLOAD_MIN_ROWS and F >= 2 * self.world:
+            # frames in two parts (1/8, 7/8 of the rows): the second part's upload + all-gather runs on a side stream
+            # under the first part's matching.  Inside a part the frames are dealt to the ranks in contiguous runs of
+            # nearly equal row counts; each rank uploads its run, then the runs are all-gathered in place over NVLink.
+            cut = int(np.searchsorted(off, rows // 8, side="left"))
+            cut = min(max(cut, self.world), F - self.world)
+            plan = []
+            for f0, f1 in ((0, cut), (cut, F)):
+                r0, r1 = int(off[f0]), int(off[f1])
+                edges = [r0 + (r1 - r0) * k // self.world for k in range(self.world + 1)]
+                fe = [int(np.searchsorted(off, e, side="left")) for e in edges]
+                fe[0], fe[-1] = f0, f1
+                runs = [(int(off[fe[k]]), int(off[fe[k + 1]])) for k in range(self.world)]
+                if any(y <= x for x, y in runs):   # wildly uneven frames: a rank would have nothing to send
+                    plan = None
+                    break
+                plan.append((f0, f1, runs))
+        if plan is None:
+            if rows:
+                dq.copy_(src, non_blocking=True)   # small batch (a DOR step): every rank uploads it whole
+            parts = [(0, F)]
+            events = [None]
+        else:
+            parts = [(f0, f1) for f0, f1, _ in plan]
+            side = self._bufs.get("side_stream")
+            if side is None:
+                side = self._bufs["side_stream"] = torch.cuda.Stream()
+            side.wait_stream(main)
+            events = []
+            with torch.cuda.stream(side):
+                for f0, f1, runs in plan:
+                    a, b = runs[self.rank]
+                    dq[a:b].copy_(src[a:b], non_blocking=True)
+                    d.all_gather([dq[x:y] for x, y in runs], dq[a:b], group=self.group)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    events.append(ev)
+        counts = self._buf("counts_out", (F, self.n_images), torch.int32)
+        batches = []
+        for (f0, f1), ev in zip(parts, events):
+            if ev is not None:
+                main.wait_event(ev)
+            r0 = int(off[f0])
+            q = _lib.QueryBatch(self.local.ctx, self.local.kind,
+                                device=(off[f0:f1 + 1] - r0, dq.data_ptr() + r0 * row_elems * cat.dtype.itemsize, code, main.cuda_stream))
+            batches.append(q)
+            part = self.match_counts_device(q, mode=mode, ratio=ratio, d_mask=None if d_mask is None else d_mask[f0:f1],
+                                            fill_value=fill_value, algo=algo)
+            counts[f0:f1].copy_(part)
+        host = self._buf("counts_host", (F, self.n_images), torch.int32, pinned=True)
+        host.copy_(counts, non_blocking=True)
+        main.synchronize()
+        for q in batches:
+            q.validate()
+            q.close()
+        return host.numpy().copy()
 
 
 _pinned_cache = {}
@@ -192,13 +339,52 @@ class ShardedBow(object):
         if self.local is not None and hasattr(self.local, "close"):
             self.local.close()
 
+    def _on_device(self):
+        d = _dist()
+        return (self.world > 1 and d is not None and d.get_backend(self.group) == "nccl" and
+                (self.local is None or isinstance(self.local, _lib.BowIndex)))
+
     def score(self, q_descs):
-        """(n_queries, total_images) float32 on every rank: BOWMatch of every query against every location.
-        (Keeping the scores on the device for the all-gather was measured: no faster than this host hand-over at 2 GPUs.)"""
+        """(n_queries, total_images) float32 on every rank: BOWMatch of every query against every location.  With NCCL the
+        scores stay on the device: mcl_bow_score_device, one all-gather of the (zero-padded) column blocks, one D2H."""
         lo, hi = self.bounds[self.rank]
+        if self._on_device():
+            return self._score_nccl(q_descs)
         if self.local is None:
             local = np.zeros((len(q_descs), 0), dtype=np.float32)
         else:
             local = self.local.score(q_descs)[0]
         assert local.shape[1] == hi - lo
         return gather_columns(local, self.bounds, self.group)
+
+    def _score_nccl(self, q_descs):
+        import torch
+        d = _dist()
+        F = len(q_descs)
+        lo, hi = self.bounds[self.rank]
+        w = hi - lo
+        maxw = max(h - l for l, h in self.bounds)
+        key = (F, maxw)
+        if getattr(self, "_key", None) != key:
+            self._mine = torch.zeros((F, maxw), dtype=torch.float32, device="cuda")
+            self._tight = self._mine if w == maxw else torch.zeros((F, max(w, 1)), dtype=torch.float32, device="cuda")
+            self._all = torch.empty((self.world, F, maxw), dtype=torch.float32, device="cuda")
+            self._host = torch.empty((self.world, F, maxw), dtype=torch.float32).pin_memory()
+            self._key = key
+        stream = torch.cuda.current_stream()
+        q = None
+        if self.local is not None and w:
+            q = _lib.QueryBatch(self.local.ctx, _lib.BOWQ, q_descs)
+            self.local.score_device(q, self._tight.data_ptr(), stream=stream.cuda_stream)
+            if self._tight is not self._mine:
+                self._mine[:, :w].copy_(self._tight[:, :w])
+        d.all_gather_into_tensor(self._all, self._mine, group=self.group)
+        self._host.copy_(self._all, non_blocking=True)
+        stream.synchronize()
+        if q is not None:
+            q.close()
+        out = self._host.numpy()
+        full = np.empty((F, self.total_images), dtype=np.float32)
+        for r, (l, h) in enumerate(self.bounds):
+            full[:, l:h] = out[r][:, :h - l]
+        return full

@@ -157,7 +157,7 @@ def _draw_strip(rng, height, width, n_shapes):
 
 
 def make_dataset(root, seed=0, n_locations=7, n_images=25, n_frames=6, view=(160, 120),
-                 n_shapes=260, commands="lrfbs"):
+                 n_shapes=260, commands="lrfbs", angle_step=15):
     """Writes map/<l>/angleNNN.png, cam1_img/NNNN.png and commands.txt under `root`."""
     import cv2
     rng = np.random.default_rng(seed)
@@ -171,7 +171,7 @@ def make_dataset(root, seed=0, n_locations=7, n_images=25, n_frames=6, view=(160
         os.makedirs(d, exist_ok=True)
         for k in range(n_images):
             crop = strip[:, k * step:k * step + vw]
-            cv2.imwrite(os.path.join(d, "angle" + str(k * 15).zfill(3) + ".png"), crop)
+            cv2.imwrite(os.path.join(d, "angle" + str(k * angle_step).zfill(3) + ".png"), crop)
     os.makedirs(os.path.join(root, "cam1_img"), exist_ok=True)
     lines = []
     for f in range(n_frames):
@@ -188,3 +188,23 @@ def make_dataset(root, seed=0, n_locations=7, n_images=25, n_frames=6, view=(160
     with open(os.path.join(root, "commands.txt"), "w") as fh:
         fh.write("\n".join(lines) + "\n")
     return root
+
+
+def textured_views(seed, n_views=48, n_queries=12, view=(800, 600), shapes_per_view=600):
+    """Overlapping views of one richly textured synthetic panorama (map images) and re-observations of some of them with
+    pixel noise and a small shift (query frames), as BGR uint8 arrays.  cv2.SIFT finds 1-3 k keypoints per 800x600 view: the
+    image-level stand-in for the README's 800x600 case (no datasets ship with the reference)."""
+    rng = np.random.default_rng(seed)
+    vw, vh = view
+    step = vw // 3
+    width = step * n_views + vw
+    strip = _draw_strip(rng, vh, width, int(shapes_per_view * width / vw))
+    views = [np.ascontiguousarray(strip[:, k * step:k * step + vw]) for k in range(n_views)]
+    queries = []
+    for f in range(n_queries):
+        k = (5 * f + 2) % n_views
+        off = int(rng.integers(-step // 5, step // 5 + 1))
+        x0 = int(np.clip(k * step + off, 0, strip.shape[1] - vw))
+        crop = strip[:, x0:x0 + vw].astype(np.int16)
+        queries.append(np.clip(crop + rng.integers(-5, 6, size=crop.shape), 0, 255).astype(np.uint8))
+    return views, queries

@@ -12,7 +12,7 @@ local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
-root = os.path.join(tempfile.gettempdir(), "mcl_multi_gpu_ds")
+root = os.path.join(os.environ.get("MCL_MULTI_GPU_ROOT") or tempfile.gettempdir(), "mcl_multi_gpu_ds")
 if rank == 0:
     synth.make_dataset(root, seed=0, n_locations=7, n_images=25, n_frames=6, view=(160, 120))
 dist.barrier()
@@ -75,5 +75,52 @@ if rank == 0:
     a.writeProb(want, "rawP_single.txt", "w")
     ok = open("rawP.txt").read() == open("rawP_single.txt").read() and len(want) == 42
     print("MULTI_GPU_BOW_OK" if ok else "MULTI_GPU_BOW_MISMATCH")
+dist.barrier()
+
+# descriptor level, the sharded paths of engine.ShardedMap over NCCL against one GPU holding the whole map:
+#  (a) a big batch: every frame uploaded by ONE rank, rows all-gathered over NVLink, counts all-gathered on the device;
+#  (b) a small batch with a DOR mask: uploaded whole by every rank;  (c) resident queries (match_counts_device);  (d) ORB.
+from pymcl_b200.engine import ShardedMap
+ctx = _lib.default_context()
+rng = np.random.default_rng(3)
+map_des = [synth.sift_like(rng, int(n)) for n in rng.integers(300, 900, size=23)] + [None]
+frames = [synth.sift_like(rng, int(n)) for n in rng.integers(700, 1300, size=44)]
+for f in range(0, 44, 3):
+    src = map_des[(5 * f) % 23]
+    frames[f][:200] = synth.sift_noisy_copy(rng, src[:200], 4.0)
+assert sum(len(f) for f in frames) >= ShardedMap.SHARED_UPLOAD_MIN_ROWS
+sm = ShardedMap("SIFT", map_des, ctx=ctx)
+got_big = sm.match_counts(frames)
+mask = (rng.random((3, 24)) < 0.5).astype(np.uint8)
+got_small = sm.match_counts(frames[:3], mask=mask, fill_value=1)
+q = _lib.QueryBatch(ctx, "SIFT", frames[:9])
+got_dev = sm.match_counts_device(q).cpu().numpy()
+q.close()
+bad = sm.match_counts  # non-integer rows must be rejected on the sharded path too (checked on the device, reported after the step)
+try:
+    broken = [f.copy() for f in frames]
+    broken[17][3, 3] = 0.5
+    sm.match_counts(broken)
+    rejected = False
+except _lib.MclError:
+    rejected = True
+omap = [synth.orb_like(rng, int(n)) for n in rng.integers(100, 600, size=13)]
+oq = [synth.orb_like(rng, 500) for _ in range(5)]
+oq[1][:150] = synth.orb_flip(rng, omap[4][:150], 25)
+so = ShardedMap("ORB", omap, ctx=ctx)
+got_orb = [so.match_counts(oq, mode=m) for m in (_lib.KNN2_RATIO, _lib.CROSSCHECK)]
+if rank == 0:
+    whole = _lib.MapIndex(ctx, "SIFT", map_des)
+    want_big = whole.match_counts(frames)
+    ok = (np.array_equal(got_big, want_big) and got_big[0, 0] >= 150 and
+          np.array_equal(got_small, np.where(mask > 0, want_big[:3], 1)) and np.array_equal(got_dev, want_big[:9]) and rejected)
+    whole.close()
+    print("MULTI_GPU_SHARDED_UPLOAD_OK" if ok else "MULTI_GPU_SHARDED_UPLOAD_MISMATCH", "shards", sm.bounds)
+    wo = _lib.MapIndex(ctx, "ORB", omap)
+    ok = all(np.array_equal(g, wo.match_counts(oq, mode=m)) for g, m in zip(got_orb, (_lib.KNN2_RATIO, _lib.CROSSCHECK)))
+    wo.close()
+    print("MULTI_GPU_ORB_OK" if ok else "MULTI_GPU_ORB_MISMATCH")
+sm.close()
+so.close()
 dist.barrier()
 dist.destroy_process_group()

@@ -79,7 +79,7 @@ if "sift_cfg2" in names:   # cfg2: 200 frames x 256 rows vs 8 loc x 50 img x 256
     map_des, frames = synth.sift_map_and_frames(2, 400, 256, 200, 256)
     m = _lib.MapIndex(ctx, "SIFT", map_des)
     res = {}
-    for algo, tag in ((_lib.ALGO_TENSOR, "tc2"), (_lib.ALGO_TENSOR_V1, "tc1"), (_lib.ALGO_SIMT, "simt")):
+    for algo, tag in ((_lib.ALGO_TENSOR, "tc2"), (_lib.ALGO_SIMT, "simt")):
         e2e = timeit(lambda: m.match_counts(frames, algo=algo), reps=5, warm=2)
         res[tag + "_e2e_ms"] = e2e * 1e3
     k_ms = prof(lambda: m.match_counts(frames, algo=_lib.ALGO_TENSOR), "sift_tc", reps=5, warm=2)

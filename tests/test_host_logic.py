@@ -23,7 +23,10 @@ def test_angle_window_equals_reference_logic():
 def test_matcher_signature_and_positional_quirk():
     """Matcher(algorithm, index=None, width=800, height=600): positional ('SIFT', 320, 240) sets index=320, w=240."""
     sig = inspect.signature(Matcher.__init__)
-    assert list(sig.parameters) == ["self", "algorithm", "index", "width", "height"]
+    positional = [n for n, q in sig.parameters.items() if q.kind == q.POSITIONAL_OR_KEYWORD]
+    assert positional == ["self", "algorithm", "index", "width", "height"]      # the reference's signature, Matcher.py:41
+    keyword_only = {n: q.default for n, q in sig.parameters.items() if q.kind == q.KEYWORD_ONLY}
+    assert keyword_only == {"imagesPerLocation": 25, "angleStep": 15}           # the reference's constants as defaults
     m = Matcher("SIFT", 320, 240)
     assert (m.index, m.w, m.h, m.numWords) == (320, 240, 600, 10000)
     m = Matcher("ORB", width=320, height=240)
@@ -36,7 +39,9 @@ def test_matcher_signature_and_positional_quirk():
 def test_analyzer_signature():
     from pymcl_b200.analyze import analyzer
     sig = inspect.signature(analyzer.__init__)
-    assert list(sig.parameters)[:4] == ["self", "method", "width", "height"]
+    assert list(sig.parameters)[:5] == ["self", "method", "width", "height", "numLocations"]
+    assert sig.parameters["numLocations"].default == 7 and sig.parameters["imagesPerLocation"].default == 25
+    assert sig.parameters["angleStep"].default == 15 and sig.parameters["imagesPerLocation"].kind == inspect.Parameter.KEYWORD_ONLY
     for name in ("createIndex", "createRawP", "processRaw", "optP", "probUpdate", "prevWeight", "accountCommand",
                  "writeProb", "readProb", "readCommand", "readBestGuess", "Laplacian", "writeSidecar", "readSidecar"):
         assert callable(getattr(analyzer, name))
@@ -88,6 +93,18 @@ def test_sidecar_round_trips_what_readprob_parses(tmp_path, monkeypatch):
     assert np.load("rawP.npz")["counts"].shape == (4, 75)
     open("rawP.txt", "a").write("1\n[1.0]\n")
     assert a.readSidecar("rawP.txt") is None
+    # bag of words: every location owns its own number of images, so the probability lists are ragged
+    ragged = []
+    for f in range(2):
+        for n in (4, 9, 6):
+            v = rng.random(n).astype(np.float32)
+            ragged.append([np.float32(10) * v.max(), list(v)])
+    a.writeProb(ragged, "rawP.txt", "w")
+    a.writeSidecar(ragged, "rawP.txt")
+    got = a.readSidecar("rawP.txt")
+    assert [len(c[1]) for c in got["0001"]] == [4, 9, 6]
+    # (readProb's own parse of the same text, for the values)
+    assert got == a.readProb("rawP.txt")
 
 
 def test_large_batches_are_staged_without_changing_the_bytes():
@@ -312,16 +329,16 @@ class FakeContext:
         conv = {_lib.T_PY: float, _lib.T_F64: np.float64, _lib.T_F32: np.float32}
         return [[conv[int(t0)](row[0]), [conv[int(t1)](v) for v in row[1:]]] for row, (t0, t1) in zip(values, tags)]
 
-    def filter_step(self, stages, cmd, blur, prev, cur):
+    def filter_step(self, stages, cmd, blur, prev, cur, angle_step=15):
         assert stages == _lib.F_ALL
         z = np.zeros((len(prev), 2), np.int8)
-        p2, out, _, best = self.filter_step_typed(stages, cmd, blur, _lib.T_PY, prev, z, cur, z)
+        p2, out, _, best = self.filter_step_typed(stages, cmd, blur, _lib.T_PY, prev, z, cur, z, angle_step=angle_step)
         return p2, out, best
 
-    def filter_step_typed(self, stages, cmd, blur, blur_type, prev, prev_type, cur, cur_type):
+    def filter_step_typed(self, stages, cmd, blur, blur_type, prev, prev_type, cur, cur_type, angle_step=15):
         assert stages == _lib.F_ALL
         p, c = self._lists(prev, prev_type), self._lists(cur, cur_type)
-        adj, best = oracle.filter_step(cmd, p, c, np.float64(blur) if blur_type == _lib.T_F64 else float(blur))
+        adj, best = oracle.filter_step(cmd, p, c, np.float64(blur) if blur_type == _lib.T_F64 else float(blur), angle_step)
         tag = lambda x: _lib.T_F32 if isinstance(x, np.float32) else (_lib.T_F64 if isinstance(x, np.float64) else _lib.T_PY)
         pack = lambda rows: np.array([[r[0]] + list(r[1]) for r in rows], dtype=np.float64)
         return pack(p), pack(adj), np.array([[tag(r[0]), tag(r[1][0])] for r in adj], np.int8), tuple(best)
@@ -419,3 +436,37 @@ def test_analyzer_orb_driver_on_a_fake_context(tmp_path, monkeypatch, golden_dir
     a.orb_mode = mode
     a.createRawP()
     assert open("rawP.txt").read() == open(os.path.join(golden_dir, tag + "_rawP.txt")).read()
+
+
+def test_analyzer_generic_map_shape_on_a_fake_context(tmp_path, monkeypatch):
+    """Keyword-only generalisations of the reference's hard-coded 7 locations x 25 images x 15 degrees (analyze.py:35,107,
+    Matcher.py:309): 3 locations x 10 images x 36 degrees, frames matched in chunks of 3 -- createRawP / processRaw / optP
+    against the oracle pipeline with the same shape (BASELINE configs 2, 3 and 5 are such generalisations)."""
+    import glob
+    import pipeline
+    from pymcl_b200.analyze import analyzer
+    root = str(tmp_path / "ds")
+    synth.make_dataset(root, seed=3, n_locations=3, n_images=10, n_frames=5, view=(160, 120), angle_step=36)
+    monkeypatch.chdir(root)
+    orig = glob.glob
+    monkeypatch.setattr(glob, "glob", lambda *a, **k: sorted(orig(*a, **k)))
+    monkeypatch.setattr(_lib, "default_context", lambda: FakeContext())
+    monkeypatch.setattr(_lib, "MapIndex", OracleMap)
+    shape = dict(n_locations=3, n_images=10, step=36)
+    a = analyzer("ORB", 160, 120, numLocations=3, imagesPerLocation=10, angleStep=36, framesPerCall=3)
+    a.createRawP()
+    oracle.write_prob(pipeline.create_raw_p(root, "ORB", 160, 120, **shape), "want_rawP.txt")
+    assert open("rawP.txt").read() == open("want_rawP.txt").read()
+    assert len(a.rawP) == 5 * 3 and all(len(c[1]) == 10 for c in a.rawP)
+    a.processRaw()
+    blur_p, best = pipeline.process_raw(root, "rawP.txt", **shape)
+    oracle.write_prob(blur_p, "want_out.txt")
+    assert open("out.txt").read() == open("want_out.txt").read() and a.bestGuess == best
+    b = analyzer("ORB", 160, 120, numLocations=3, imagesPerLocation=10, angleStep=36)
+    b.optP()
+    blur_p, best = pipeline.opt_p(root, "ORB", 160, 120, **shape)
+    oracle.write_prob(blur_p, "want_dor.txt")
+    assert open("out.txt").read() == open("want_dor.txt").read() and b.bestGuess == best
+    m = Matcher("ORB", width=160, height=120, imagesPerLocation=10, angleStep=36)
+    m.setDirectory("map/1")
+    assert m._angle_paths() == ["map/1/angle%03d.png" % (36 * k) for k in range(10)]

@@ -192,7 +192,35 @@ def test_laplacian_restatement_equals_cv2():
         lap = cv2.Laplacian(img, cv2.CV_64F)
         s1, s2, n = oracle.laplacian_sums(img)
         assert s1 == int(lap.sum()) and s2 == int((lap * lap).sum()) and n == img.size
-        assert abs(oracle.laplacian_var(img) - lap.var()) <= 1e-9 * max(1.0, lap.var())
+        assert np.array_equal(oracle.laplacian_int(img), lap.astype(np.int64))
+        assert oracle.laplacian_var(img) == lap.var()
+        assert abs(oracle.laplacian_var_from_sums(img) - lap.var()) <= 1e-9 * max(1.0, lap.var())
+
+
+def test_laplacian_var_is_bit_identical_to_numpy_two_pass_variance():
+    """The reference's blur weight is cv2.Laplacian(img, CV_64F).var() (analyze.py:441-445) and, below 200, enters every number
+    of out.txt (analyze.py:245-248): the restatement must reproduce ndarray.var() bit for bit -- numpy's two-pass variance with
+    pairwise summation -- not merely to 1e-9.  Blurred images are the ones that matter (their variance is below 200) and the
+    ones on which the one-pass integer formula differs from numpy in the last bits."""
+    import cv2
+    rng = np.random.default_rng(11)
+    differs_from_one_pass = 0
+    cases = 0
+    for shape in [(600, 800), (240, 320), (120, 160), (481, 641), (33, 129), (600, 801), (9, 7), (3, 5), (1, 1), (130, 1)]:
+        for k in range(5):
+            img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+            if k and min(shape) > 4:
+                img = cv2.GaussianBlur(img, (0, 0), 0.6 * k + 0.5)
+            ref = cv2.Laplacian(np.ascontiguousarray(img), cv2.CV_64F).var()
+            got = oracle.laplacian_var(img)
+            assert isinstance(got, np.float64) and got == ref, (shape, k, got, ref)
+            differs_from_one_pass += int(oracle.laplacian_var_from_sums(img) != ref)
+            cases += 1
+    assert differs_from_one_pass > 0, "the one-pass formula happened to agree everywhere: the test images do not discriminate"
+    x = rng.random(100003)
+    assert oracle.pairwise_sum_f64(x) == np.add.reduce(x)
+    for n in (0, 1, 7, 8, 9, 127, 128, 129, 255, 1000, 4097):
+        assert oracle.pairwise_sum_f64(x[:n]) == np.add.reduce(x[:n]), n
 
 
 def test_bow_restatement_equals_scipy_sklearn():
@@ -257,3 +285,32 @@ def test_run_from_counts_and_text_roundtrip(tmp_path):
     oracle.write_prob(p, f)
     back = oracle.read_prob(f)
     assert back["0000"][0][0] == 8.0 and back["0000"][6][1][:4] == probs
+
+
+def test_oracle_pipeline_reproduces_the_reference_at_800x600(tmp_path, golden_dir):
+    """The README's image size (README.md:44): 7 x 25 textured 800x600 views with 1-3 k SIFT descriptors each, 4 frames.
+    tests/golden/sift800_* was written by the UNMODIFIED reference (oracle/make_golden.py --big, exact search); the oracle
+    pipeline must reproduce its rawP.txt byte for byte and its per-image SIFTMatch counts."""
+    import cv2
+    g = np.load(os.path.join(golden_dir, "sift800_case.npz"))
+    if str(g["cv2"]) != cv2.__version__:
+        pytest.skip("different OpenCV build than the golden run")
+    root = str(tmp_path / "ds800")
+    synth.make_dataset(root, seed=8, n_locations=7, n_images=25, n_frames=4, view=(800, 600), n_shapes=5600)
+    from concurrent.futures import ThreadPoolExecutor
+    paths = [p for loc in range(7) for p in pipeline.angle_paths(root, loc)]
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as pool:
+        mdes = list(pool.map(lambda p: cv2.SIFT_create().detectAndCompute(cv2.imread(p), None)[1], paths))
+        qdes = list(pool.map(lambda p: pipeline.query_descriptors(p, "SIFT", 800, 600), pipeline.frame_paths(root)))
+    assert np.array_equal([len(d) for d in mdes], g["n_desc"]) and np.array_equal([len(d) for d in qdes], g["n_query_desc"])
+    p = []
+    for f, q in enumerate(qdes):
+        for loc in range(7):
+            counts = [oracle.sift_pair_count(q, m) for m in mdes[loc * 25:(loc + 1) * 25]]
+            if loc == 0:
+                assert counts == g["counts"][f].tolist()
+            total, probs = oracle.run_from_counts(counts)
+            p.append([total, probs])
+    out = str(tmp_path / "rawP.txt")
+    oracle.write_prob(p, out)
+    assert open(out).read() == open(os.path.join(golden_dir, "sift800_rawP.txt")).read()
