@@ -71,7 +71,8 @@ int mcl_set_option(mcl_ctx* ctx, int option, int value);
 int64_t mcl_launch_count(mcl_ctx* ctx);
 /* per-kernel device timing with CUDA events on the launching stream.  which: 0 = SIFT tensor-core kernel,
  * 1 = SIFT fix-up, 2 = ORB, 3 = SURF, 4 = BOW vq, 5 = BOW score, 6 = Laplacian, 7 = ingest (prep),
- * 8 = SIFT SIMT (dp4a) kernel, 9 = BOW vq tensor-core kernel, 10 = BOW float32 resolve kernel, 11 = chi-squared kernel.
+ * 8 = SIFT SIMT (dp4a) kernel, 9 = BOW vq tensor-core kernel, 10 = BOW float32 resolve kernels, 11 = chi-squared kernel,
+ * 12 = ORB exact fix-up / repair kernels (slot 2 = the ORB tensor-core or SIMT matching kernel).
  * mcl_profile_read synchronises, returns accumulated milliseconds and launch count, and resets them. */
 int mcl_profile_enable(mcl_ctx* ctx, int on);
 int mcl_profile_read(mcl_ctx* ctx, int which, double* ms, int64_t* launches);

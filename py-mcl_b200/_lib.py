@@ -23,7 +23,7 @@ T_PY, T_F64, T_F32 = 0, 1, 2
 KIND_BY_NAME = {"SIFT": SIFT, "ORB": ORB, "SURF": SURF}
 ROW_DIM = {SIFT: 128, ORB: 32, SURF: 64, BOWQ: 128}
 PROFILE_SLOTS = {"sift_tc": 0, "sift_fixup": 1, "orb": 2, "surf": 3, "bow_vq": 4, "bow_score": 5, "laplacian": 6,
-                 "ingest": 7, "sift_simt": 8, "bow_vq_tc": 9, "bow_resolve": 10, "chi2": 11}
+                 "ingest": 7, "sift_simt": 8, "bow_vq_tc": 9, "bow_resolve": 10, "chi2": 11, "orb_fixup": 12}
 
 
 class MclError(RuntimeError):

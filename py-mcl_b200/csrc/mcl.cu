@@ -22,6 +22,7 @@
 #include "simt_match.cuh"
 #include "bow_lap_filter.cuh"
 #include "lap_var.cuh"
+#include "tc9.cuh"
 #include "bow_tc.cuh"
 #include "kmeans.cuh"
 #include "color.cuh"
@@ -48,7 +49,7 @@ int fail(int code, const char* fmt, ...) {
             return fail(MCL_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-enum { PROF_SIFT_TC = 0, PROF_SIFT_FIX, PROF_ORB, PROF_SURF, PROF_VQ, PROF_SCORE, PROF_LAP, PROF_PREP, PROF_SIFT_SIMT, PROF_VQ_TC, PROF_VQ_RESOLVE, PROF_CHI2, PROF_N };
+enum { PROF_SIFT_TC = 0, PROF_SIFT_FIX, PROF_ORB, PROF_SURF, PROF_VQ, PROF_SCORE, PROF_LAP, PROF_PREP, PROF_SIFT_SIMT, PROF_VQ_TC, PROF_VQ_RESOLVE, PROF_CHI2, PROF_ORB_FIX, PROF_N };
 constexpr int QROW_PAD = 384;  // sift_tc4's query block
 
 // growable device scratch buffer (never shrinks; avoids cudaMalloc on the per-frame path)
@@ -95,13 +96,13 @@ struct mcl_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[PROF_N];
     // scratch
     DevBuf stage, cand, dirty, flags /* ints: [0]=cand_count [1]=overflow [2]=bad [3]=rescans [6]=bow bad [8..10]=bow state; bytes 64..: statistics */, row_arg, bow_best, lap_pix, lap_meta, filt, tmp_counts,
-        tmp_mask, tmp_words, tmp_scores, chi2, tq_off, tq_desc, tq_norm, tq_frame, bow_q8, bow_qaux, bow_tc_out;
-    bool bowtc_attr = false;
+        tmp_mask, tmp_words, tmp_scores, chi2, tq_off, tq_desc, tq_norm, tq_frame, bow_q8, bow_qaux, bow_tc_out, bow_sort, orb_q;
+    bool tc9_attr = false;
+    int tc9_clusters[2] = {0, 0};   // co-resident tc9 CTA pairs (ORB, BOW)
     size_t cand_cap_entries = 0;
     bool tc4_attr = false;
     int opt[8] = {0};  // mcl_set_option: [0] = sift_tc4 diagnostic mode
     int max_clusters2 = 0;          // co-resident sift_tc4 clusters of 2 CTAs
-    int bow_max_clusters = 0;       // co-resident bow_vq_tc clusters of 2 CTAs
     int bow_score_smem = 0;         // dynamic shared memory opt-in of bow_score_kernel so far
     std::map<int64_t, LapPlan> lap_plans;   // by pixel count
     // free list of device blocks for the query batches of mcl_queries_create_device: the per-step batches of the multi-GPU
@@ -147,6 +148,11 @@ struct mcl_map {
     std::vector<ChunkSet> chunk_sets;
     mcl::sifttc3::TileMeta* d_meta3 = nullptr;   // per 64-row unit: image ids, descriptor counts, norm brackets
     int n_units = 0;                             // 64-row units
+    // ORB on the tensor cores (tc9.cuh): +-1 byte tiles, the packed rows in padded order, tile records, rows per image
+    uint8_t* d_tiles9 = nullptr;
+    uint8_t* d_packed9 = nullptr;
+    mcl::tc9::TileRec* d_rec9 = nullptr;
+    int32_t* d_seg_rows = nullptr;
     int max_rows_per_image = 0;
 };
 
@@ -156,10 +162,14 @@ struct mcl_bow {
     int64_t total_images = 0, voc_rows = 0;
     int max_words = 0;
     std::vector<int64_t> h_voc_off, h_img_off;
-    // tensor-core word assignment (bow_tc.cuh): codebook planes per 128-word tile
+    // tensor-core word assignment (tc9.cuh, KIND_BOW): fp16 code-book tiles with the norm extension, per 128 words
     std::vector<int32_t> h_tile_off;
     int32_t* d_tile_off = nullptr;
     uint8_t* d_tiles = nullptr;
+    mcl::tc9::TileRec* d_rec = nullptr;
+    float* d_key_c = nullptr;
+    struct Split { int n_splits = 0, n_chunks = 0; mcl::sifttc3::Chunk* d = nullptr; };
+    std::vector<Split> splits;   // chunk tables: every location's tiles cut into 1, 2, 4, 8 ranges
     bool tc_ok = false;
     float* d_voc = nullptr;
     float* d_idf = nullptr;
@@ -306,7 +316,8 @@ void build_chunks(const mcl_map* m, int TILE_N, int target_tiles, std::vector<mc
     }
 }
 
-const mcl_map::ChunkSet* pick_chunks(const std::vector<mcl_map::ChunkSet>& sets, int n_qblocks, int sm_count, int64_t total_tiles) {
+const mcl_map::ChunkSet* pick_chunks(const std::vector<mcl_map::ChunkSet>& sets, int n_qblocks, int sm_count, int64_t total_tiles,
+                                     double refill = 2.5) {
     // every work item pays a pipeline refill (the query tiles in tensor memory are single buffered: ~2.5 tile times), and
     // the last round of items is only partly filled: take the set with the smallest estimated makespan
     const mcl_map::ChunkSet* best = &sets.front();
@@ -315,7 +326,7 @@ const mcl_map::ChunkSet* pick_chunks(const std::vector<mcl_map::ChunkSet>& sets,
         if (cs.n == 0) continue;
         const int64_t items = (int64_t)cs.n * n_qblocks;
         const int64_t rounds = (items + sm_count - 1) / sm_count;
-        const double cost = (double)rounds * ((double)total_tiles / cs.n + 2.5);
+        const double cost = (double)rounds * ((double)total_tiles / cs.n + refill);
         if (cost < best_cost) { best_cost = cost; best = &cs; }
     }
     return best;
@@ -365,7 +376,7 @@ extern "C" void mcl_shutdown(mcl_ctx* c) {
         for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     DevBuf* bufs[] = {&c->stage, &c->cand, &c->dirty, &c->flags, &c->row_arg, &c->bow_best, &c->lap_pix, &c->lap_meta, &c->filt,
                       &c->tmp_counts, &c->tmp_mask, &c->tmp_words, &c->tmp_scores, &c->tq_off, &c->tq_desc, &c->tq_norm,
-                      &c->tq_frame, &c->bow_q8, &c->bow_qaux, &c->bow_tc_out};
+                      &c->tq_frame, &c->bow_q8, &c->bow_qaux, &c->bow_tc_out, &c->bow_sort, &c->orb_q};
     for (DevBuf* b : bufs) b->release();
     for (auto& kv : c->lap_plans) cudaFree(kv.second.d_tab);
     for (auto& b : c->pool) cudaFree(b.first);
@@ -478,6 +489,10 @@ extern "C" void mcl_map_destroy(mcl_map* m) {
     cudaFree(m->d_img_of);
     for (auto& cs : m->chunk_sets) cudaFree(cs.d);
     cudaFree(m->d_meta3);
+    cudaFree(m->d_tiles9);
+    cudaFree(m->d_packed9);
+    cudaFree(m->d_rec9);
+    cudaFree(m->d_seg_rows);
     delete m;
 }
 
@@ -599,6 +614,58 @@ extern "C" int mcl_map_create(mcl_ctx* c, int kind, int n_images, const int64_t*
         MCU(cudaMalloc(&m->d_desc, std::max<size_t>((size_t)rows * rb, 256)));
         if (rows) MCU(cudaMemcpyAsync(m->d_desc, desc, (size_t)rows * rb, cudaMemcpyHostToDevice, st));
         m->resident_bytes = (size_t)rows * rb;
+        if (kind == MCL_ORB) {
+            // tensor-core copy: every image padded to whole 32-row groups, the map to whole 128-row tiles of 256 signed bytes
+            using namespace mcl::tc9;
+            m->h_dst_off.resize(n_images + 1);
+            int64_t acc = 0;
+            std::vector<int32_t> seg_rows((size_t)std::max(1, n_images));
+            for (int i = 0; i < n_images; ++i) {
+                m->h_dst_off[i] = acc;
+                const int64_t r = row_offsets[i + 1] - row_offsets[i];
+                seg_rows[i] = (int32_t)r;
+                acc += (r + GROUP - 1) / GROUP * GROUP;
+            }
+            m->h_dst_off[n_images] = acc;
+            m->padded_rows = std::max<int64_t>(TILE_N, (acc + TILE_N - 1) / TILE_N * TILE_N);
+            m->n_tiles = (int)(m->padded_rows / TILE_N);
+            MCU(cudaMalloc(&m->d_dst_off, (size_t)(n_images + 1) * 8));
+            MCU(cudaMemcpyAsync(m->d_dst_off, m->h_dst_off.data(), (size_t)(n_images + 1) * 8, cudaMemcpyHostToDevice, st));
+            MCU(cudaMalloc(&m->d_seg_rows, seg_rows.size() * 4));
+            MCU(cudaMemcpyAsync(m->d_seg_rows, seg_rows.data(), seg_rows.size() * 4, cudaMemcpyHostToDevice, st));
+            MCU(cudaMalloc(&m->d_tiles9, (size_t)m->n_tiles * Shape<KIND_ORB>::TILE_BYTES));
+            MCU(cudaMalloc(&m->d_packed9, (size_t)m->padded_rows * 32));
+            MCU(cudaMalloc(&m->d_img_of, (size_t)m->padded_rows * 4));
+            MCU(cudaMalloc(&m->d_rec9, (size_t)m->n_tiles * sizeof(TileRec)));
+            MCU(cudaMemsetAsync(m->d_tiles9, 0, (size_t)m->n_tiles * Shape<KIND_ORB>::TILE_BYTES, st));
+            MCU(cudaMemsetAsync(m->d_packed9, 0, (size_t)m->padded_rows * 32, st));
+            MCU(cudaMemsetAsync(m->d_img_of, 0xFF, (size_t)m->padded_rows * 4, st));
+            {
+                ProfScope ps(c, PROF_PREP, st);
+                if (rows) orb_map_prep_kernel<<<grid_for(rows * 32, 256, c->sm_count * 8), 256, 0, st>>>(
+                    (const uint8_t*)m->d_desc, rows, m->d_src_off, m->d_dst_off, n_images, m->d_tiles9, m->d_packed9, m->d_img_of);
+                orb_build_rec_kernel<<<(m->n_tiles + 127) / 128, 128, 0, st>>>(m->d_img_of, m->d_src_off, m->d_dst_off, m->n_tiles, m->d_rec9);
+            }
+            MCU(cudaGetLastError());
+            std::vector<mcl::sifttc3::Chunk> ch;
+            int last_n = -1;
+            for (int target : {512, 128, 32, 8, 4, 2, 1}) {
+                build_chunks(m, TILE_N, target, ch);
+                if ((int)ch.size() == last_n) continue;
+                last_n = (int)ch.size();
+                mcl_map::ChunkSet cs;
+                cs.target = target;
+                cs.n = (int)ch.size();
+                if (cs.n) {
+                    MCU(cudaMalloc(&cs.d, ch.size() * sizeof(mcl::sifttc3::Chunk)));
+                    m->chunk_sets.push_back(cs);
+                    MCU(cudaMemcpy(cs.d, ch.data(), ch.size() * sizeof(mcl::sifttc3::Chunk), cudaMemcpyHostToDevice));
+                } else {
+                    m->chunk_sets.push_back(cs);
+                }
+            }
+            m->resident_bytes += (size_t)m->n_tiles * Shape<KIND_ORB>::TILE_BYTES + (size_t)m->padded_rows * 36;
+        }
     }
     MCU(cudaStreamSynchronize(st));
 #undef MCU
@@ -798,6 +865,21 @@ int max_active_clusters(K kernel, int sm_count, int threads, size_t smem, int cl
     return n;
 }
 
+// one-time attributes + co-residency of the tc9 kernels
+int tc9_prepare(mcl_ctx* c) {
+    using namespace mcl::tc9;
+    if (c->tc9_attr) return MCL_OK;
+    CU(cudaFuncSetAttribute(tc9_kernel<KIND_ORB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<KIND_ORB>)));
+    CU(cudaFuncSetAttribute(tc9_kernel<KIND_ORB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<KIND_ORB>)));
+    CU(cudaFuncSetAttribute(tc9_kernel<KIND_BOW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<KIND_BOW>)));
+    CU(cudaFuncSetAttribute(tc9_kernel<KIND_BOW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<KIND_BOW>)));
+    c->tc9_clusters[0] = max_active_clusters(tc9_kernel<KIND_ORB, 2>, c->sm_count, THREADS, sizeof(Smem<KIND_ORB>), 2);
+    c->tc9_clusters[1] = max_active_clusters(tc9_kernel<KIND_BOW, 2>, c->sm_count, THREADS, sizeof(Smem<KIND_BOW>), 2);
+    if (getenv("MCL_DEBUG")) fprintf(stderr, "[mcl] co-resident tc9 CTA pairs: ORB %d, BOW %d\n", c->tc9_clusters[0], c->tc9_clusters[1]);
+    c->tc9_attr = true;
+    return MCL_OK;
+}
+
 // SIFT on the tensor cores: sift_tc4_kernel (bracketed pre-filter, candidates) + sift_fixup3_kernel (exact resolution) per
 // batch of query blocks, then the exact SIMT kernel on the (frame, image) pairs that lost a candidate to a full list.
 int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, cudaStream_t st) {
@@ -915,6 +997,101 @@ int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
     return MCL_OK;
 }
 
+// ORB 2-NN + ratio on the tensor cores: tc9_kernel<KIND_ORB> (exact best key, lower bound of the second) + orb_fixup_kernel
+// (xor + popc on the best group) per batch of query blocks, then the SIMT kernel on the (frame, image) pairs that lost a
+// candidate to a full list.
+int launch_orb_tc(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, cudaStream_t st) {
+    using namespace mcl::tc9;
+    mcl_ctx* c = m->ctx;
+    int rc = tc9_prepare(c);
+    if (rc) return rc;
+    const int n_qblocks_total = (int)((q->rows + QBLK - 1) / QBLK);
+    const int64_t padded = (int64_t)n_qblocks_total * QBLK;
+    CU(c->orb_q.ensure((size_t)padded * (256 + 8)));
+    uint8_t* q_rows = c->orb_q.as<uint8_t>();
+    int32_t* q_aux = reinterpret_cast<int32_t*>(q_rows + (size_t)padded * 256);
+    int32_t* q_frame = q_aux + padded;
+    CU(cudaMemsetAsync(q_rows, 0, (size_t)padded * 256, st));
+    CU(cudaMemsetAsync(q_aux, 0xFF, (size_t)padded * 8, st));
+    {
+        ProfScope ps(c, PROF_PREP, st);
+        orb_query_prep_kernel<<<grid_for(q->rows * 32, 256, c->sm_count * 8), 256, 0, st>>>((const uint8_t*)q->d_desc, q->rows, q->d_off,
+                                                                                         q->n_queries, q_rows, q_aux, q_frame);
+    }
+    CU(cudaGetLastError());
+    const int64_t pairs_total = padded * (int64_t)std::max(1, m->n_images);
+    const int64_t want = std::min<int64_t>(std::max<int64_t>(pairs_total / 4, 1 << 16), (int64_t)48 << 20);
+    if ((size_t)want > c->cand_cap_entries) {
+        CU(c->cand.ensure((size_t)want * sizeof(int4)));
+        c->cand_cap_entries = (size_t)want;
+    }
+    const int64_t cap = c->opt[3] > 0 ? std::min<int64_t>(c->opt[3], (int64_t)c->cand_cap_entries) : (int64_t)c->cand_cap_entries;
+    int batch_qblocks = (int)std::max<int64_t>(1, cap * 4 / ((int64_t)std::max(1, m->n_images) * QBLK));
+    batch_qblocks = std::min(batch_qblocks, n_qblocks_total);
+    unsigned int* d_cand_count = c->flags.as<unsigned int>();
+    int* d_overflow = c->flags.as<int>() + 1;
+    unsigned long long* d_stats = c->flags.as<unsigned long long>() + 8;
+    const size_t n_pairs = (size_t)std::max(1, q->n_queries) * std::max(1, m->n_images);
+    CU(c->dirty.ensure(n_pairs));
+    CU(cudaMemsetAsync(c->dirty.p, 0, n_pairs, st));
+    CU(cudaMemsetAsync(d_overflow, 0, 4, st));
+    for (int qb0 = 0; qb0 < n_qblocks_total; qb0 += batch_qblocks) {
+        const int nqb = std::min(batch_qblocks, n_qblocks_total - qb0);
+        const mcl_map::ChunkSet* cs = pick_chunks(m->chunk_sets, nqb, c->sm_count, m->n_tiles, 1.5);
+        if (cs->n == 0) break;
+        CU(cudaMemsetAsync(d_cand_count, 0, 4, st));
+        Params p = {};
+        p.q_rows = q_rows + (size_t)qb0 * QBLK * 256;
+        p.q_aux = q_aux + (size_t)qb0 * QBLK;
+        p.q_frame = q_frame + (size_t)qb0 * QBLK;
+        p.m_tiles = m->d_tiles9;
+        p.m_rec = m->d_rec9;
+        p.chunks = cs->d;
+        p.seg_rows = m->d_seg_rows;
+        p.n_qblocks = nqb;
+        p.n_chunks = cs->n;
+        p.ratio = ratio;
+        p.cand = c->cand.as<int4>();
+        p.cand_count = d_cand_count;
+        p.cand_cap = (unsigned)cap;
+        p.overflow = d_overflow;
+        p.dirty = c->dirty.as<uint8_t>();
+        p.n_images = m->n_images;
+        p.q_row_base = qb0 * QBLK;
+        p.meta_cap = c->opt[1] == 1 ? 0 : META_CAP;
+        int cl = 1;
+        if (c->opt[5] == 2 || (c->opt[5] == 0 && ((nqb % 2 == 0 && nqb >= 2) || nqb >= 32))) cl = 2;
+        if (cl == 2 && c->tc9_clusters[0] < 1) cl = 1;
+        const int64_t n_items = (int64_t)((nqb + cl - 1) / cl) * cs->n;
+        {
+            ProfScope ps(c, PROF_ORB, st);
+            constexpr size_t smem = sizeof(Smem<KIND_ORB>);
+            if (cl == 2) CU(launch_cluster(tc9_kernel<KIND_ORB, 2>, 2 * (int)std::min<int64_t>(n_items, c->tc9_clusters[0]), THREADS, smem, st, 2, p));
+            else tc9_kernel<KIND_ORB, 1><<<(int)std::min<int64_t>(n_items, c->sm_count), THREADS, smem, st>>>(p);
+        }
+        CU(cudaGetLastError());
+        {
+            ProfScope ps(c, PROF_ORB_FIX, st);
+            orb_fixup_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->cand.as<int4>(), d_cand_count, (unsigned)cap, (const uint4*)q->d_desc,
+                                                             q_frame, (const uint4*)m->d_packed9, m->d_src_off, m->d_dst_off, ratio,
+                                                             m->n_images, d_counts, d_stats + 2);
+        }
+        CU(cudaGetLastError());
+    }
+    {   // exact repair of the dirty (frame, image) pairs, if any: their counts are reset and recomputed by the SIMT kernel
+        ProfScope ps(c, PROF_ORB_FIX, st);
+        zero_where_mask_kernel<<<grid_for((int64_t)n_pairs, 256, c->sm_count * 4), 256, 0, st>>>(d_counts, c->dirty.as<uint8_t>(), (int64_t)n_pairs, d_overflow);
+        int64_t max_q = 0;
+        for (int f = 0; f < q->n_queries; ++f) max_q = std::max(max_q, q->h_off[f + 1] - q->h_off[f]);
+        dim3 grid(std::max(1, m->n_images), std::max(1, q->n_queries), (unsigned)std::max<int64_t>(1, (max_q + 127) / 128));
+        mcl::orb_knn_kernel<<<grid, 128, 0, st>>>((const uint4*)q->d_desc, q->d_off, (const uint4*)m->d_desc, m->d_src_off, m->n_images,
+                                                  ratio, c->dirty.as<uint8_t>(), d_counts, d_overflow, d_stats + 1);
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    return MCL_OK;
+}
+
 int match_device(mcl_map* m, mcl_queries* q, int mode, double ratio, const uint8_t* d_mask, int32_t fill, int algo,
                  int32_t* d_counts, cudaStream_t st) {
     mcl_ctx* c = m->ctx;
@@ -957,10 +1134,16 @@ int match_device(mcl_map* m, mcl_queries* q, int mode, double ratio, const uint8
             if (zq > 65535 || ni > 2147483647) return fail(MCL_EINVAL, "query frame too large");
             dim3 grid(ni, nf, zq);
             if (m->kind == MCL_ORB) {
-                if (mode == MCL_KNN2_RATIO) {
+                // 2-NN + ratio: the tensor cores unless the call is small or DOR-masked (the SIMT kernel skips masked pairs)
+                const bool tensor = mode == MCL_KNN2_RATIO &&
+                                    (algo == MCL_ALGO_TENSOR || (algo == MCL_ALGO_AUTO && !d_mask && (double)q->rows * (double)m->rows >= 2.0e6));
+                if (tensor) {
+                    int rc = launch_orb_tc(m, q, ratio, d_counts, st);
+                    if (rc) return rc;
+                } else if (mode == MCL_KNN2_RATIO) {
                     ProfScope ps(c, PROF_ORB, st);
                     mcl::orb_knn_kernel<<<grid, bt, 0, st>>>((const uint4*)q->d_desc, q->d_off, (const uint4*)m->d_desc,
-                                                              m->d_src_off, ni, ratio, d_mask, d_counts);
+                                                              m->d_src_off, ni, ratio, d_mask, d_counts, nullptr, nullptr);
                 } else if (mode == MCL_CROSSCHECK) {
                     CU(c->row_arg.ensure((size_t)q->rows * ni * 4));
                     {
@@ -1175,6 +1358,73 @@ extern "C" int mcl_match_counts(mcl_map* m, int n_queries, const int64_t* q_row_
 // ================================================================================================
 // bag of words
 // ================================================================================================
+namespace {
+void bow_free_tc(mcl_bow* b) {
+    cudaFree(b->d_tile_off);
+    cudaFree(b->d_tiles);
+    cudaFree(b->d_rec);
+    cudaFree(b->d_key_c);
+    for (auto& sp : b->splits) cudaFree(sp.d);
+    b->d_tile_off = nullptr; b->d_tiles = nullptr; b->d_rec = nullptr; b->d_key_c = nullptr;
+    b->splits.clear();
+    b->tc_ok = false;
+}
+
+// (re)builds the tensor-core structures of an index from its float32 code book (d_voc, d_voc_off, h_voc_off, n_loc)
+int bow_build_tc(mcl_bow* b, cudaStream_t st) {
+    using namespace mcl::tc9;
+    mcl_ctx* c = b->ctx;
+    bow_free_tc(b);
+    const int L = b->n_loc;
+    b->h_tile_off.resize(L + 1);
+    int32_t acc = 0;
+    for (int l = 0; l < L; ++l) {
+        b->h_tile_off[l] = acc;
+        acc += (int32_t)((b->h_voc_off[l + 1] - b->h_voc_off[l] + TILE_N - 1) / TILE_N);
+    }
+    b->h_tile_off[L] = acc;
+    CU(cudaMalloc(&b->d_tile_off, (size_t)(L + 1) * 4));
+    CU(cudaMemcpyAsync(b->d_tile_off, b->h_tile_off.data(), (size_t)(L + 1) * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMalloc(&b->d_tiles, std::max<size_t>((size_t)acc * Shape<KIND_BOW>::TILE_BYTES, 256)));
+    CU(cudaMalloc(&b->d_rec, std::max<size_t>((size_t)acc * sizeof(TileRec), 256)));
+    CU(cudaMalloc(&b->d_key_c, (size_t)L * 4));
+    int* bad = c->flags.as<int>() + 6;
+    CU(cudaMemsetAsync(bad, 0, 4, st));
+    {
+        ProfScope ps(c, PROF_PREP, st);
+        bow_key_c_kernel<<<L, 256, 0, st>>>(b->d_voc, b->d_voc_off, b->d_key_c);
+        bow_build_tiles_kernel<<<acc, 256, 0, st>>>(b->d_voc, b->d_voc_off, L, b->d_tile_off, b->d_key_c, b->d_tiles, b->d_rec, bad);
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    for (int ns : {1, 2, 4, 8}) {
+        std::vector<mcl::sifttc3::Chunk> ch;
+        for (int sp = 0; sp < ns; ++sp)
+            for (int l = 0; l < L; ++l) {
+                const int t0 = b->h_tile_off[l], nt = b->h_tile_off[l + 1] - t0, per = (nt + ns - 1) / ns;
+                mcl::sifttc3::Chunk k;
+                k.tile_begin = t0 + std::min(nt, sp * per);
+                k.tile_end = t0 + std::min(nt, (sp + 1) * per);
+                k.img_begin = l;    // location
+                k.img_end = sp;     // range index: where the range's records go
+                if (k.tile_end > k.tile_begin) ch.push_back(k);
+            }
+        mcl_bow::Split s;
+        s.n_splits = ns;
+        s.n_chunks = (int)ch.size();
+        CU(cudaMalloc(&s.d, std::max<size_t>(ch.size() * sizeof(mcl::sifttc3::Chunk), 16)));
+        b->splits.push_back(s);
+        if (!ch.empty()) CU(cudaMemcpyAsync(s.d, ch.data(), ch.size() * sizeof(mcl::sifttc3::Chunk), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));   // `ch` is a local
+    }
+    int h_bad = 0;
+    CU(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    b->tc_ok = h_bad == 0;   // centroids outside [0, 256): the float32 SIMT kernel is used instead
+    return MCL_OK;
+}
+}  // namespace
+
 extern "C" void mcl_bow_destroy(mcl_bow* b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
@@ -1184,8 +1434,7 @@ extern "C" void mcl_bow_destroy(mcl_bow* b) {
     cudaFree(b->d_imf);
     cudaFree(b->d_voc_off);
     cudaFree(b->d_img_off);
-    cudaFree(b->d_tile_off);
-    cudaFree(b->d_tiles);
+    bow_free_tc(b);
     delete b;
 }
 
@@ -1240,29 +1489,10 @@ extern "C" int mcl_bow_create(mcl_ctx* c, int n_locations, const int64_t* voc_ro
         BCU(cudaFuncSetAttribute(mcl::bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W * 12));
         c->bow_score_smem = W * 12;
     }
-    // codebook planes for the tensor-core word assignment
-    {
-        b->h_tile_off.resize(n_locations + 1);
-        int32_t acc = 0;
-        for (int l = 0; l < n_locations; ++l) {
-            b->h_tile_off[l] = acc;
-            acc += (int32_t)((voc_row_offsets[l + 1] - voc_row_offsets[l] + mcl::bowtc::TILE_N - 1) / mcl::bowtc::TILE_N);
-        }
-        b->h_tile_off[n_locations] = acc;
-        BCU(cudaMalloc(&b->d_tile_off, (size_t)(n_locations + 1) * 4));
-        BCU(cudaMemcpyAsync(b->d_tile_off, b->h_tile_off.data(), (size_t)(n_locations + 1) * 4, cudaMemcpyHostToDevice, st));
-        BCU(cudaMalloc(&b->d_tiles, (size_t)acc * mcl::bowtc::STAGE_BYTES));
-        int* bad = c->flags.as<int>() + 6;
-        BCU(cudaMemsetAsync(bad, 0, 4, st));
-        {
-            ProfScope ps(c, PROF_PREP, st);
-            mcl::bowtc::build_planes_kernel<<<acc, 256, 0, st>>>(b->d_voc, b->d_voc_off, n_locations, b->d_tile_off, b->d_tiles, bad);
-        }
-        BCU(cudaGetLastError());
-        int h_bad = 0;
-        BCU(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
-        BCU(cudaStreamSynchronize(st));
-        b->tc_ok = h_bad == 0;   // centroids outside [0, 256) or huge norms: the SIMT kernel is used instead
+    BCU(cudaStreamSynchronize(st));
+    {   // fp16 code-book tiles for the tensor-core word assignment
+        const int r = bow_build_tc(b, st);
+        if (r) { mcl_bow_destroy(b); return r; }
     }
     BCU(cudaStreamSynchronize(st));
 #undef BCU
@@ -1281,97 +1511,82 @@ int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
     if (n_q > 0) {
         const int* only_if = nullptr;
         if (b->tc_ok && c->opt[2] != 1) {
-            // ---- tensor cores: u8 copy of the query rows in the SW128 image, two-plane contraction, float32 resolve
+            // ---- tensor cores: fp16 copy of the query rows, approximate keys per 32-word group, float32 resolve
+            using namespace mcl::tc9;
             using namespace mcl::bowtc;
-            const int n_qtiles = (n_q + QTILE - 1) / QTILE;
-            const int64_t padded = (int64_t)n_qtiles * QTILE;
-            CU(c->bow_q8.ensure((size_t)padded * 128));
-            CU(c->bow_qaux.ensure((size_t)padded * 8 + 64));
-            const int n_qt = n_qtiles;
-            int n_splits = (2 * c->sm_count + b->n_loc * n_qt - 1) / (b->n_loc * n_qt);
-            n_splits = std::max(1, std::min(n_splits, 8));
-            const int n_parts = n_splits * HALVES;   // records per (location, row): every split reports once per epilogue half
-            CU(c->bow_tc_out.ensure((size_t)n_parts * nbest * sizeof(int4) + nbest * 4));
-            int* queue = reinterpret_cast<int*>(c->bow_tc_out.as<int4>() + (size_t)n_parts * nbest);
-            int32_t* q_norm = c->bow_qaux.as<int32_t>();
-            int32_t* q_seg = q_norm + padded;
-            int64_t* q_off = reinterpret_cast<int64_t*>(q_seg + padded);
-            const int64_t h_off[2] = {0, n_q};
-            CU(cudaMemcpyAsync(q_off, h_off, 16, cudaMemcpyHostToDevice, st));
-            CU(cudaMemsetAsync(c->bow_q8.p, 0, (size_t)padded * 128, st));
+            const int n_qblocks = (n_q + QBLK - 1) / QBLK;
+            const int64_t padded = (int64_t)n_qblocks * QBLK;
+            const int groups_per_loc = (b->max_words + GROUP - 1) / GROUP;
+            const int64_t n_buckets = (int64_t)b->n_loc * groups_per_loc;
+            // work items = (code-book range, location, pair of query blocks): enough ranges to fill the GPU twice
+            const int n_qgroups = (n_qblocks + 1) / 2;
+            int want = (2 * c->sm_count / 2 + b->n_loc * n_qgroups - 1) / (b->n_loc * n_qgroups);
+            const mcl_bow::Split* sp = &b->splits.front();
+            for (const auto& cand : b->splits) { sp = &cand; if (cand.n_splits >= want) break; }
+            const int n_splits = sp->n_splits;
+            CU(c->bow_q8.ensure((size_t)padded * Shape<KIND_BOW>::ROW_BYTES));
+            CU(c->bow_qaux.ensure((size_t)padded * 4));
+            CU(c->bow_tc_out.ensure((size_t)n_splits * nbest * sizeof(int4)));
+            // sort scratch: job_grp[nbest] | sorted[nbest] | queue[nbest] | bucket_cnt[n_buckets]
+            CU(c->bow_sort.ensure((3 * nbest + (size_t)n_buckets) * 4));
+            int* job_grp = c->bow_sort.as<int>();
+            int* sorted = job_grp + nbest;
+            int* queue = sorted + nbest;
+            int* bucket = queue + nbest;
             int* bad = c->flags.as<int>() + 6;
             unsigned int* state = c->flags.as<unsigned int>() + 8;   // [8] queued rows, [9] SIMT flag, [10] rescans
+            CU(cudaMemsetAsync(c->bow_q8.p, 0, (size_t)padded * Shape<KIND_BOW>::ROW_BYTES, st));
+            CU(cudaMemsetAsync(c->bow_qaux.p, 0xFF, (size_t)padded * 4, st));
+            CU(cudaMemsetAsync(c->bow_tc_out.p, 0, (size_t)n_splits * nbest * sizeof(int4), st));
+            CU(cudaMemsetAsync(bucket, 0, (size_t)n_buckets * 4, st));
             CU(cudaMemsetAsync(bad, 0, 4, st));
             CU(cudaMemsetAsync(state, 0, 8, st));
             {
                 ProfScope ps(c, PROF_PREP, st);
-                mcl::prep_rows128_kernel<true><<<grid_for((int64_t)n_q * 32, 256, c->sm_count * 8), 256, 0, st>>>(
-                    d_q, n_q, q_off, q_off, 1, c->bow_q8.as<uint8_t>(), q_norm, q_seg, bad, nullptr);
+                bow_query_prep_kernel<<<grid_for((int64_t)n_q * 32, 256, c->sm_count * 8), 256, 0, st>>>(
+                    d_q, n_q, c->bow_q8.as<uint8_t>(), c->bow_qaux.as<int32_t>(), bad);
             }
             CU(cudaGetLastError());
-            const size_t smem = sizeof(Smem);
-            if (!c->bowtc_attr) {
-                CU(cudaFuncSetAttribute(bow_vq_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                CU(cudaFuncSetAttribute(bow_vq_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3((c->sm_count / 2) * 2);
-                cfg.blockDim = dim3(THREADS);
-                cfg.dynamicSmemBytes = smem;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = 2;
-                at[0].val.clusterDim.y = 1;
-                at[0].val.clusterDim.z = 1;
-                cfg.attrs = at;
-                cfg.numAttrs = 1;
-                int n = 0;
-                if (cudaOccupancyMaxActiveClusters(&n, bow_vq_tc_kernel<2>, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
-                c->bow_max_clusters = n;
-                c->bowtc_attr = true;
-            }
-            Params p;
-            p.q_desc = c->bow_q8.as<uint8_t>();
-            p.tiles = b->d_tiles;
-            p.tile_off = b->d_tile_off;
-            p.n_loc = b->n_loc;
-            p.n_qtiles = n_qtiles;
-            p.n_q = n_q;
-            p.n_splits = n_splits;
+            int rc9 = tc9_prepare(c);
+            if (rc9) return rc9;
+            Params p = {};
+            p.q_rows = c->bow_q8.as<uint8_t>();
+            p.q_aux = c->bow_qaux.as<int32_t>();
+            p.m_tiles = b->d_tiles;
+            p.m_rec = b->d_rec;
+            p.chunks = sp->d;
+            p.n_qblocks = n_qblocks;
+            p.n_chunks = sp->n_chunks;
             p.out = c->bow_tc_out.as<int4>();
-            // CTA pairs share the codebook tiles (multicast) when there are query tiles to pair; option 5 = 1 turns it off
-            const bool cl2 = c->bow_max_clusters > 0 && c->opt[5] != 1 && n_qtiles >= 2 && (n_qtiles % 2 == 0 || n_qtiles >= 16);
-            const int n_items = n_splits * b->n_loc * (cl2 ? (n_qtiles + 1) / 2 : n_qtiles);
+            p.n_q = n_q;
+            p.n_loc = b->n_loc;
+            p.meta_cap = META_CAP;
+            // CTA pairs share the code-book tiles (multicast) when there are query blocks to pair; option 5 = 1 turns it off
+            int cl = 1;
+            if (c->opt[5] == 2 || (c->opt[5] == 0 && n_qblocks >= 2 && (n_qblocks % 2 == 0 || n_qblocks >= 16))) cl = 2;
+            if (cl == 2 && c->tc9_clusters[1] < 1) cl = 1;
+            const int64_t n_items = (int64_t)((n_qblocks + cl - 1) / cl) * sp->n_chunks;
             {
                 ProfScope ps(c, PROF_VQ_TC, st);
-                if (cl2) {
-                    cudaLaunchConfig_t cfg = {};
-                    cfg.gridDim = dim3(2 * std::min(n_items, c->bow_max_clusters));
-                    cfg.blockDim = dim3(THREADS);
-                    cfg.dynamicSmemBytes = smem;
-                    cfg.stream = st;
-                    cudaLaunchAttribute at[1];
-                    at[0].id = cudaLaunchAttributeClusterDimension;
-                    at[0].val.clusterDim.x = 2;
-                    at[0].val.clusterDim.y = 1;
-                    at[0].val.clusterDim.z = 1;
-                    cfg.attrs = at;
-                    cfg.numAttrs = 1;
-                    CU(cudaLaunchKernelEx(&cfg, bow_vq_tc_kernel<2>, p));
-                } else {
-                    bow_vq_tc_kernel<1><<<std::min(n_items, c->sm_count), THREADS, smem, st>>>(p);
-                }
+                constexpr size_t smem = sizeof(Smem<KIND_BOW>);
+                if (cl == 2) CU(launch_cluster(tc9_kernel<KIND_BOW, 2>, 2 * (int)std::min<int64_t>(n_items, c->tc9_clusters[1]), THREADS, smem, st, 2, p));
+                else tc9_kernel<KIND_BOW, 1><<<(int)std::min<int64_t>(n_items, c->sm_count), THREADS, smem, st>>>(p);
             }
             CU(cudaGetLastError());
             {
                 ProfScope ps(c, PROF_VQ_RESOLVE, st);
-                bow_accept_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->bow_tc_out.as<int4>(), n_parts, d_q, n_q, b->n_loc, bad,
-                                                                  b->d_voc, b->d_voc_off, c->bow_best.as<unsigned long long>(),
-                                                                  queue, state);
+                const int g = grid_for((int64_t)nbest, 256, c->sm_count * 8);
+                bow_merge_kernel<<<g, 256, 0, st>>>(c->bow_tc_out.as<int4>(), n_splits, n_q, b->n_loc, groups_per_loc, bad, job_grp,
+                                                    bucket, queue, state);
+                bow_scan_kernel<<<1, 1024, 0, st>>>(bucket, (int)n_buckets);
+                bow_scatter_kernel<<<g, 256, 0, st>>>(job_grp, n_q, (int64_t)nbest, groups_per_loc, bucket, sorted);
+                bow_resolve_kernel<<<grid_for(((int64_t)nbest + RESOLVE_RUN - 1) / RESOLVE_RUN * 32, 128, c->sm_count * 16), 128, 0, st>>>(
+                    sorted, state, (int64_t)nbest, job_grp, d_q, n_q, b->d_voc, b->d_voc_off, c->bow_best.as<unsigned long long>());
                 bow_decide_kernel<<<1, 1, 0, st>>>(bad, (int64_t)nbest, state);
                 bow_rescan_kernel<<<c->sm_count * 8, 256, 0, st>>>(queue, d_q, n_q, b->d_voc, b->d_voc_off,
                                                                   c->bow_best.as<unsigned long long>(), state);
             }
-            c->launches += 2;
+            c->launches += 5;
             CU(cudaGetLastError());
             only_if = reinterpret_cast<const int*>(state + 1);   // many ambiguous rows or non-integer queries: float32 SIMT pass
         }
@@ -1459,21 +1674,19 @@ extern "C" int mcl_kmeans(mcl_ctx* c, int64_t n, const void* obs, int obs_dtype,
     if (max_iter <= 0) max_iter = INT_MAX;   // scipy's loop has no iteration cap
     CU(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
-    using namespace mcl::bowtc;
-    const int max_tiles = (k + TILE_N - 1) / TILE_N;
     float* d_obs = nullptr;
     float* d_voc[2] = {nullptr, nullptr};
     float* d_sums = nullptr;
     int* d_counts = nullptr;
     int64_t* d_voc_off = nullptr;
-    int32_t* d_tile_off = nullptr;
-    uint8_t* d_tiles = nullptr;
     double* d_sum = nullptr;   // [0] distortion sum; the following int is k_new
+    mcl_bow tmp;   // a one-location "index" over the current code book, for bow_assign
     auto cleanup = [&]() {   // idempotent: an error inside assign_and_distort frees here and the caller frees again
         cudaStreamSynchronize(st);
         void** ptrs[] = {(void**)&d_obs, (void**)&d_voc[0], (void**)&d_voc[1], (void**)&d_sums, (void**)&d_counts,
-                         (void**)&d_voc_off, (void**)&d_tile_off, (void**)&d_tiles, (void**)&d_sum};
+                         (void**)&d_voc_off, (void**)&d_sum};
         for (void** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+        bow_free_tc(&tmp);
     };
 #define KCU(expr)                                                                                                \
     do {                                                                                                          \
@@ -1489,8 +1702,6 @@ extern "C" int mcl_kmeans(mcl_ctx* c, int64_t n, const void* obs, int obs_dtype,
     KCU(cudaMalloc(&d_sums, (size_t)k * 512));
     KCU(cudaMalloc(&d_counts, (size_t)k * 4));
     KCU(cudaMalloc(&d_voc_off, 16));
-    KCU(cudaMalloc(&d_tile_off, 8));
-    KCU(cudaMalloc(&d_tiles, (size_t)max_tiles * STAGE_BYTES));
     KCU(cudaMalloc(&d_sum, 16));
     if (obs_dtype == MCL_F32) {
         KCU(cudaMemcpyAsync(d_obs, obs, (size_t)n * 512, cudaMemcpyHostToDevice, st));
@@ -1501,32 +1712,25 @@ extern "C" int mcl_kmeans(mcl_ctx* c, int64_t n, const void* obs, int obs_dtype,
         mcl::u8_to_f32_kernel<<<grid_for(n * 128, 256, c->sm_count * 8), 256, 0, st>>>(c->stage.as<uint8_t>(), d_obs, n * 128);
     }
     KCU(cudaMemcpyAsync(d_voc[0], guess, (size_t)k * 512, cudaMemcpyHostToDevice, st));
-    mcl_bow tmp;   // a one-location "index" over the current code book, for bow_assign
     tmp.ctx = c;
     tmp.n_loc = 1;
     tmp.W = k;
     tmp.d_voc_off = d_voc_off;
-    tmp.d_tile_off = d_tile_off;
-    tmp.d_tiles = d_tiles;
     int cur = 0, k_cur = k, iters = 0;
     double prev = INFINITY, avg = 0.0;
     int rc = MCL_OK;
     auto assign_and_distort = [&]() -> int {
         const int64_t h_off[2] = {0, k_cur};
-        const int32_t h_toff[2] = {0, (k_cur + TILE_N - 1) / TILE_N};
         KCU(cudaMemcpyAsync(d_voc_off, h_off, 16, cudaMemcpyHostToDevice, st));
-        KCU(cudaMemcpyAsync(d_tile_off, h_toff, 8, cudaMemcpyHostToDevice, st));
-        int* bad = c->flags.as<int>() + 6;
-        KCU(cudaMemsetAsync(bad, 0, 4, st));
-        c->launches++;
-        build_planes_kernel<<<h_toff[1], 256, 0, st>>>(d_voc[cur], d_voc_off, 1, d_tile_off, d_tiles, bad);
-        int h_bad = 0;
-        KCU(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));
         KCU(cudaStreamSynchronize(st));
         tmp.d_voc = d_voc[cur];
         tmp.max_words = k_cur;
         tmp.voc_rows = k_cur;
-        tmp.tc_ok = h_bad == 0;
+        tmp.h_voc_off.assign(h_off, h_off + 2);
+        {
+            const int rb = bow_build_tc(&tmp, st);   // fp16 tiles of the current code book
+            if (rb) return rb;
+        }
         const int r = bow_assign(&tmp, d_obs, (int)n, st);
         if (r) return r;
         KCU(cudaMemsetAsync(d_sum, 0, 16, st));
@@ -1569,7 +1773,7 @@ extern "C" int mcl_kmeans(mcl_ctx* c, int64_t n, const void* obs, int obs_dtype,
         if (out_distortion) *out_distortion = avg;
         if (out_iters) *out_iters = iters;
     }
-    tmp.d_voc = nullptr; tmp.d_voc_off = nullptr; tmp.d_tile_off = nullptr; tmp.d_tiles = nullptr;
+    tmp.d_voc = nullptr; tmp.d_voc_off = nullptr;
     cleanup();
 #undef KCU
     return rc;

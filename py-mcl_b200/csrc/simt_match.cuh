@@ -91,9 +91,12 @@ __device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, cons
 __global__ void __launch_bounds__(128) orb_knn_kernel(
     const uint4* __restrict__ q_desc, const int64_t* __restrict__ q_off, const uint4* __restrict__ m_desc,
     const int64_t* __restrict__ m_off, int n_images, double ratio, const uint8_t* __restrict__ mask,
-    int32_t* __restrict__ counts) {
+    int32_t* __restrict__ counts, const int* __restrict__ only_if /* optional device flag: run only when *only_if != 0 */,
+    unsigned long long* __restrict__ n_pairs_run /* optional statistics */) {
     const int img = blockIdx.x, frame = blockIdx.y;
+    if (only_if && *only_if == 0) return;
     if (mask && !mask[(int64_t)frame * n_images + img]) return;
+    if (n_pairs_run && blockIdx.z == 0 && threadIdx.x == 0) atomicAdd(n_pairs_run, 1ULL);
     __shared__ uint4 sm[ORB_STAGE_ROWS][2];
     const int64_t q0 = q_off[frame], q1 = q_off[frame + 1];
     const int64_t m0 = m_off[img];

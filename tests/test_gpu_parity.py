@@ -312,46 +312,125 @@ def test_sift_host_batch_pipelined_equals_resident(ctx):
 # ------------------------------------------------------------------------------------------------
 # ORB
 # ------------------------------------------------------------------------------------------------
-def test_orb_golden_reference_counts(ctx, golden_dir):
+ORB_ALGOS = [_lib.ALGO_SIMT, _lib.ALGO_TENSOR, _lib.ALGO_AUTO]
+
+
+@pytest.mark.parametrize("algo", ORB_ALGOS)
+def test_orb_golden_reference_counts(ctx, golden_dir, algo):
     z = np.load(os.path.join(golden_dir, "orb_desc_case.npz"))
     qs, ms = split(z["q"], z["q_off"]), split(z["m"], z["m_off"])
     m = _lib.MapIndex(ctx, "ORB", ms)
-    assert np.array_equal(m.match_counts(qs, mode=_lib.KNN2_RATIO), z["counts_knn"])
-    assert np.array_equal(m.match_counts(qs, mode=_lib.CROSSCHECK), z["counts_crosscheck"])
+    assert np.array_equal(m.match_counts(qs, mode=_lib.KNN2_RATIO, algo=algo), z["counts_knn"])
+    assert np.array_equal(m.match_counts(qs, mode=_lib.CROSSCHECK, algo=algo), z["counts_crosscheck"])
     m.close()
 
 
-def test_orb_cfg1_vs_oracle(ctx):
+@pytest.mark.parametrize("algo", ORB_ALGOS)
+def test_orb_cfg1_vs_oracle(ctx, algo):
     """BASELINE config 1 at full size: one (500,32) query vs 50 images of (500,32)."""
     map_des, q = synth.orb_map_and_query(1)
     m = _lib.MapIndex(ctx, "ORB", map_des)
     want_knn = oracle_counts(oracle.orb_pair_count_knn, [q], map_des)
     want_cc = oracle_counts(oracle.orb_pair_count_crosscheck, [q], map_des)
     assert want_knn.sum() > 50
-    assert np.array_equal(m.match_counts([q], mode=_lib.KNN2_RATIO), want_knn)
-    assert np.array_equal(m.match_counts([q], mode=_lib.CROSSCHECK), want_cc)
+    for cl in tensor_launch_variants(ctx):
+        assert np.array_equal(m.match_counts([q], mode=_lib.KNN2_RATIO, algo=algo), want_knn), cl
+    assert np.array_equal(m.match_counts([q], mode=_lib.CROSSCHECK, algo=algo), want_cc)
     m.close()
 
 
-def test_orb_ragged_ties_and_mask(ctx):
+@pytest.mark.parametrize("algo", ORB_ALGOS)
+def test_orb_ragged_ties_and_mask(ctx, algo):
     rng = np.random.default_rng(9)
-    sizes = [0, 1, 2, 3, 127, 128, 129, 257, 700]
+    sizes = [0, 1, 2, 3, 127, 128, 129, 257, 700, 31, 32, 33, 5]
     map_des = [synth.orb_like(rng, n) if n else None for n in sizes]
     # low-entropy rows -> many distance ties (first-index tie-breaking matters for crossCheck)
     map_des[6] = (rng.integers(0, 2, size=(129, 32)) * 255).astype(np.uint8)
+    # an image whose rows are all far from every query row (Hamming > 128): the zero rows that pad its last group must not win
     frames = [synth.orb_like(rng, 300), (rng.integers(0, 2, size=(140, 32)) * 255).astype(np.uint8), None,
-              synth.orb_like(rng, 1)]
+              synth.orb_like(rng, 1), synth.orb_like(rng, 257)]
+    map_des[12] = (~frames[4][:5]).copy()
+    map_des[12][1, 0] ^= 3
     frames[0][:80] = synth.orb_flip(rng, map_des[8][:80], 30)
+    frames[4][100:180] = synth.orb_flip(rng, map_des[8][300:380], 20)
     want_knn = oracle_counts(oracle.orb_pair_count_knn, frames, map_des)
     want_cc = oracle_counts(oracle.orb_pair_count_crosscheck, frames, map_des)
     m = _lib.MapIndex(ctx, "ORB", map_des)
-    assert np.array_equal(m.match_counts(frames, mode=_lib.KNN2_RATIO), want_knn)
-    assert np.array_equal(m.match_counts(frames, mode=_lib.CROSSCHECK), want_cc)
+    for cl in tensor_launch_variants(ctx):
+        assert np.array_equal(m.match_counts(frames, mode=_lib.KNN2_RATIO, algo=algo), want_knn), cl
+    assert np.array_equal(m.match_counts(frames, mode=_lib.CROSSCHECK, algo=algo), want_cc)
     mask = (rng.random(want_knn.shape) < 0.5).astype(np.uint8)
-    assert np.array_equal(m.match_counts(frames, mode=_lib.KNN2_RATIO, mask=mask, fill_value=1),
+    assert np.array_equal(m.match_counts(frames, mode=_lib.KNN2_RATIO, mask=mask, fill_value=1, algo=algo),
                           np.where(mask > 0, want_knn, 1))
-    assert np.array_equal(m.match_counts(frames, mode=_lib.CROSSCHECK, mask=mask, fill_value=7),
+    assert np.array_equal(m.match_counts(frames, mode=_lib.CROSSCHECK, mask=mask, fill_value=7, algo=algo),
                           np.where(mask > 0, want_cc, 7))
+    m.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_orb_tensor_core_fuzz_equals_exact_kernel(ctx, seed):
+    """ORB 2-NN + ratio on the tensor cores (+-1 rows, s8 x s8 -> s32, exact keys) against the xor + popc SIMT kernel and,
+    on a sample, the oracle: random shapes (tiny images, images of thousands of rows), random / low-entropy / duplicated
+    rows, bit-flipped copies at every distance, ratios other than 0.7."""
+    rng = np.random.default_rng(500 + seed)
+
+    def rows(n, style):
+        if style == 0:
+            return synth.orb_like(rng, n)
+        if style == 1:
+            return (rng.integers(0, 2, size=(n, 32)) * 255).astype(np.uint8)
+        base = synth.orb_like(rng, max(1, n // 7 + 1))
+        return synth.orb_flip(rng, base[rng.integers(0, len(base), size=n)], int(rng.integers(1, 60)))
+
+    n_img = int(rng.integers(1, 40))
+    big = int(rng.integers(0, n_img))
+    map_des = [rows(int(rng.integers(0, 700)) if i != big else int(rng.integers(2000, 6000)), int(rng.integers(0, 3))) for i in range(n_img)]
+    map_des = [m if len(m) else None for m in map_des]
+    frames = [rows(int(rng.integers(1, 900)), int(rng.integers(0, 3))) for _ in range(int(rng.integers(1, 6)))]
+    for f in frames:
+        src = [m for m in map_des if m is not None and len(m) >= 2]
+        m = src[int(rng.integers(0, len(src)))]
+        n = min(len(f), len(m)) // 2
+        if n:
+            f[:n] = synth.orb_flip(rng, m[rng.integers(0, len(m), size=n)], int(rng.integers(0, 90)))
+    ratio = float(rng.choice([0.7, 0.7, 0.5, 0.9, 1.0]))
+    mi = _lib.MapIndex(ctx, "ORB", map_des)
+    exact = mi.match_counts(frames, ratio=ratio, algo=_lib.ALGO_SIMT)
+    for cl in tensor_launch_variants(ctx):
+        assert np.array_equal(mi.match_counts(frames, ratio=ratio, algo=_lib.ALGO_TENSOR), exact), (seed, cl)
+    mi.close()
+    assert np.array_equal(exact[0], [oracle.orb_pair_count_knn(frames[0], m, ratio) for m in map_des])
+
+
+def test_orb_candidate_overflow_is_repaired_on_the_device(ctx):
+    map_des, q = synth.orb_map_and_query(3, n_images=12, nm=400, nq=500)
+    frames = [q, synth.orb_flip(np.random.default_rng(1), map_des[5][:300], 20)]
+    m = _lib.MapIndex(ctx, "ORB", map_des)
+    want = m.match_counts(frames, algo=_lib.ALGO_SIMT)
+    assert want.sum() > 300
+    repaired0 = ctx.stats()["repaired_pairs"]
+    ctx.set_option(3, 16)
+    try:
+        for cl in tensor_launch_variants(ctx):
+            assert np.array_equal(m.match_counts(frames, algo=_lib.ALGO_TENSOR), want), cl
+        assert ctx.stats()["repaired_pairs"] > repaired0, "the dirty-pair repair did not run"
+    finally:
+        ctx.set_option(3, 0)
+    m.close()
+
+
+def test_orb_throughput_shape_tensor_equals_simt(ctx):
+    """The batch shape the ORB bench times (frames x images x 500 x 500), reduced: tensor cores vs SIMT, bit-exact."""
+    rng = np.random.default_rng(2)
+    map_des = [synth.orb_like(rng, 500) for _ in range(60)]
+    frames = [synth.orb_like(rng, 500) for _ in range(12)]
+    for f in range(12):
+        frames[f][:200] = synth.orb_flip(rng, map_des[(7 * f) % 60][:200], 40)
+    m = _lib.MapIndex(ctx, "ORB", map_des)
+    tc = m.match_counts(frames, algo=_lib.ALGO_TENSOR)
+    assert np.array_equal(tc, m.match_counts(frames, algo=_lib.ALGO_SIMT))
+    assert all(tc[f, (7 * f) % 60] >= 100 for f in range(12))
+    assert ctx.stats()["orb_candidates"] > 0
     m.close()
 
 
