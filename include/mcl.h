@@ -54,7 +54,8 @@ int mcl_device_info(mcl_ctx* ctx, int64_t info[8]);
 int mcl_sync(mcl_ctx* ctx);
 /* statistics since mcl_init (synchronises): out[0] = SIFT candidates resolved by the exact fix-up, [1] = SIFT whole-image exact
  * rescans, [2] = SIFT/ORB (frame, image) pairs recomputed by the SIMT kernel because a candidate list was full, [3] = BOW
- * rows rescanned over a whole code book in the last call, [4] = ORB candidates resolved exactly, [5..7] reserved.
+ * rows rescanned over a whole code book, [4] = ORB candidates resolved exactly, [6] = entries of the BOW resolve list in the
+ * last call, [5], [7] reserved.
  * No reference counterpart (bench.py reports them per input distribution). */
 int mcl_stats(mcl_ctx* ctx, int64_t out[8]);
 /* pinned host memory for the end-to-end path (cudaHostAlloc) */
@@ -72,7 +73,8 @@ int64_t mcl_launch_count(mcl_ctx* ctx);
 /* per-kernel device timing with CUDA events on the launching stream.  which: 0 = SIFT tensor-core kernel,
  * 1 = SIFT fix-up, 2 = ORB, 3 = SURF, 4 = BOW vq, 5 = BOW score, 6 = Laplacian, 7 = ingest (prep),
  * 8 = SIFT SIMT (dp4a) kernel, 9 = BOW vq tensor-core kernel, 10 = BOW float32 resolve kernels, 11 = chi-squared kernel,
- * 12 = ORB exact fix-up / repair kernels (slot 2 = the ORB tensor-core or SIMT matching kernel).
+ * 12 = ORB exact fix-up / repair kernels (slot 2 = the ORB tensor-core or SIMT matching kernel), 13 = BOW whole-code-book
+ * rescans of ambiguous rows.
  * mcl_profile_read synchronises, returns accumulated milliseconds and launch count, and resets them. */
 int mcl_profile_enable(mcl_ctx* ctx, int on);
 int mcl_profile_read(mcl_ctx* ctx, int which, double* ms, int64_t* launches);

@@ -23,7 +23,7 @@ T_PY, T_F64, T_F32 = 0, 1, 2
 KIND_BY_NAME = {"SIFT": SIFT, "ORB": ORB, "SURF": SURF}
 ROW_DIM = {SIFT: 128, ORB: 32, SURF: 64, BOWQ: 128}
 PROFILE_SLOTS = {"sift_tc": 0, "sift_fixup": 1, "orb": 2, "surf": 3, "bow_vq": 4, "bow_score": 5, "laplacian": 6,
-                 "ingest": 7, "sift_simt": 8, "bow_vq_tc": 9, "bow_resolve": 10, "chi2": 11, "orb_fixup": 12}
+                 "ingest": 7, "sift_simt": 8, "bow_vq_tc": 9, "bow_resolve": 10, "chi2": 11, "orb_fixup": 12, "bow_rescan": 13}
 
 
 class MclError(RuntimeError):
@@ -230,7 +230,7 @@ class Context:
         a = (C.c_int64 * 8)()
         _check(self._lib.mcl_stats(self._h, a), "mcl_stats")
         return {"sift_candidates": a[0], "sift_rescans": a[1], "repaired_pairs": a[2], "bow_rescanned_rows": a[3],
-                "orb_candidates": a[4]}
+                "orb_candidates": a[4], "bow_resolve_entries": a[6]}
 
     def set_option(self, option, value):
         _check(self._lib.mcl_set_option(self._h, int(option), int(value)), "mcl_set_option")

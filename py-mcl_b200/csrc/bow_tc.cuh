@@ -30,39 +30,55 @@ constexpr int GROUP_W = tc9::GROUP;   // 32 words per group
 constexpr float KEY_REL = 0.00048828125f + 0.0001220703125f;   // 2^-11 + 2^-13
 constexpr float KEY_ABS = 4.0f;
 
-// Pass 1 (one thread per (location, row) job): merge the ranges' records; accepted jobs are counted into their group's
-// bucket, the others queued for a full rescan.
-// state: [0] = queued rows, [1] = run-the-SIMT-kernel flag (bow_decide_kernel), [2] = rows rescanned (statistics)
+// Pass 1 (one thread per (location, row) job): merge the ranges' records into the three best groups, their keys
+// k1 >= k2 >= k3 and the fourth-best key k4.  With the margin 2 E(k1): the first k_i that trails k1 by more than the margin
+// proves that the argmin lies in the groups before it -> one entry in each of those groups' buckets (the resolve combines
+// them with a 64-bit atomicMin on (distance, word)).  If even k4 is within the margin the row is queued for a full rescan.
+// state: [0] = queued rows, [1] = run-the-SIMT-kernel flag (bow_decide_kernel), [2] = rows rescanned (statistics),
+//        [3] = entries in the sorted list (bow_scan_kernel)
+constexpr int TOPG = 3;
 __global__ void __launch_bounds__(256) bow_merge_kernel(const int4* __restrict__ tc, int n_splits, int n_q, int n_loc, int groups_per_loc,
-                                                        const int* __restrict__ bad, int* __restrict__ job_grp,
+                                                        const int* __restrict__ bad, int* __restrict__ job_grp /* [n_jobs][TOPG] */,
                                                         int* __restrict__ bucket_cnt, int* __restrict__ queue,
                                                         unsigned int* __restrict__ state) {
     const int64_t n_jobs = (int64_t)n_loc * n_q;
     const bool all_bad = *bad != 0;   // non-integer query rows: nothing from the tensor-core pass can be trusted
     for (int64_t job = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; job < n_jobs; job += (int64_t)gridDim.x * blockDim.x) {
-        int b1 = sifttc3::NONE, b2 = sifttc3::NONE, grp = 0;   // positive float32 keys compare like their bit patterns
+        int k1 = 0, k2 = 0, k3 = 0, k4 = 0, p1 = 0, p2 = 0, p3 = 0;   // positive float32 keys compare like their bit patterns; 0 = none
+        auto ins = [&](int k, int pos) {
+            if (k > k1) { k4 = k3; k3 = k2; p3 = p2; k2 = k1; p2 = p1; k1 = k; p1 = pos; }
+            else if (k > k2) { k4 = k3; k3 = k2; p3 = p2; k2 = k; p2 = pos; }
+            else if (k > k3) { k4 = k3; k3 = k; p3 = pos; }
+            else k4 = max(k4, k);
+        };
         for (int sp = 0; sp < n_splits; ++sp) {
-            const int4 r = tc[(size_t)sp * n_jobs + job];
-            if (r.y > b1) { b2 = max(b1, r.z); b1 = r.y; grp = r.x; }
-            else { b2 = max(b2, r.y); }
+            const int4 pp = tc[2 * ((size_t)sp * n_jobs + job)], kk = tc[2 * ((size_t)sp * n_jobs + job) + 1];
+            if (kk.x <= 0) continue;   // this range reported nothing for the row
+            ins(kk.x, pp.x);
+            if (kk.y > 0) ins(kk.y, pp.y);
+            if (kk.z > 0) ins(kk.z, pp.z);
+            if (kk.w > 0) k4 = max(k4, kk.w);
         }
-        bool accept = !all_bad && b1 > 0;
-        if (accept && b2 > 0) {
-            const float k1 = __int_as_float(b1), k2 = __int_as_float(b2);
-            accept = (k1 - k2) > 2.0f * (KEY_REL * k1 + KEY_ABS);
+        int g[TOPG] = {-1, -1, -1};
+        if (!all_bad && k1 > 0) {
+            const float f1 = __int_as_float(k1);
+            const float margin = 2.0f * (KEY_REL * f1 + KEY_ABS);
+            if (k2 <= 0 || f1 - __int_as_float(k2) > margin) { g[0] = p1; }
+            else if (k3 <= 0 || f1 - __int_as_float(k3) > margin) { g[0] = p1; g[1] = p2; }
+            else if (k4 <= 0 || f1 - __int_as_float(k4) > margin) { g[0] = p1; g[1] = p2; g[2] = p3; }
         }
-        if (accept) {
-            job_grp[job] = grp;
-            atomicAdd(&bucket_cnt[(int)(job / n_q) * groups_per_loc + grp], 1);
-        } else {
-            job_grp[job] = -1;
-            queue[atomicAdd(&state[0], 1u)] = (int)job;
+        const int base = (int)(job / n_q) * groups_per_loc;
+#pragma unroll
+        for (int i = 0; i < TOPG; ++i) {
+            job_grp[TOPG * job + i] = g[i];
+            if (g[i] >= 0) atomicAdd(&bucket_cnt[base + g[i]], 1);
         }
+        if (g[0] < 0) queue[atomicAdd(&state[0], 1u)] = (int)job;
     }
 }
 
 // exclusive prefix sum of the bucket counts (one CTA); cnt[] becomes the running fill position of every bucket
-__global__ void __launch_bounds__(1024) bow_scan_kernel(int* __restrict__ cnt, int n) {
+__global__ void __launch_bounds__(1024) bow_scan_kernel(int* __restrict__ cnt, int n, unsigned int* __restrict__ state) {
     __shared__ int part[1024];
     const int per = (n + 1023) / 1024;
     const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
@@ -78,37 +94,54 @@ __global__ void __launch_bounds__(1024) bow_scan_kernel(int* __restrict__ cnt, i
     }
     int run = part[threadIdx.x] - sum;
     for (int i = lo; i < hi; ++i) { const int c = cnt[i]; cnt[i] = run; run += c; }
+    if (threadIdx.x == 1023) state[3] = (unsigned int)part[1023];   // entries of the sorted list
 }
 
 __global__ void __launch_bounds__(256) bow_scatter_kernel(const int* __restrict__ job_grp, int n_q, int64_t n_jobs, int groups_per_loc,
-                                                          int* __restrict__ bucket_pos, int* __restrict__ sorted) {
+                                                          int* __restrict__ bucket_pos, int2* __restrict__ sorted) {
     for (int64_t job = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; job < n_jobs; job += (int64_t)gridDim.x * blockDim.x) {
-        const int g = job_grp[job];
-        if (g >= 0) sorted[atomicAdd(&bucket_pos[(int)(job / n_q) * groups_per_loc + g], 1)] = (int)job;
+        const int base = (int)(job / n_q) * groups_per_loc;
+#pragma unroll
+        for (int which = 0; which < TOPG; ++which) {
+            const int g = job_grp[TOPG * job + which];
+            if (g >= 0) sorted[atomicAdd(&bucket_pos[base + g], 1)] = make_int2((int)job, g);   // entry = (job, one of its groups)
+        }
     }
 }
 
-// Pass 2: a warp takes RUN consecutive jobs of the sorted list; the 32 code-book rows of the current (location, group) stay in
-// registers while the jobs' bucket does not change.  Lane l holds dims 4l..4l+3; it forms its partial sum for all 32 words,
-// then the partials are summed ACROSS lanes by a transposing reduction (at distance 16 a lane keeps the half of the word list
-// that matches its bit 4 and adds the partner's partials of those words, and so on: 31 shuffles instead of 32 x 5), after
-// which lane i owns word i.  Every word's sum is formed by the same pairing (l, l^16), (l, l^8), ... as bow_rescan_kernel's
-// butterfly, so the float32 distances are bit-identical to the rescan's and the SIMT kernel's tie-breaking is preserved.
-constexpr int RESOLVE_RUN = 8;
-__global__ void __launch_bounds__(128) bow_resolve_kernel(const int* __restrict__ sorted, const unsigned int* __restrict__ state,
-                                                          int64_t n_jobs, const int* __restrict__ job_grp, const float* __restrict__ q_desc,
+// Pass 2: a warp takes RESOLVE_RUN consecutive entries of the sorted list (chosen by the host from the batch size: long runs
+// re-use the group, short runs keep every SM busy on small batches); the 32 code-book rows of the current (location, group)
+// stay in registers while the entries' bucket does not change, and the next entry's (job, group) and query row are fetched
+// while the current one is evaluated (entry -> row -> arithmetic is a chain of dependent trips to L2 otherwise, and with
+// 239 registers only two warps per scheduler are there to hide it).  Lane l holds dims 4l..4l+3; it forms its partial sum for
+// all 32 words, then the partials are summed ACROSS lanes by a transposing reduction (at distance 16 a lane keeps the half of
+// the word list that matches its bit 4 and adds the partner's partials of those words, and so on: 31 shuffles instead of
+// 32 x 5), after which lane i owns word i.  Every word's sum is formed by the same pairing (l, l^16), (l, l^8), ... as
+// bow_rescan_kernel's butterfly, so the float32 distances are bit-identical to the rescan's and the SIMT kernel's
+// tie-breaking is preserved.
+__global__ void __launch_bounds__(128) bow_resolve_kernel(const int2* __restrict__ sorted, const unsigned int* __restrict__ state,
+                                                          int RESOLVE_RUN, const float* __restrict__ q_desc,
                                                           int n_q, const float* __restrict__ voc, const int64_t* __restrict__ voc_off,
                                                           unsigned long long* __restrict__ best) {
     const int lane = threadIdx.x & 31;
-    const int64_t n_sorted = n_jobs - (int64_t)state[0];   // accepted jobs
+    const int64_t n_sorted = (int64_t)state[3];
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     float4 cw[GROUP_W];
     for (int64_t run = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; run * RESOLVE_RUN < n_sorted; run += n_warps) {
         int cur_loc = -1, cur_grp = -1, n_words = 0;
-        const int64_t end = min(n_sorted, (run + 1) * RESOLVE_RUN);
-        for (int64_t i = run * RESOLVE_RUN; i < end; ++i) {
-            const int job = sorted[i];
-            const int loc = job / n_q, row = job - loc * n_q, grp = job_grp[job];
+        const int64_t begin = run * (int64_t)RESOLVE_RUN, end = min(n_sorted, begin + RESOLVE_RUN);
+        int2 e_next = sorted[begin];
+        float4 o_next = reinterpret_cast<const float4*>(q_desc + (size_t)(e_next.x % n_q) * 128)[lane];
+#pragma unroll 1
+        for (int64_t i = begin; i < end; ++i) {
+            const int2 e = e_next;
+            const float4 o = o_next;
+            if (i + 1 < end) {
+                e_next = sorted[i + 1];
+                o_next = reinterpret_cast<const float4*>(q_desc + (size_t)(e_next.x % n_q) * 128)[lane];
+            }
+            const int job = e.x, grp = e.y;
+            const int loc = job / n_q;
             if (loc != cur_loc || grp != cur_grp) {   // warp-uniform
                 const int64_t v0 = voc_off[loc];
                 n_words = (int)(voc_off[loc + 1] - v0);
@@ -120,7 +153,6 @@ __global__ void __launch_bounds__(128) bow_resolve_kernel(const int* __restrict_
                 cur_loc = loc;
                 cur_grp = grp;
             }
-            const float4 o = reinterpret_cast<const float4*>(q_desc + (size_t)row * 128)[lane];
             float pw[GROUP_W];
 #pragma unroll
             for (int j = 0; j < GROUP_W; ++j) {
@@ -174,7 +206,7 @@ __global__ void __launch_bounds__(128) bow_resolve_kernel(const int* __restrict_
                 const unsigned long long other = __shfl_xor_sync(0xffffffffu, bk, k);
                 bk = other < bk ? other : bk;
             }
-            if (lane == 0) best[job] = bk;
+            if (lane == 0) atomicMin(&best[job], bk);   // a row with several candidate groups gets the best of them
         }
     }
 }
@@ -185,24 +217,28 @@ __global__ void bow_decide_kernel(const int* __restrict__ bad, int64_t n_jobs, u
     state[1] = (*bad != 0 || state[0] > thr) ? 1u : 0u;
 }
 
-// Pass 2 (one CTA per queued row, 8 warps striding over the words, 4 words in flight per warp): exact float32
-// direct-difference scan of the location's codebook, lowest index on ties.
-// best[] gets (distance bits << 32 | word) like bow_vq_kernel's atomicMin key.
+// Pass 3 (RESCAN_SLICES CTAs per queued row, each scanning one slice of the code book with 8 warps x 4 words in flight): exact
+// float32 direct-difference scan, lowest index on ties, merged with a 64-bit atomicMin -- one CTA per row took 0.28 ms for a
+// 10 000-word code book however few rows were queued (312 dependent trips through L2 per warp).
+// best[] gets (distance bits << 32 | word) like bow_vq_kernel's atomicMin key (pre-set to all ones by the caller).
+constexpr int RESCAN_SLICES = 16;
 __global__ void __launch_bounds__(256) bow_rescan_kernel(const int* __restrict__ queue, const float* __restrict__ q_desc, int n_q,
                                                          const float* __restrict__ voc, const int64_t* __restrict__ voc_off,
                                                          unsigned long long* __restrict__ best, unsigned int* __restrict__ state) {
     if (state[1] != 0) return;
-    __shared__ unsigned long long part[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned n = state[0];
-    for (unsigned c = blockIdx.x; c < n; c += gridDim.x) {
+    for (unsigned u = blockIdx.x; u < n * RESCAN_SLICES; u += gridDim.x) {
+        const unsigned c = u / RESCAN_SLICES, slice = u % RESCAN_SLICES;
         const int job = queue[c];
         const int loc = job / n_q, row = job % n_q;
         const float4 o = reinterpret_cast<const float4*>(q_desc + (size_t)row * 128)[lane];
         const int64_t v0 = voc_off[loc];
         const int n_words = (int)(voc_off[loc + 1] - v0);
+        const int per = ((n_words + RESCAN_SLICES - 1) / RESCAN_SLICES + 3) & ~3;   // words per slice, a multiple of 4
+        const int w_lo = (int)slice * per, w_hi = min(n_words, w_lo + per);
         unsigned long long bk = ~0ULL;
-        for (int w0 = warp * 4; w0 < n_words; w0 += 32) {
+        for (int w0 = w_lo + warp * 4; w0 < w_hi; w0 += 32) {
             float d[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -218,21 +254,14 @@ __global__ void __launch_bounds__(256) bow_rescan_kernel(const int* __restrict__
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (w0 + j < n_words) {
+                if (w0 + j < w_hi) {
                     const unsigned long long key = ((unsigned long long)__float_as_uint(d[j]) << 32) | (unsigned)(w0 + j);
                     bk = key < bk ? key : bk;
                 }
             }
         }
-        if (lane == 0) part[warp] = bk;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long m = part[0];
-            for (int k = 1; k < 8; ++k) m = part[k] < m ? part[k] : m;
-            best[job] = m;
-            atomicAdd(&state[2], 1u);
-        }
-        __syncthreads();
+        if (lane == 0 && bk != ~0ULL) atomicMin(&best[job], bk);
+        if (threadIdx.x == 0 && slice == 0) atomicAdd(&state[2], 1u);
     }
 }
 

@@ -49,7 +49,7 @@ int fail(int code, const char* fmt, ...) {
             return fail(MCL_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-enum { PROF_SIFT_TC = 0, PROF_SIFT_FIX, PROF_ORB, PROF_SURF, PROF_VQ, PROF_SCORE, PROF_LAP, PROF_PREP, PROF_SIFT_SIMT, PROF_VQ_TC, PROF_VQ_RESOLVE, PROF_CHI2, PROF_ORB_FIX, PROF_N };
+enum { PROF_SIFT_TC = 0, PROF_SIFT_FIX, PROF_ORB, PROF_SURF, PROF_VQ, PROF_SCORE, PROF_LAP, PROF_PREP, PROF_SIFT_SIMT, PROF_VQ_TC, PROF_VQ_RESOLVE, PROF_CHI2, PROF_ORB_FIX, PROF_VQ_RESCAN, PROF_N };
 constexpr int QROW_PAD = 384;  // sift_tc4's query block
 
 // growable device scratch buffer (never shrinks; avoids cudaMalloc on the per-frame path)
@@ -420,10 +420,11 @@ extern "C" int mcl_stats(mcl_ctx* c, int64_t out[8]) {
     out[0] = (int64_t)st[0];   // SIFT candidates resolved by the exact fix-up
     out[1] = f[3];             // SIFT whole-image exact rescans
     out[2] = (int64_t)st[1];   // SIFT (frame, image) pairs recomputed by the SIMT kernel after a full candidate list
-    out[3] = f[10];            // BOW rows rescanned over the whole code book (last call)
+    out[3] = f[10];            // BOW rows rescanned over the whole code book
+    out[6] = f[11];            // BOW entries of the sorted resolve list in the last call (rows with two candidate groups count twice)
     out[4] = (int64_t)st[2];   // ORB candidates resolved exactly
     out[5] = (int64_t)st[3];
-    out[6] = out[7] = 0;
+    out[7] = 0;
     return MCL_OK;
 }
 
@@ -1514,41 +1515,54 @@ int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
             // ---- tensor cores: fp16 copy of the query rows, approximate keys per 32-word group, float32 resolve
             using namespace mcl::tc9;
             using namespace mcl::bowtc;
+            {
+                const int rc9 = tc9_prepare(c);
+                if (rc9) return rc9;
+            }
             const int n_qblocks = (n_q + QBLK - 1) / QBLK;
             const int64_t padded = (int64_t)n_qblocks * QBLK;
             const int groups_per_loc = (b->max_words + GROUP - 1) / GROUP;
             const int64_t n_buckets = (int64_t)b->n_loc * groups_per_loc;
-            // work items = (code-book range, location, pair of query blocks): enough ranges to fill the GPU twice
+            // work items = (code-book range, location, pair of query blocks): the number of ranges per location with the
+            // smallest estimated makespan (rounds of items over the co-resident CTA pairs x (tiles per range + pipeline refill))
             const int n_qgroups = (n_qblocks + 1) / 2;
-            int want = (2 * c->sm_count / 2 + b->n_loc * n_qgroups - 1) / (b->n_loc * n_qgroups);
             const mcl_bow::Split* sp = &b->splits.front();
-            for (const auto& cand : b->splits) { sp = &cand; if (cand.n_splits >= want) break; }
+            {
+                const double tiles_per_loc = (double)b->h_tile_off[b->n_loc] / b->n_loc;
+                const int slots = std::max(1, c->tc9_clusters[1] > 0 ? c->tc9_clusters[1] : c->sm_count / 2);
+                double best_cost = 1e300;
+                for (const auto& cand : b->splits) {
+                    const int64_t items = (int64_t)cand.n_chunks * n_qgroups;
+                    const double cost = (double)((items + slots - 1) / slots) * (tiles_per_loc / cand.n_splits + 1.5);
+                    if (cost < best_cost) { best_cost = cost; sp = &cand; }
+                }
+            }
             const int n_splits = sp->n_splits;
             CU(c->bow_q8.ensure((size_t)padded * Shape<KIND_BOW>::ROW_BYTES));
             CU(c->bow_qaux.ensure((size_t)padded * 4));
-            CU(c->bow_tc_out.ensure((size_t)n_splits * nbest * sizeof(int4)));
-            // sort scratch: job_grp[nbest] | sorted[nbest] | queue[nbest] | bucket_cnt[n_buckets]
-            CU(c->bow_sort.ensure((3 * nbest + (size_t)n_buckets) * 4));
-            int* job_grp = c->bow_sort.as<int>();
-            int* sorted = job_grp + nbest;
-            int* queue = sorted + nbest;
+            if (nbest >= ((size_t)1 << 29)) return fail(MCL_EINVAL, "bow: too many (location, row) pairs in one call");
+            CU(c->bow_tc_out.ensure((size_t)n_splits * nbest * 2 * sizeof(int4)));
+            // sort scratch: sorted[3 nbest] (int2) | job_grp[nbest][3] | queue[nbest] | bucket_cnt[n_buckets]
+            CU(c->bow_sort.ensure((10 * nbest + (size_t)n_buckets) * 4));
+            int2* sorted = c->bow_sort.as<int2>();
+            int* job_grp = reinterpret_cast<int*>(sorted + 3 * nbest);
+            int* queue = job_grp + 3 * nbest;
             int* bucket = queue + nbest;
             int* bad = c->flags.as<int>() + 6;
             unsigned int* state = c->flags.as<unsigned int>() + 8;   // [8] queued rows, [9] SIMT flag, [10] rescans
             CU(cudaMemsetAsync(c->bow_q8.p, 0, (size_t)padded * Shape<KIND_BOW>::ROW_BYTES, st));
             CU(cudaMemsetAsync(c->bow_qaux.p, 0xFF, (size_t)padded * 4, st));
-            CU(cudaMemsetAsync(c->bow_tc_out.p, 0, (size_t)n_splits * nbest * sizeof(int4), st));
+            CU(cudaMemsetAsync(c->bow_tc_out.p, 0, (size_t)n_splits * nbest * 2 * sizeof(int4), st));
             CU(cudaMemsetAsync(bucket, 0, (size_t)n_buckets * 4, st));
             CU(cudaMemsetAsync(bad, 0, 4, st));
             CU(cudaMemsetAsync(state, 0, 8, st));
+            CU(cudaMemsetAsync(state + 3, 0, 4, st));
             {
                 ProfScope ps(c, PROF_PREP, st);
                 bow_query_prep_kernel<<<grid_for((int64_t)n_q * 32, 256, c->sm_count * 8), 256, 0, st>>>(
                     d_q, n_q, c->bow_q8.as<uint8_t>(), c->bow_qaux.as<int32_t>(), bad);
             }
             CU(cudaGetLastError());
-            int rc9 = tc9_prepare(c);
-            if (rc9) return rc9;
             Params p = {};
             p.q_rows = c->bow_q8.as<uint8_t>();
             p.q_aux = c->bow_qaux.as<int32_t>();
@@ -1578,10 +1592,15 @@ int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
                 const int g = grid_for((int64_t)nbest, 256, c->sm_count * 8);
                 bow_merge_kernel<<<g, 256, 0, st>>>(c->bow_tc_out.as<int4>(), n_splits, n_q, b->n_loc, groups_per_loc, bad, job_grp,
                                                     bucket, queue, state);
-                bow_scan_kernel<<<1, 1024, 0, st>>>(bucket, (int)n_buckets);
+                bow_scan_kernel<<<1, 1024, 0, st>>>(bucket, (int)n_buckets, state);
                 bow_scatter_kernel<<<g, 256, 0, st>>>(job_grp, n_q, (int64_t)nbest, groups_per_loc, bucket, sorted);
-                bow_resolve_kernel<<<grid_for(((int64_t)nbest + RESOLVE_RUN - 1) / RESOLVE_RUN * 32, 128, c->sm_count * 16), 128, 0, st>>>(
-                    sorted, state, (int64_t)nbest, job_grp, d_q, n_q, b->d_voc, b->d_voc_off, c->bow_best.as<unsigned long long>());
+                // entries per warp: enough warps for ~16 per SM, runs of 8..64 entries
+                const int run_len = (int)std::max<int64_t>(8, std::min<int64_t>(64, (int64_t)nbest / ((int64_t)c->sm_count * 16)));
+                bow_resolve_kernel<<<grid_for((3 * (int64_t)nbest + run_len - 1) / run_len * 32, 128, c->sm_count * 16), 128, 0, st>>>(
+                    sorted, state, run_len, d_q, n_q, b->d_voc, b->d_voc_off, c->bow_best.as<unsigned long long>());
+            }
+            {
+                ProfScope ps(c, PROF_VQ_RESCAN, st);
                 bow_decide_kernel<<<1, 1, 0, st>>>(bad, (int64_t)nbest, state);
                 bow_rescan_kernel<<<c->sm_count * 8, 256, 0, st>>>(queue, d_q, n_q, b->d_voc, b->d_voc_off,
                                                                   c->bow_best.as<unsigned long long>(), state);

@@ -13,10 +13,10 @@
 //             both kinds share the 3-input integer max tree.  tcgen05.mma kind::f16, 8 + 1 k-steps of 16.  The approximate
 //             keys only select a 32-word group; bow_resolve_kernel then evaluates that group in float32 exactly as before.
 //
-// Pipeline (per CTA, persistent): TWO query tiles of 128 rows stationary in TENSOR MEMORY (72 columns each: row = lane, 4
-// K-bytes per column), two 128-column accumulators (one per query tile, single buffered: while the epilogue warps drain one,
-// the tensor pipe fills the other -- 8-9 MMAs of 64 cycles each, twice sift_tc4's time per tile, so two tiles suffice where
-// sift_tc4 needs three), 128-row map tiles (two SWIZZLE_128B atoms of 16 KB + a 4 KB no-swizzle extension slice) streamed by
+// Pipeline (per CTA, persistent): TWO query tiles of 128 rows stationary in TENSOR MEMORY (64 / 72 columns each: row = lane,
+// 4 K-bytes per column), 128-column accumulators in the rest (BOW: two, one per query tile -- while the epilogue warps drain
+// one, the tensor pipe fills the other, 8-9 MMAs of 64 cycles each, twice sift_tc4's time per tile, so two tiles suffice where
+// sift_tc4 needs three; ORB: three, taken round robin, which first measured 78 % -> see DESIGN.md), 128-row map tiles (two SWIZZLE_128B atoms of 16 KB + a 4 KB no-swizzle extension slice) streamed by
 // ONE linear bulk copy each into a 4-stage ring; CTA pairs (clusters of 2) fetch every tile once and multicast it.
 // Warps 0-7: epilogue (query tile = warp / 4, TMEM lane quadrant = warp % 4), warp 8: TMA producer, warp 9: MMA issuer.
 // Epilogue per 128 x 128 tile and thread: two tcgen05.ld.x64, four 32-column max trees, top-2 over GROUP maxima with the
@@ -24,7 +24,7 @@
 //   ORB, end of an image: best key H1 is exact; the second best is >= H2 (the best other group); a row whose ratio test
 //        fails with (H1, H2) fails with the true second best too and is dropped; the others go to a candidate list and
 //        orb_fixup_kernel recomputes the 32 rows of the best group with xor + popc on the packed descriptors.
-//   BOW, end of a code-book range: (best group, its key, best key of the other groups) per (range, location, row).
+//   BOW, end of a code-book range: (the three best groups, their keys, the fourth-best key) per (range, location, row).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -45,8 +45,6 @@ constexpr int ATILES = 2;
 constexpr int QBLK = ATILES * QTILE;          // 256 query rows per work item
 constexpr int ATOM_BYTES = TILE_N * 128;      // 16 KB: 128 rows x 128 K-bytes, SWIZZLE_128B
 constexpr int EXT_BYTES = TILE_N * 32;        // 4 KB: 128 rows x 32 K-bytes, no swizzle (8 x 16 B core matrices, LBO 128, SBO 256)
-constexpr int A_COLS = 72;                    // TMEM columns per query tile: 288 bytes per row
-constexpr int ACC_COL0 = 256;
 constexpr int B_STAGES = 4;
 constexpr int EPI_WARPS = ATILES * 4;
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
@@ -54,8 +52,12 @@ constexpr int TMEM_COLS = 512;
 constexpr int META_CAP = 1024;                // tile records staged per chunk (32 KB)
 
 template <int KIND> struct Shape;
-template <> struct Shape<KIND_ORB> { static constexpr int KSTEPS = 8, TILE_BYTES = 2 * ATOM_BYTES, ROW_BYTES = 256; };
-template <> struct Shape<KIND_BOW> { static constexpr int KSTEPS = 9, TILE_BYTES = 2 * ATOM_BYTES + EXT_BYTES, ROW_BYTES = 288; };
+// A_COLS: TMEM columns per query tile (4 K-bytes per column).  ACCS accumulators of 128 columns fill the rest of the 512
+// columns: ORB has room for three, used round robin by the two query tiles (one spare: the MMAs of a tile need not wait for
+// the epilogue of the tile before last), BOW for two.
+template <> struct Shape<KIND_ORB> { static constexpr int KSTEPS = 8, TILE_BYTES = 2 * ATOM_BYTES, ROW_BYTES = 256, A_COLS = 64, ACCS = 3; };
+template <> struct Shape<KIND_BOW> { static constexpr int KSTEPS = 9, TILE_BYTES = 2 * ATOM_BYTES + EXT_BYTES, ROW_BYTES = 288, A_COLS = 72, ACCS = 2; };
+constexpr int MAX_ACCS = 3;
 
 // per 128-row map tile
 struct TileRec {
@@ -86,7 +88,7 @@ struct Params {
     int n_images;
     int q_row_base;
     // BOW outputs
-    int4* out;                // [n_splits][n_loc][n_q]: {best group, its key bits, best key bits of the other groups, -}
+    int4* out;                // [n_splits][n_loc][n_q][2]: {the three best groups, -}, {their key bits, fourth-best key bits}
     int n_q, n_loc;
     int meta_cap;
 };
@@ -97,7 +99,7 @@ struct Smem {
     alignas(16) TileRec rec[META_CAP];
     alignas(8) uint64_t b_full[B_STAGES];
     uint64_t b_empty[B_STAGES];
-    uint64_t acc_full[ATILES], acc_empty[ATILES];
+    uint64_t acc_full[MAX_ACCS], acc_empty[MAX_ACCS];
     uint64_t a_full, a_free;
     uint32_t tmem_base;
 };
@@ -122,6 +124,8 @@ __device__ __forceinline__ void mask_group(uint32_t (&v)[32], int nv) {
 template <int KIND, int CL>
 __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__ Params p) {
     using S = Shape<KIND>;
+    constexpr int A_COLS = S::A_COLS, ACCS = S::ACCS, ACC_COL0 = TMEM_COLS - ACCS * TILE_N;
+    static_assert(ATILES * A_COLS <= ACC_COL0, "query tiles and accumulators overlap in tensor memory");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     Smem<KIND>& s = *reinterpret_cast<Smem<KIND>*>(smem_raw);
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < B_STAGES; ++i) { mbar_init(&s.b_full[i], 1); mbar_init(&s.b_empty[i], CL); }
-        for (int a = 0; a < ATILES; ++a) { mbar_init(&s.acc_full[a], 1); mbar_init(&s.acc_empty[a], 4); }
+        for (int a = 0; a < MAX_ACCS; ++a) { mbar_init(&s.acc_full[a], 1); mbar_init(&s.acc_empty[a], 4); }
         mbar_init(&s.a_full, EPI_WARPS);
         mbar_init(&s.a_free, 1);
         mbar_fence_init();
@@ -184,9 +188,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                 const uint64_t de = umma_desc_noswizzle(sb + 2 * ATOM_BYTES, 128, 256);
 #pragma unroll
                 for (int a = 0; a < ATILES; ++a) {
-                    mbar_wait(&s.acc_empty[a], (bn & 1) ^ 1);
+                    // the n-th (tile, query tile) product of this CTA goes to accumulator n mod ACCS
+                    const uint32_t n = ATILES * bn + a, x = n % ACCS, use = n / ACCS;
+                    mbar_wait(&s.acc_empty[x], (use & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t d = tmem_base + ACC_COL0 + a * TILE_N;
+                    const uint32_t d = tmem_base + ACC_COL0 + x * TILE_N;
                     const uint32_t ta = tmem_base + a * A_COLS;
 #pragma unroll
                     for (int k = 0; k < S::KSTEPS; ++k) {
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                         if (KIND == KIND_ORB) umma_i8_ts_if(leader, d, ta + 8 * k, bd, idesc, k > 0);
                         else umma_f16_ts_if(leader, d, ta + 8 * k, bd, idesc, k > 0);
                     }
-                    tc_commit_if(leader, &s.acc_full[a]);
+                    tc_commit_if(leader, &s.acc_full[x]);
                 }
                 if (CL == 1) tc_commit_if(leader, &s.b_empty[bs]);
                 else tc_commit_multicast_if(leader, &s.b_empty[bs], ALL_CTAS);
@@ -241,11 +247,23 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                 if (lane == 0) mbar_arrive(&s.a_full);
             }
             const bool row_valid = p.q_aux[qrow] >= 0 && qb_raw < p.n_qblocks;
-            int H1 = NONE, H2 = NONE, pos = 0;
+            // running top keys over the GROUP maxima of the current segment: ORB keeps the best group and the best key of the
+            // others; BOW keeps the THREE best groups and the fourth-best key (a near-tie between up to three groups is then
+            // resolved inside those groups instead of over the whole code book)
+            int H1 = NONE, H2 = NONE, H3 = NONE, H4 = NONE, pos = 0, pos2 = 0, pos3 = 0;
             auto join = [&](int gm, int id) {
-                const bool better = gm > H1;
-                H2 = max(H2, better ? H1 : gm);
-                pos = better ? id : pos;
+                const bool g1 = gm > H1;
+                if (KIND == KIND_BOW) {
+                    const bool g2 = gm > H2, g3 = gm > H3;
+                    H4 = max(H4, g3 ? H3 : gm);
+                    H3 = g2 ? H2 : (g3 ? gm : H3);
+                    pos3 = g2 ? pos2 : (g3 ? id : pos3);
+                    H2 = g1 ? H1 : (g2 ? gm : H2);
+                    pos2 = g1 ? pos : (g2 ? id : pos2);
+                } else {
+                    H2 = max(H2, g1 ? H1 : gm);
+                }
+                pos = g1 ? id : pos;
                 H1 = max(H1, gm);
             };
             // the chunk's tile records, staged once per work item (named barrier 1 among the epilogue warps)
@@ -294,17 +312,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                     }
                 } else {
                     // ch.img_begin = location, ch.img_end = index of this code-book range among the location's splits
-                    if (row_valid) p.out[((size_t)ch.img_end * p.n_loc + ch.img_begin) * p.n_q + (p.q_row_base + qrow)] = make_int4(pos, H1, H2, 0);
+                    if (row_valid) {
+                        int4* o = p.out + 2 * (((size_t)ch.img_end * p.n_loc + ch.img_begin) * p.n_q + (p.q_row_base + qrow));
+                        o[0] = make_int4(pos, pos2, pos3, 0);
+                        o[1] = make_int4(H1, H2, H3, H4);
+                    }
                 }
-                H1 = NONE; H2 = NONE;
+                H1 = NONE; H2 = NONE; H3 = NONE; H4 = NONE;
             };
 #pragma unroll 1
             for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
                 const int ri = (t - ch.tile_begin) * 2;
                 const int4 r0 = ldrec(ri), r1 = ldrec(ri + 1);   // r0 = seg[4]; r1 = {nvalid, end_mask, plain, first_group}
-                mbar_wait(&s.acc_full[atile], bn & 1);
+                const uint32_t n = ATILES * bn + atile, x = n % ACCS, use = n / ACCS;
+                mbar_wait(&s.acc_full[x], use & 1);
                 tc_fence_after();
-                const uint32_t tcol = t_lane + ACC_COL0 + atile * TILE_N;
+                const uint32_t tcol = t_lane + ACC_COL0 + x * TILE_N;
                 uint32_t v[2][32];
                 tmem_ld64(tcol, reinterpret_cast<uint32_t(&)[64]>(v));
                 tmem_wait_all();
@@ -317,7 +340,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                 tmem_wait_all();
                 tmem_fence_regs(v[0]);
                 tmem_fence_regs(v[1]);
-                if (lane == 0) mbar_arrive(&s.acc_empty[atile]);   // both halves are out of tensor memory: the accumulator is free
+                if (lane == 0) mbar_arrive(&s.acc_empty[x]);   // both halves are out of tensor memory: the accumulator is free
                 if (!plain) { mask_group(v[0], (r1.x >> 16) & 255); mask_group(v[1], (r1.x >> 24) & 255); }
                 const int g2 = sifttc3::group_max<0>(v[0]), g3 = sifttc3::group_max<0>(v[1]);
                 // group position: ORB = padded row / 32 over the whole map; BOW = group index within the location
