@@ -11,7 +11,7 @@
   itself); --scaling strong keeps config 3's 3200 images in total and splits them over the N ranks.
 --workload bow (BASELINE config 5): 256 locations x 100 images, 10 000 visual words per location, sharded by location
   (32 per GPU, weak); one step = 50 frames x 300 descriptors assigned to words and scored against every location;
-  a unit is one (frame, location) pair.
+  a unit is one (query frame, map image) tf-idf score (bench_other.py).
 --workload orb (BASELINE config 1's shape as a batch): 200 frames x 400 images x 500 ORB descriptors.
 
   value         inputs resident in HBM: the product's sharded path (engine.ShardedMap.match_counts_device: this rank's kernels +
@@ -487,13 +487,17 @@ def run_sift(args, H):
 def main():
     args = parse()
     if args.impl == "reference":
-        run_reference(args)
+        if args.workload == "sift":
+            run_reference(args)
+        else:
+            import bench_other
+            getattr(bench_other, "run_" + args.workload)(args, None, ClockSampler, peaks)
         return
     H = Harness(args)
     if args.workload == "sift":
         run_sift(args, H)
     else:
-        from pymcl_b200 import bench_other
+        import bench_other
         getattr(bench_other, "run_" + args.workload)(args, H, ClockSampler, peaks)
     H.finish()
 

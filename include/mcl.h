@@ -182,7 +182,8 @@ int mcl_chi2(mcl_ctx* ctx, int n_q, int n_map, int bins, const float* q_hist, co
 /* ---- roofline denominators ------------------------------------------------------------------------------
  * MEASURED_PEAKS.json carries HBM GB/s and bf16 TFLOP/s only; the hot path is bounded by the int8 tensor pipe
  * (SIFT) and the popc pipe (ORB).  which: 0 = tcgen05 kind::i8 128x128x32 MMAs issued back to back from shared
- * memory on every SM (out[0] = int8 ops/s, 2 per MAC), 1 = XOR+popc.b32 issue rate (out[0] = popc32 results/s).
+ * memory on every SM (out[0] = int8 ops/s, 2 per MAC), 1 = XOR+popc.b32 issue rate (out[0] = popc32 results/s), 2 = fp32
+ * (a - b)^2 accumulation, one FADD + one FFMA per element as in SURF's direct-difference distance (out[0] = elements/s).
  * out[1] = elapsed milliseconds.  No reference counterpart (SURVEY.md section 8d asks for these). */
 int mcl_microbench(mcl_ctx* ctx, int which, int iters, double* out);
 

@@ -30,7 +30,9 @@ def build(force=False, verbose=False):
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, os.path.join(CSRC, "mcl.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr[-4000:]))
+        # with -Xptxas -v the tail of stderr is resource usage: show the diagnostics, not the last 4000 characters
+        lines = [l for l in r.stderr.splitlines() if not l.startswith("ptxas info") and "bytes stack frame" not in l]
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), "\n".join(lines)[-6000:]))
     if verbose:
         print(r.stderr)
     return OUT

@@ -104,6 +104,7 @@ struct mcl_ctx {
     int opt[8] = {0};  // mcl_set_option: [0] = sift_tc4 diagnostic mode
     int max_clusters2 = 0;          // co-resident sift_tc4 clusters of 2 CTAs
     int bow_score_smem = 0;         // dynamic shared memory opt-in of bow_score_kernel so far
+    int64_t active_pairs_hint = -1; // (frame, image) pairs a host DOR mask leaves active, for the launch shape of small problems
     std::map<int64_t, LapPlan> lap_plans;   // by pixel count
     // free list of device blocks for the query batches of mcl_queries_create_device: the per-step batches of the multi-GPU
     // driver come and go with the same few sizes, and cudaMalloc / cudaFree (which synchronises the device) cost more than
@@ -1166,8 +1167,18 @@ int match_device(mcl_map* m, mcl_queries* q, int mode, double ratio, const uint8
             } else {  // SURF
                 if (mode != MCL_KNN2_RATIO) return fail(MCL_EINVAL, "SURF supports mode MCL_KNN2_RATIO only");
                 ProfScope ps(c, PROF_SURF, st);
-                mcl::surf_knn_kernel<<<grid, bt, 0, st>>>((const float4*)q->d_desc, q->d_off, (const float4*)m->d_desc,
-                                                           m->d_src_off, ni, ratio, d_mask, d_counts);
+                // few (frame, image, row block) CTAs -- a DOR step -- : cut every map image into row slices, one 128-thread
+                // group each, until there are ~8 warps per scheduler; plenty of CTAs: one thread per query row
+                const int64_t pairs = (d_mask && c->active_pairs_hint >= 0) ? std::max<int64_t>(1, c->active_pairs_hint) : (int64_t)ni * nf;
+                const int64_t blocks128 = pairs * ((max_q + 127) / 128);
+                int S = 1;
+                while (S < 4 && blocks128 * S * 4 < (int64_t)c->sm_count * 32 && m->max_rows_per_image >= 64 * S) S *= 2;   // 8 slices = 1024 threads = 64 registers: spills
+                dim3 grid128(ni, nf, (unsigned)std::max<int64_t>(1, (max_q + 127) / 128));
+                const float4* qd = (const float4*)q->d_desc;
+                const float4* md = (const float4*)m->d_desc;
+                if (S == 4) mcl::surf_knn_sliced_kernel<4><<<grid128, 512, 0, st>>>(qd, q->d_off, md, m->d_src_off, ni, ratio, d_mask, d_counts);
+                else if (S == 2) mcl::surf_knn_sliced_kernel<2><<<grid128, 256, 0, st>>>(qd, q->d_off, md, m->d_src_off, ni, ratio, d_mask, d_counts);
+                else mcl::surf_knn_kernel<<<grid, bt, 0, st>>>(qd, q->d_off, md, m->d_src_off, ni, ratio, d_mask, d_counts);
             }
             CU(cudaGetLastError());
         }
@@ -1345,7 +1356,14 @@ extern "C" int mcl_match_counts(mcl_map* m, int n_queries, const int64_t* q_row_
             CU(cudaMemcpyAsync(c->tmp_mask.p, mask, n_out, cudaMemcpyHostToDevice, st));
             d_mask = c->tmp_mask.as<uint8_t>();
         }
+        c->active_pairs_hint = -1;
+        if (mask) {
+            int64_t act = 0;
+            for (size_t i = 0; i < n_out; ++i) act += mask[i] != 0;
+            c->active_pairs_hint = act;
+        }
         int r = match_device(m, q, mode, ratio, d_mask, fill_value, algo, c->tmp_counts.as<int32_t>(), st);
+        c->active_pairs_hint = -1;
         if (r) return r;
         CU(cudaMemcpyAsync(out_counts, c->tmp_counts.p, n_out * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -2083,6 +2101,12 @@ extern "C" int mcl_microbench(mcl_ctx* c, int which, int iters, double* out /* [
         mcl::popc_peak_kernel<<<c->sm_count * 8, 256, 0, st>>>(iters, c->stage.as<int>());
         CU(cudaEventRecord(b, st));
         ops = 16.0 * (double)iters * 256.0 * c->sm_count * 8;  // popc32 results
+    } else if (which == 2) {  // fp32 FADD + FFMA pairs (SURF's direct-difference form): issue rate of the FMA pipe
+        mcl::ffma_peak_kernel<<<c->sm_count * 8, 256, 0, st>>>(iters / 8 + 1, c->stage.as<int>());
+        CU(cudaEventRecord(a, st));
+        mcl::ffma_peak_kernel<<<c->sm_count * 8, 256, 0, st>>>(iters, c->stage.as<int>());
+        CU(cudaEventRecord(b, st));
+        ops = 16.0 * (double)iters * 256.0 * c->sm_count * 8;  // (FADD, FFMA) element pairs
     } else if (which >= 50 && which < 60) {  // development probe: integer-pipe issue rates, which = 50 + OP
         void (*k)(int, int*) = nullptr;
         switch (which - 50) {
@@ -2118,7 +2142,7 @@ extern "C" int mcl_microbench(mcl_ctx* c, int which, int iters, double* out /* [
         CU(cudaEventRecord(b, st));
         ops = 2.0 * 128 * n * 32 * 15.0 * (double)iters * c->sm_count;
     } else {
-        return fail(MCL_EINVAL, "mcl_microbench: which must be 0 (int8 tensor) or 1 (popc)");
+        return fail(MCL_EINVAL, "mcl_microbench: which must be 0 (int8 tensor), 1 (popc) or 2 (fp32 difference-square pairs)");
     }
     c->launches += 2;
     CU(cudaGetLastError());

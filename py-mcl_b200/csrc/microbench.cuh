@@ -161,4 +161,28 @@ __global__ void __launch_bounds__(256) popc_peak_kernel(int iters, int* __restri
     if (s == 0x7fffffff) sink[0] = s;
 }
 
+// fp32 issue rate for the direct-difference form SURF uses: one FADD (a - b) and one FFMA (d * d + s) per element, 16
+// independent chains per thread.  out: element pairs (FADD + FFMA) per second.
+__global__ void __launch_bounds__(256) ffma_peak_kernel(int iters, int* __restrict__ sink) {
+    float a[16], s[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        a[i] = (float)(threadIdx.x + i) * 1e-3f;
+        s[i] = 0.f;
+    }
+    float b = (float)blockIdx.x * 1e-4f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float d = a[i] - b;
+            s[i] = fmaf(d, d, s[i]);
+        }
+        b += 1e-6f;
+    }
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += s[i];
+    if (t == 123.456f) sink[0] = 1;
+}
+
 }  // namespace mcl

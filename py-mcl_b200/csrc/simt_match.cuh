@@ -237,4 +237,68 @@ __global__ void __launch_bounds__(128) surf_knn_kernel(
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&counts[(int64_t)frame * n_images + img], __popc(bal));
 }
 
+// The same arithmetic with the map image cut into S slices of rows, each scanned by its own group of 128 threads
+// (thread = (query row, slice)); the S partial top-2 pairs of a query row are merged through shared memory.  A DOR step is one
+// frame against <= 30 images (BASELINE config 4: 30 x 1024 query rows = 240 warps for 148 SMs): the slices are what fills the
+// GPU there (0.41 -> see DESIGN.md).  The per-row sums are formed exactly as in surf_knn_kernel, so counts are identical.
+// grid = (n_images, n_frames, row blocks of 128), block = 128 * S.
+constexpr int SURF_SLICE_STAGE = 16;   // rows staged per slice and pass (4 slices x 16 rows x 256 B = 16 KB of static shared memory)
+
+template <int S>
+__global__ void __launch_bounds__(128 * S) surf_knn_sliced_kernel(
+    const float4* __restrict__ q_desc, const int64_t* __restrict__ q_off, const float4* __restrict__ m_desc,
+    const int64_t* __restrict__ m_off, int n_images, double ratio, const uint8_t* __restrict__ mask,
+    int32_t* __restrict__ counts) {
+    const int img = blockIdx.x, frame = blockIdx.y;
+    if (mask && !mask[(int64_t)frame * n_images + img]) return;
+    __shared__ float4 sm[S][SURF_SLICE_STAGE][16];
+    __shared__ float2 part[S][128];
+    const int64_t q0 = q_off[frame], q1 = q_off[frame + 1];
+    const int64_t m0 = m_off[img];
+    const int nm_rows = (int)(m_off[img + 1] - m0);
+    if (nm_rows < 2) return;
+    if (q0 + (int64_t)blockIdx.z * 128 >= q1) return;
+    const int qr = threadIdx.x & 127, sl = threadIdx.x >> 7;
+    const int64_t qrow = q0 + (int64_t)blockIdx.z * 128 + qr;
+    const bool active = qrow < q1;
+    float4 a[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) a[c] = active ? q_desc[qrow * 16 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int per = (nm_rows + S - 1) / S;                    // rows per slice
+    const int lo = min(nm_rows, sl * per), hi = min(nm_rows, lo + per);
+    float best = INFINITY, second = INFINITY;
+    for (int base = 0; base < per; base += SURF_SLICE_STAGE) {   // every slice runs the same number of passes (block-wide barriers)
+        const int r0 = lo + base;
+        const int nrow = max(0, min(SURF_SLICE_STAGE, hi - r0));
+        __syncthreads();
+        for (int i = qr; i < nrow * 16; i += 128) sm[sl][i >> 4][i & 15] = m_desc[(m0 + r0) * 16 + i];
+        __syncthreads();
+        for (int r = 0; r < nrow; ++r) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float4 b = sm[sl][r][c];
+                const float dx = a[c].x - b.x, dy = a[c].y - b.y, dz = a[c].z - b.z, dw = a[c].w - b.w;
+                s0 = fmaf(dx, dx, s0); s1 = fmaf(dy, dy, s1); s2 = fmaf(dz, dz, s2); s3 = fmaf(dw, dw, s3);
+            }
+            const float d = (s0 + s1) + (s2 + s3);
+            second = fminf(second, fmaxf(best, d));
+            best = fminf(best, d);
+        }
+    }
+    part[sl][qr] = make_float2(best, second);
+    __syncthreads();
+    if (sl != 0) return;
+#pragma unroll
+    for (int k = 1; k < S; ++k) {   // two smallest (with multiplicity) of the union of the slices' pairs
+        const float2 o = part[k][qr];
+        second = fminf(fminf(second, o.y), fmaxf(best, o.x));
+        best = fminf(best, o.x);
+    }
+    const float f0 = __fsqrt_rn(best), f1 = __fsqrt_rn(second);
+    const bool pass = active && ((double)f0 < __dmul_rn(ratio, (double)f1));
+    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&counts[(int64_t)frame * n_images + img], __popc(bal));
+}
+
 }  // namespace mcl

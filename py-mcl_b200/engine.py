@@ -32,6 +32,12 @@ def shard_bounds(rows_per_image, world):
     return [(int(edges[r]), int(edges[r + 1])) for r in range(world)]
 
 
+def _stream_handle(stream):
+    """cudaStream_t of a torch stream for libmcl's *_device calls.  torch's default stream has handle 0, which those calls read
+    as "the context's own stream" (not ordered with torch's work): cudaStreamLegacy (0x1) names the default stream explicitly."""
+    return stream.cuda_stream or 1
+
+
 def _dist():
     # a process that never imported torch cannot have initialised torch.distributed: do not pay the import (seconds) for it
     if "torch" not in sys.modules and "WORLD_SIZE" not in os.environ:
@@ -156,7 +162,7 @@ class ShardedMap(object):
         if w:
             self.local.match_counts_device(queries, tight.data_ptr(), mode=mode, ratio=ratio,
                                            d_mask_ptr=d_mask.data_ptr() if d_mask is not None else None, fill_value=fill_value,
-                                           algo=algo, stream=stream.cuda_stream)
+                                           algo=algo, stream=_stream_handle(stream))
             if tight is not mine:
                 mine[:, :w].copy_(tight)
         if self.world == 1:
@@ -217,10 +223,17 @@ class ShardedMap(object):
             side.wait_stream(main)
             events = []
             with torch.cuda.stream(side):
-                for f0, f1, runs in plan:
+                for pi, (f0, f1, runs) in enumerate(plan):
+                    # every rank's run lands in its slot of one (world, longest run, row) buffer: this rank's straight from
+                    # the host, the others' by ONE in-place all_gather_into_tensor; the runs are then packed back to back
+                    # (device copies) so that the part is one contiguous batch
+                    maxrun = max(y - x for x, y in runs)
+                    g = self._buf("gather%d" % pi, (self.world, maxrun, row_elems), tdt)
                     a, b = runs[self.rank]
-                    dq[a:b].copy_(src[a:b], non_blocking=True)
-                    d.all_gather([dq[x:y] for x, y in runs], dq[a:b], group=self.group)
+                    g[self.rank, :b - a].copy_(src[a:b], non_blocking=True)
+                    d.all_gather_into_tensor(g.view(self.world * maxrun, row_elems), g[self.rank], group=self.group)
+                    for r, (x, y) in enumerate(runs):
+                        dq[x:y].copy_(g[r, :y - x], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(side)
                     events.append(ev)
@@ -231,7 +244,7 @@ class ShardedMap(object):
                 main.wait_event(ev)
             r0 = int(off[f0])
             q = _lib.QueryBatch(self.local.ctx, self.local.kind,
-                                device=(off[f0:f1 + 1] - r0, dq.data_ptr() + r0 * row_elems * cat.dtype.itemsize, code, main.cuda_stream))
+                                device=(off[f0:f1 + 1] - r0, dq.data_ptr() + r0 * row_elems * cat.dtype.itemsize, code, _stream_handle(main)))
             batches.append(q)
             part = self.match_counts_device(q, mode=mode, ratio=ratio, d_mask=None if d_mask is None else d_mask[f0:f1],
                                             fill_value=fill_value, algo=algo)
@@ -357,6 +370,33 @@ class ShardedBow(object):
         assert local.shape[1] == hi - lo
         return gather_columns(local, self.bounds, self.group)
 
+    def score_device(self, queries):
+        """Resident query batch (a _lib.QueryBatch of kind BOWQ on this rank's context) -> torch float32 tensor
+        (world, n_queries, widest rank's images) on the device, valid on the current torch stream: this rank's kernels + the
+        device all-gather (rank r's scores are [r, :, :bounds[r][1] - bounds[r][0]]); nothing touches the host."""
+        import torch
+        d = _dist()
+        F = queries.n_queries
+        lo, hi = self.bounds[self.rank]
+        w = hi - lo
+        maxw = max(h - l for l, h in self.bounds)
+        key = (F, maxw)
+        if getattr(self, "_key", None) != key:
+            self._mine = torch.zeros((F, maxw), dtype=torch.float32, device="cuda")
+            self._tight = self._mine if w == maxw else torch.zeros((F, max(w, 1)), dtype=torch.float32, device="cuda")
+            self._all = torch.empty((self.world, F, maxw), dtype=torch.float32, device="cuda")
+            self._host = torch.empty((self.world, F, maxw), dtype=torch.float32).pin_memory()
+            self._key = key
+        stream = torch.cuda.current_stream()
+        if self.local is not None and w:
+            self.local.score_device(queries, self._tight.data_ptr(), stream=_stream_handle(stream))
+            if self._tight is not self._mine:
+                self._mine[:, :w].copy_(self._tight[:, :w])
+        if self.world == 1:
+            return self._mine[None]
+        d.all_gather_into_tensor(self._all, self._mine, group=self.group)
+        return self._all
+
     def _score_nccl(self, q_descs):
         import torch
         d = _dist()
@@ -375,7 +415,7 @@ class ShardedBow(object):
         q = None
         if self.local is not None and w:
             q = _lib.QueryBatch(self.local.ctx, _lib.BOWQ, q_descs)
-            self.local.score_device(q, self._tight.data_ptr(), stream=stream.cuda_stream)
+            self.local.score_device(q, self._tight.data_ptr(), stream=_stream_handle(stream))
             if self._tight is not self._mine:
                 self._mine[:, :w].copy_(self._tight[:, :w])
         d.all_gather_into_tensor(self._all, self._mine, group=self.group)

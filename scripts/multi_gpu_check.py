@@ -106,18 +106,28 @@ except _lib.MclError:
     rejected = True
 omap = [synth.orb_like(rng, int(n)) for n in rng.integers(100, 600, size=13)]
 oq = [synth.orb_like(rng, 500) for _ in range(5)]
-oq[1][:150] = synth.orb_flip(rng, omap[4][:150], 25)
+n_pl = min(150, len(omap[4]))
+oq[1][:n_pl] = synth.orb_flip(rng, omap[4][:n_pl], 25)
 so = ShardedMap("ORB", omap, ctx=ctx)
 got_orb = [so.match_counts(oq, mode=m) for m in (_lib.KNN2_RATIO, _lib.CROSSCHECK)]
 if rank == 0:
     whole = _lib.MapIndex(ctx, "SIFT", map_des)
     want_big = whole.match_counts(frames)
-    ok = (np.array_equal(got_big, want_big) and got_big[0, 0] >= 150 and
-          np.array_equal(got_small, np.where(mask > 0, want_big[:3], 1)) and np.array_equal(got_dev, want_big[:9]) and rejected)
+    checks = {"big": np.array_equal(got_big, want_big), "planted": bool(got_big[0, 0] >= 150),
+              "small_masked": np.array_equal(got_small, np.where(mask > 0, want_big[:3], 1)),
+              "resident": np.array_equal(got_dev, want_big[:9]), "rejected": rejected}
+    ok = all(checks.values())
+    if not ok:
+        print("sharded checks:", checks, "differing cells (big):", int((got_big != want_big).sum()), "of", got_big.size,
+              "first rows got", got_big[:2].tolist(), "want", want_big[:2].tolist())
     whole.close()
     print("MULTI_GPU_SHARDED_UPLOAD_OK" if ok else "MULTI_GPU_SHARDED_UPLOAD_MISMATCH", "shards", sm.bounds)
     wo = _lib.MapIndex(ctx, "ORB", omap)
-    ok = all(np.array_equal(g, wo.match_counts(oq, mode=m)) for g, m in zip(got_orb, (_lib.KNN2_RATIO, _lib.CROSSCHECK)))
+    want_orb = [wo.match_counts(oq, mode=m) for m in (_lib.KNN2_RATIO, _lib.CROSSCHECK)]
+    ok = all(np.array_equal(g, w) for g, w in zip(got_orb, want_orb))
+    if not ok:
+        print("orb:", [(int((g != w).sum()), g.shape, w.shape) for g, w in zip(got_orb, want_orb)], "shards", so.bounds,
+              "got", got_orb[1][:2].tolist(), "want", want_orb[1][:2].tolist())
     wo.close()
     print("MULTI_GPU_ORB_OK" if ok else "MULTI_GPU_ORB_MISMATCH")
 sm.close()

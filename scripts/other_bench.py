@@ -96,12 +96,17 @@ if "surf" in names:   # cfg4 shape: 1024 x 1024 x 64 f32, one frame vs 30 images
     q = synth.surf_like(rng, 1024)
     m = _lib.MapIndex(ctx, "SURF", map_des)
     mask = np.zeros((1, 175), np.uint8); mask[0, :30] = 1
-    for tag, kw, n in (("175 images", {}, 175), ("30 of 175 (DOR mask)", {"mask": mask}, 30)):
-        e2e = timeit(lambda: m.match_counts([q], **kw), reps=20)
-        k_ms = prof(lambda: m.match_counts([q], **kw), "surf", reps=20)
-        flop = 3.0 * 1024 * 1024 * 64 * n
-        out.append({"config": "cfg4 SURF 1 frame vs " + tag, "e2e_ms": e2e * 1e3, "kernel_ms": k_ms,
-                    "tflops": flop / (k_ms * 1e-3) / 1e12, "pairs_per_s_e2e": n / e2e})
+    pair_peak, _ = ctx.microbench(2, 20000)     # (FADD, FFMA) element pairs per second: the direct-difference form's bound
+    frames40 = [synth.surf_like(rng, 1024) for _ in range(40)]
+    for tag, kw, n, qq in (("175 images", {}, 175, [q]), ("30 of 175 (DOR mask)", {"mask": mask}, 30, [q]),
+                           ("40 frames x 175 images (throughput shape)", {}, 175 * 40, frames40)):
+        e2e = timeit(lambda: m.match_counts(qq, **kw), reps=20 if len(qq) == 1 else 3)
+        k_ms = prof(lambda: m.match_counts(qq, **kw), "surf", reps=20 if len(qq) == 1 else 3)
+        elems = 1024.0 * 1024 * 64 * n
+        out.append({"config": "cfg4 SURF 1024x1024x64: " + tag, "e2e_ms": e2e * 1e3, "kernel_ms": k_ms,
+                    "tflops_at_3_flop_per_element": 3.0 * elems / (k_ms * 1e-3) / 1e12,
+                    "element_pairs_per_s": elems / (k_ms * 1e-3), "fp32_pair_peak_measured": pair_peak,
+                    "frac_of_fp32_peak": elems / (k_ms * 1e-3) / pair_peak, "pairs_per_s_e2e": n / e2e})
     import cv2
     cpu = cpu_rate(lambda: [oracle.cv2_l2_pair_count(q, d) for d in map_des[:10]], 3.0) * 10
     out[-1]["cpu_pairs_per_s"] = cpu
