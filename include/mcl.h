@@ -140,12 +140,17 @@ int mcl_kmeans(mcl_ctx* ctx, int64_t n, const void* obs, int obs_dtype, int k, c
 
 /* ---- small stages --------------------------------------------------------------------------------------
  * mcl_laplacian_var: analyzer.Laplacian (analyze.py:441-445) for n grayscale u8 images (host pointers,
- * row stride in bytes): out[i] = cv2.Laplacian(img, CV_64F).var().
+ * row stride in bytes): out[i] = cv2.Laplacian(img, CV_64F).var(), bit for bit: numpy's two-pass variance with its pairwise
+ * summation order (csrc/lap_var.cuh).
  * mcl_laplacian_sums: the exact integer sums behind it, sums[2i] = sum L, sums[2i+1] = sum L^2. */
 int mcl_laplacian_var(mcl_ctx* ctx, int n, const uint8_t* const* imgs, const int* h, const int* w,
                       const int* stride, double* out);
 int mcl_laplacian_sums(mcl_ctx* ctx, int n, const uint8_t* const* imgs, const int* h, const int* w,
                        const int* stride, int64_t* sums);
+/* mcl_laplacian_var for images the caller has already packed the way the device keeps them -- every row padded to a
+ * multiple of 16 bytes, image i at byte offset sum_{j<i} h[j] * ((w[j] + 15) & ~15) -- in ONE (ideally pinned, mcl_host_alloc)
+ * host buffer: one host-to-device copy instead of one strided copy per image (analyze.py:441-445 for a whole sequence). */
+int mcl_laplacian_var_packed(mcl_ctx* ctx, int n, const uint8_t* packed, const int* h, const int* w, double* out);
 /* mcl_filter_step: one frame of analyzer.processRaw (analyze.py:119-134).  `stages` selects which of the
  * reference's steps run, in this order:
  *   MCL_F_COMMAND  accountCommand (analyze.py:312-336) on `prev`, in place like the reference's shallow copy

@@ -66,6 +66,7 @@ SIGNATURES = {
     "mcl_kmeans": (C.c_int, [_p, C.c_int64, _p, C.c_int, C.c_int, _p, C.c_double, C.c_int, _p, C.POINTER(C.c_int),
                             C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "mcl_laplacian_var": (C.c_int, [_p, C.c_int, C.POINTER(_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _p]),
+    "mcl_laplacian_var_packed": (C.c_int, [_p, C.c_int, _p, C.POINTER(C.c_int), C.POINTER(C.c_int), _p]),
     "mcl_laplacian_sums": (C.c_int, [_p, C.c_int, C.POINTER(_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _p]),
     "mcl_filter_step": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_char, C.c_double, _p, _p, _p, _p]),
     "mcl_filter_step_typed": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_char, C.c_double, C.c_int, _p, _p, _p, _p, _p, _p, _p]),
@@ -280,10 +281,14 @@ class Context:
 
     def _lap(self, images, sums):
         n = len(images)
-        imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        imgs = [np.asarray(im, dtype=np.uint8) for im in images]
         for im in imgs:
             if im.ndim != 2:
                 raise MclError("laplacian: images must be 2-D grayscale uint8")
+        total = sum(im.shape[0] * ((im.shape[1] + 15) & ~15) for im in imgs)
+        if not sums and n > 1 and total >= _STAGE_MIN_BYTES:
+            return self._lap_packed(imgs, total)
+        imgs = [np.ascontiguousarray(im) for im in imgs]
         ptrs = (_p * max(n, 1))(*[im.ctypes.data for im in imgs])
         hs = (C.c_int * max(n, 1))(*[im.shape[0] for im in imgs])
         ws = (C.c_int * max(n, 1))(*[im.shape[1] for im in imgs])
@@ -294,6 +299,45 @@ class Context:
         else:
             out = np.zeros(n, dtype=np.float64)
             _check(self._lib.mcl_laplacian_var(self._h, n, ptrs, hs, ws, st, _ptr(out)), "mcl_laplacian_var")
+        return out
+
+    def _lap_packed(self, imgs, total):
+        """A sequence's worth of frames: the images are copied (a few threads; numpy releases the GIL) into a reusable PINNED
+        buffer in the device's own layout -- rows padded to 16 bytes, images back to back -- and go to the GPU in one DMA
+        instead of one pageable strided copy per image (which bounded the call at 7.4 GB/s)."""
+        n = len(imgs)
+        buf = getattr(_stage_local, "lap", None)
+        if buf is None or buf.nbytes < total:
+            try:
+                buf = pinned_empty((int(total * 1.25) + 4096,), np.uint8)
+            except Exception:
+                buf = np.empty((int(total * 1.25) + 4096,), dtype=np.uint8)
+            _stage_local.lap = buf
+        jobs, pos = [], 0
+        for im in imgs:
+            h, w = im.shape
+            pitch = (w + 15) & ~15
+            jobs.append((pos, h, w, pitch, im))
+            pos += h * pitch
+
+        def copy(group):
+            for at, h, w, pitch, im in group:
+                np.copyto(buf[at:at + h * pitch].reshape(h, pitch)[:, :w], im)
+
+        workers = 4
+        if n >= workers and total >= (8 << 20):
+            from concurrent.futures import ThreadPoolExecutor
+            pool = getattr(_stage_local, "pool", None)
+            if pool is None:
+                pool = _stage_local.pool = ThreadPoolExecutor(max_workers=workers)
+            per = (n + workers - 1) // workers
+            list(pool.map(copy, [jobs[i:i + per] for i in range(0, n, per)]))
+        else:
+            copy(jobs)
+        hs = (C.c_int * n)(*[im.shape[0] for im in imgs])
+        ws = (C.c_int * n)(*[im.shape[1] for im in imgs])
+        out = np.zeros(n, dtype=np.float64)
+        _check(self._lib.mcl_laplacian_var_packed(self._h, n, _ptr(buf), hs, ws, _ptr(out)), "mcl_laplacian_var_packed")
         return out
 
     def filter_step(self, stages, cmd, blur, prev, cur, angle_step=15):

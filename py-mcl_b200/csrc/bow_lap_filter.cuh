@@ -56,6 +56,10 @@ __global__ void __launch_bounds__(128) bow_vq_kernel(
     }
 }
 
+__device__ __forceinline__ void bow_gather_scores(const int* __restrict__ nz_word, const float* __restrict__ nz_val, int n_nz,
+                                                  const float* __restrict__ im_features_t, const int64_t* __restrict__ img_off,
+                                                  int loc, int W, int frame, int total_images, float* __restrict__ out_scores);
+
 // tf-idf scoring (Matcher.py:249-258): histogram of words, *idf, L2 normalise, dot with every image row.
 // The query vector has at most (rows of the frame) non-zeros out of W = 10000 words, so after normalisation it is
 // compacted, in word order (deterministic summation order), into a (word, value) list and every image row is only
@@ -63,7 +67,7 @@ __global__ void __launch_bounds__(128) bow_vq_kernel(
 // grid = (n_locations, n_frames), block = 256; dynamic smem = W floats + list_cap x (int + float).
 __global__ void __launch_bounds__(256) bow_score_kernel(
     const unsigned long long* __restrict__ best /* [n_loc][n_q] */, int n_q, const int64_t* __restrict__ q_off /* frames */,
-    const float* __restrict__ idf /* [n_loc][W] */, const float* __restrict__ im_features /* rows of W */,
+    const float* __restrict__ idf /* [n_loc][W] */, const float* __restrict__ im_features_t /* per location (W, N_l) */,
     const int64_t* __restrict__ img_off /* n_loc+1 */, int W, int total_images, int list_cap,
     int32_t* __restrict__ out_words, float* __restrict__ out_scores /* [n_frames][total_images] */) {
     extern __shared__ float hist[];
@@ -127,14 +131,130 @@ __global__ void __launch_bounds__(256) bow_score_kernel(
         __syncthreads();
     }
     const int n_nz = nz_total;
-    const int64_t i0 = img_off[loc], i1 = img_off[loc + 1];
-    for (int64_t im = i0 + warp; im < i1; im += 8) {
-        const float* row = im_features + im * W;
+    bow_gather_scores(nz_word, nz_val, n_nz, im_features_t, img_off, loc, W, frame, total_images, out_scores);
+}
+
+// Scores of one (location, frame) from its compacted query vector: im_features_t holds every location's tf-idf index
+// TRANSPOSED, (W, N_l) at offset img_off[l] * W, so the N_l image values of a word are contiguous: thread = image, one
+// coalesced row per non-zero word (a (N_l, W) layout costs a 32-byte sector per 4 useful bytes: 8x the traffic).
+// The products are accumulated in list order (deterministic).
+__device__ __forceinline__ void bow_gather_scores(const int* __restrict__ nz_word, const float* __restrict__ nz_val, int n_nz,
+                                                  const float* __restrict__ im_features_t, const int64_t* __restrict__ img_off,
+                                                  int loc, int W, int frame, int total_images, float* __restrict__ out_scores) {
+    const int64_t i0 = img_off[loc];
+    const int n_img = (int)(img_off[loc + 1] - i0);
+    const float* base = im_features_t + i0 * W;
+    for (int im = threadIdx.x; im < n_img; im += blockDim.x) {
         float acc = 0.f;
-        for (int k = lane; k < n_nz; k += 32) acc = fmaf(nz_val[k], row[nz_word[k]], acc);
+        for (int k = 0; k < n_nz; ++k) acc = fmaf(nz_val[k], base[(int64_t)nz_word[k] * n_img + im], acc);
+        out_scores[(int64_t)frame * total_images + i0 + im] = acc;
+    }
+}
+
+// The same scoring for frames of up to BOW_SPARSE_ROWS descriptors without the dense W-long passes (zeroing, idf multiply, norm
+// and compaction over 10 000 words for ~300 occupied ones): the frame's words are staged in shared memory, every row counts
+// its word's occurrences by comparing with all rows (n^2 / 256 broadcast reads per thread: ~350 for n = 300) and the first
+// occurrence of a word carries count * idf; the list is compacted in row order.
+// grid = (n_locations, n_frames), block = 256.
+constexpr int BOW_SPARSE_ROWS = 512;
+
+__global__ void __launch_bounds__(256) bow_score_sparse_kernel(
+    const unsigned long long* __restrict__ best /* [n_loc][n_q] */, int n_q, const int64_t* __restrict__ q_off /* frames */,
+    const float* __restrict__ idf /* [n_loc][W] */, const float* __restrict__ im_features_t, const int64_t* __restrict__ img_off,
+    int W, int total_images, int32_t* __restrict__ out_words, float* __restrict__ out_scores) {
+    __shared__ int wd[BOW_SPARSE_ROWS];
+    __shared__ int nz_word[BOW_SPARSE_ROWS];
+    __shared__ float nz_val[BOW_SPARSE_ROWS];
+    __shared__ float red[8];
+    __shared__ int warp_cnt[8];
+    __shared__ float nrm_s;
+    __shared__ int nz_total;
+    const int loc = blockIdx.x, frame = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q0 = q_off[frame];
+    const int n = (int)(q_off[frame + 1] - q0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int word = (int)(best[(int64_t)loc * n_q + q0 + i] & 0xffffffffu);
+        wd[i] = word;
+        if (out_words) out_words[(int64_t)loc * n_q + q0 + i] = word;
+    }
+    if (threadIdx.x == 0) nz_total = 0;
+    __syncthreads();
+    float v[BOW_SPARSE_ROWS / 256];
+    float ss = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) out_scores[(int64_t)frame * total_images + im] = acc;
+    for (int r = 0; r < BOW_SPARSE_ROWS / 256; ++r) {
+        const int i = r * 256 + threadIdx.x;
+        v[r] = 0.f;
+        if (i < n) {
+            const int w = wd[i];
+            int cnt = 0;
+            bool first = true;
+            for (int j = 0; j < n; ++j) {
+                const bool eq = wd[j] == w;
+                cnt += eq;
+                first = first && !(eq && j < i);
+            }
+            if (first) v[r] = (float)cnt * idf[(int64_t)loc * W + w];   // histogram count (exact) * idf, float32 like the reference
+        }
+        ss += v[r] * v[r];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        const float nrm = sqrtf(t);
+        nrm_s = nrm > 0.f ? nrm : 1.0f;   // sklearn normalize: zero rows are left unchanged
+    }
+    __syncthreads();
+    const float nrm = nrm_s;
+#pragma unroll
+    for (int r = 0; r < BOW_SPARSE_ROWS / 256; ++r) {   // ordered compaction of the non-zeros (row order)
+        const int i = r * 256 + threadIdx.x;
+        const bool nz = v[r] != 0.f;
+        const unsigned bal = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = nz_total;
+        for (int k = 0; k < warp; ++k) off += warp_cnt[k];
+        if (nz) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1u));
+            nz_word[pos] = wd[i];
+            nz_val[pos] = v[r] / nrm;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int k = 0; k < 8; ++k) t += warp_cnt[k];
+            nz_total += t;
+        }
+        __syncthreads();
+    }
+    bow_gather_scores(nz_word, nz_val, nz_total, im_features_t, img_off, loc, W, frame, total_images, out_scores);
+}
+
+// (N_l, W) -> (W, N_l) per location, once per index.  grid = (ceil(W / 32), n_locations), block = (32, 8).
+__global__ void bow_transpose_imf_kernel(const float* __restrict__ imf, const int64_t* __restrict__ img_off, int W,
+                                         float* __restrict__ imf_t) {
+    __shared__ float tile[32][33];
+    const int loc = blockIdx.y;
+    const int64_t i0 = img_off[loc];
+    const int n_img = (int)(img_off[loc + 1] - i0);
+    const int w0 = blockIdx.x * 32;
+    for (int b = 0; b < n_img; b += 32) {
+        for (int r = threadIdx.y; r < 32; r += 8) {
+            const int im = b + r, w = w0 + threadIdx.x;
+            tile[r][threadIdx.x] = (im < n_img && w < W) ? imf[(i0 + im) * W + w] : 0.f;
+        }
+        __syncthreads();
+        for (int r = threadIdx.y; r < 32; r += 8) {
+            const int w = w0 + r, im = b + threadIdx.x;
+            if (w < W && im < n_img) imf_t[i0 * W + (int64_t)w * n_img + im] = tile[threadIdx.x][r];
+        }
+        __syncthreads();
     }
 }
 

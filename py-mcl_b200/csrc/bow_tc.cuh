@@ -31,49 +31,73 @@ constexpr float KEY_REL = 0.00048828125f + 0.0001220703125f;   // 2^-11 + 2^-13
 constexpr float KEY_ABS = 4.0f;
 
 // Pass 1 (one thread per (location, row) job): merge the ranges' records into the three best groups, their keys
-// k1 >= k2 >= k3 and the fourth-best key k4.  With the margin 2 E(k1): the first k_i that trails k1 by more than the margin
-// proves that the argmin lies in the groups before it -> one entry in each of those groups' buckets (the resolve combines
-// them with a 64-bit atomicMin on (distance, word)).  If even k4 is within the margin the row is queued for a full rescan.
+// k1 >= k2 >= k3, the fourth-best key k4 and the keys s[0..3] of the best group's four 8-word SUB-BLOCKS.  With the margin
+// 2 E(k1): the first k_i that trails k1 by more than the margin proves that the argmin lies in the groups before it, and
+// inside the best group only sub-blocks whose key is within the margin of k1 can hold it.  Every such sub-block becomes one
+// ENTRY (job, sub-block) -- most rows end with a single entry of 8 words -- the groups without sub-block keys (second,
+// third) contribute all four of theirs; the resolve combines a row's entries with a 64-bit atomicMin on (distance, word).
+// If even k4 is within the margin the row is queued for a full rescan.
 // state: [0] = queued rows, [1] = run-the-SIMT-kernel flag (bow_decide_kernel), [2] = rows rescanned (statistics),
 //        [3] = entries in the sorted list (bow_scan_kernel)
 constexpr int TOPG = 3;
-__global__ void __launch_bounds__(256) bow_merge_kernel(const int4* __restrict__ tc, int n_splits, int n_q, int n_loc, int groups_per_loc,
-                                                        const int* __restrict__ bad, int* __restrict__ job_grp /* [n_jobs][TOPG] */,
+constexpr int SUB_W = 8;                      // words per sub-block
+constexpr int SUBS = GROUP_W / SUB_W;         // 4 sub-blocks per group
+__global__ void __launch_bounds__(256) bow_merge_kernel(const int4* __restrict__ tc, int n_splits, int n_q, int n_loc, int subs_per_loc,
+                                                        const int* __restrict__ bad, int* __restrict__ job_sel /* [n_jobs][TOPG]: group << 4 | sub-block mask */,
                                                         int* __restrict__ bucket_cnt, int* __restrict__ queue,
                                                         unsigned int* __restrict__ state) {
     const int64_t n_jobs = (int64_t)n_loc * n_q;
     const bool all_bad = *bad != 0;   // non-integer query rows: nothing from the tensor-core pass can be trusted
     for (int64_t job = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; job < n_jobs; job += (int64_t)gridDim.x * blockDim.x) {
         int k1 = 0, k2 = 0, k3 = 0, k4 = 0, p1 = 0, p2 = 0, p3 = 0;   // positive float32 keys compare like their bit patterns; 0 = none
-        auto ins = [&](int k, int pos) {
-            if (k > k1) { k4 = k3; k3 = k2; p3 = p2; k2 = k1; p2 = p1; k1 = k; p1 = pos; }
-            else if (k > k2) { k4 = k3; k3 = k2; p3 = p2; k2 = k; p2 = pos; }
-            else if (k > k3) { k4 = k3; k3 = k; p3 = pos; }
-            else k4 = max(k4, k);
-        };
+        int4 sub = make_int4(0, 0, 0, 0);
         for (int sp = 0; sp < n_splits; ++sp) {
-            const int4 pp = tc[2 * ((size_t)sp * n_jobs + job)], kk = tc[2 * ((size_t)sp * n_jobs + job) + 1];
+            const int4* r = tc + 3 * ((size_t)sp * n_jobs + job);
+            const int4 pp = r[0], kk = r[1];
             if (kk.x <= 0) continue;   // this range reported nothing for the row
-            ins(kk.x, pp.x);
-            if (kk.y > 0) ins(kk.y, pp.y);
-            if (kk.z > 0) ins(kk.z, pp.z);
+            auto ins = [&](int k, int pos, bool is_best_of_range) {
+                if (k > k1) { k4 = k3; k3 = k2; p3 = p2; k2 = k1; p2 = p1; k1 = k; p1 = pos; sub = is_best_of_range ? r[2] : make_int4(0, 0, 0, 0); }
+                else if (k > k2) { k4 = k3; k3 = k2; p3 = p2; k2 = k; p2 = pos; }
+                else if (k > k3) { k4 = k3; k3 = k; p3 = pos; }
+                else k4 = max(k4, k);
+            };
+            ins(kk.x, pp.x, true);
+            if (kk.y > 0) ins(kk.y, pp.y, false);
+            if (kk.z > 0) ins(kk.z, pp.z, false);
             if (kk.w > 0) k4 = max(k4, kk.w);
         }
-        int g[TOPG] = {-1, -1, -1};
+        int sel[TOPG] = {-1, -1, -1};
         if (!all_bad && k1 > 0) {
             const float f1 = __int_as_float(k1);
             const float margin = 2.0f * (KEY_REL * f1 + KEY_ABS);
-            if (k2 <= 0 || f1 - __int_as_float(k2) > margin) { g[0] = p1; }
-            else if (k3 <= 0 || f1 - __int_as_float(k3) > margin) { g[0] = p1; g[1] = p2; }
-            else if (k4 <= 0 || f1 - __int_as_float(k4) > margin) { g[0] = p1; g[1] = p2; g[2] = p3; }
+            int n_groups = 0;
+            if (k2 <= 0 || f1 - __int_as_float(k2) > margin) n_groups = 1;
+            else if (k3 <= 0 || f1 - __int_as_float(k3) > margin) n_groups = 2;
+            else if (k4 <= 0 || f1 - __int_as_float(k4) > margin) n_groups = 3;
+            if (n_groups >= 1) {
+                // sub-blocks of the best group that can hold the argmin (no sub-block keys: all four)
+                int mask = 0;
+                const int sk[4] = {sub.x, sub.y, sub.z, sub.w};
+#pragma unroll
+                for (int j = 0; j < SUBS; ++j)
+                    if (sk[j] <= 0 || f1 - __int_as_float(sk[j]) <= margin) mask |= 1 << j;
+                if (sub.x <= 0 && sub.y <= 0 && sub.z <= 0 && sub.w <= 0) mask = 15;
+                sel[0] = (p1 << 4) | mask;
+            }
+            if (n_groups >= 2) sel[1] = (p2 << 4) | 15;
+            if (n_groups >= 3) sel[2] = (p3 << 4) | 15;
         }
-        const int base = (int)(job / n_q) * groups_per_loc;
+        const int base = (int)(job / n_q) * subs_per_loc;
 #pragma unroll
         for (int i = 0; i < TOPG; ++i) {
-            job_grp[TOPG * job + i] = g[i];
-            if (g[i] >= 0) atomicAdd(&bucket_cnt[base + g[i]], 1);
+            job_sel[TOPG * job + i] = sel[i];
+            if (sel[i] >= 0) {
+#pragma unroll
+                for (int j = 0; j < SUBS; ++j)
+                    if (sel[i] & (1 << j)) atomicAdd(&bucket_cnt[base + (sel[i] >> 4) * SUBS + j], 1);
+            }
         }
-        if (g[0] < 0) queue[atomicAdd(&state[0], 1u)] = (int)job;
+        if (sel[0] < 0) queue[atomicAdd(&state[0], 1u)] = (int)job;
     }
 }
 
@@ -97,38 +121,44 @@ __global__ void __launch_bounds__(1024) bow_scan_kernel(int* __restrict__ cnt, i
     if (threadIdx.x == 1023) state[3] = (unsigned int)part[1023];   // entries of the sorted list
 }
 
-__global__ void __launch_bounds__(256) bow_scatter_kernel(const int* __restrict__ job_grp, int n_q, int64_t n_jobs, int groups_per_loc,
+__global__ void __launch_bounds__(256) bow_scatter_kernel(const int* __restrict__ job_sel, int n_q, int64_t n_jobs, int subs_per_loc,
                                                           int* __restrict__ bucket_pos, int2* __restrict__ sorted) {
     for (int64_t job = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; job < n_jobs; job += (int64_t)gridDim.x * blockDim.x) {
-        const int base = (int)(job / n_q) * groups_per_loc;
+        const int base = (int)(job / n_q) * subs_per_loc;
 #pragma unroll
         for (int which = 0; which < TOPG; ++which) {
-            const int g = job_grp[TOPG * job + which];
-            if (g >= 0) sorted[atomicAdd(&bucket_pos[base + g], 1)] = make_int2((int)job, g);   // entry = (job, one of its groups)
+            const int sel = job_sel[TOPG * job + which];
+            if (sel < 0) continue;
+#pragma unroll
+            for (int j = 0; j < SUBS; ++j)
+                if (sel & (1 << j)) {
+                    const int sb = (sel >> 4) * SUBS + j;
+                    sorted[atomicAdd(&bucket_pos[base + sb], 1)] = make_int2((int)job, sb);   // entry = (job, sub-block of its location)
+                }
         }
     }
 }
 
 // Pass 2: a warp takes RESOLVE_RUN consecutive entries of the sorted list (chosen by the host from the batch size: long runs
-// re-use the group, short runs keep every SM busy on small batches); the 32 code-book rows of the current (location, group)
-// stay in registers while the entries' bucket does not change, and the next entry's (job, group) and query row are fetched
-// while the current one is evaluated (entry -> row -> arithmetic is a chain of dependent trips to L2 otherwise, and with
-// 239 registers only two warps per scheduler are there to hide it).  Lane l holds dims 4l..4l+3; it forms its partial sum for
-// all 32 words, then the partials are summed ACROSS lanes by a transposing reduction (at distance 16 a lane keeps the half of
-// the word list that matches its bit 4 and adds the partner's partials of those words, and so on: 31 shuffles instead of
-// 32 x 5), after which lane i owns word i.  Every word's sum is formed by the same pairing (l, l^16), (l, l^8), ... as
-// bow_rescan_kernel's butterfly, so the float32 distances are bit-identical to the rescan's and the SIMT kernel's
-// tie-breaking is preserved.
+// re-use the sub-block, short runs keep every SM busy on small batches); the 8 code-book rows of the current (location,
+// sub-block) stay in registers while the entries' bucket does not change, and the next entry and its query row are fetched
+// while the current one is evaluated.  Lane l holds dims 4l..4l+3; it forms its partial sum for the 8 words, then the partials
+// are summed ACROSS lanes by a transposing reduction (at distance 16 a lane keeps the half of the word list that matches its
+// bit 4 and adds the partner's partials of those words, then distance 8 and 4: 4 + 2 + 1 shuffles), after which a plain
+// butterfly over distances 2 and 1 leaves word i in lanes 4i .. 4i+3.  Every word's sum is formed by the same pairing
+// (l, l^16), (l, l^8), ... as bow_rescan_kernel's butterfly, so the float32 distances are bit-identical to the rescan's and
+// the SIMT kernel's tie-breaking is preserved.
 __global__ void __launch_bounds__(128) bow_resolve_kernel(const int2* __restrict__ sorted, const unsigned int* __restrict__ state,
                                                           int RESOLVE_RUN, const float* __restrict__ q_desc,
                                                           int n_q, const float* __restrict__ voc, const int64_t* __restrict__ voc_off,
                                                           unsigned long long* __restrict__ best) {
+    static_assert(SUB_W == 8, "the reduction below is written for 8 words");
     const int lane = threadIdx.x & 31;
     const int64_t n_sorted = (int64_t)state[3];
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    float4 cw[GROUP_W];
+    float4 cw[SUB_W];
     for (int64_t run = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; run * RESOLVE_RUN < n_sorted; run += n_warps) {
-        int cur_loc = -1, cur_grp = -1, n_words = 0;
+        int cur_loc = -1, cur_sb = -1, n_words = 0;
         const int64_t begin = run * (int64_t)RESOLVE_RUN, end = min(n_sorted, begin + RESOLVE_RUN);
         int2 e_next = sorted[begin];
         float4 o_next = reinterpret_cast<const float4*>(q_desc + (size_t)(e_next.x % n_q) * 128)[lane];
@@ -140,73 +170,59 @@ __global__ void __launch_bounds__(128) bow_resolve_kernel(const int2* __restrict
                 e_next = sorted[i + 1];
                 o_next = reinterpret_cast<const float4*>(q_desc + (size_t)(e_next.x % n_q) * 128)[lane];
             }
-            const int job = e.x, grp = e.y;
+            const int job = e.x, sb = e.y;
             const int loc = job / n_q;
-            if (loc != cur_loc || grp != cur_grp) {   // warp-uniform
+            if (loc != cur_loc || sb != cur_sb) {   // warp-uniform
                 const int64_t v0 = voc_off[loc];
                 n_words = (int)(voc_off[loc + 1] - v0);
 #pragma unroll
-                for (int j = 0; j < GROUP_W; ++j) {
-                    const int w = min(grp * GROUP_W + j, n_words - 1);
+                for (int j = 0; j < SUB_W; ++j) {
+                    const int w = min(sb * SUB_W + j, n_words - 1);
                     cw[j] = reinterpret_cast<const float4*>(voc + (v0 + w) * 128)[lane];
                 }
                 cur_loc = loc;
-                cur_grp = grp;
+                cur_sb = sb;
             }
-            float pw[GROUP_W];
+            if (sb * SUB_W >= n_words) continue;   // a sub-block beyond the code book (warp-uniform)
+            float pw[SUB_W];
 #pragma unroll
-            for (int j = 0; j < GROUP_W; ++j) {
+            for (int j = 0; j < SUB_W; ++j) {
                 const float dx = o.x - cw[j].x, dy = o.y - cw[j].y, dz = o.z - cw[j].z, dw = o.w - cw[j].w;
                 pw[j] = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
             }
-            static_assert(GROUP_W == 32, "the reduction below is written for 32 words");
-            float p16[16], p8[8], p4[4], p2[2];
+            float p4[4], p2[2];
             {
                 const bool up = (lane & 16) != 0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float keep = up ? pw[j + 16] : pw[j], send = up ? pw[j] : pw[j + 16];
-                    p16[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                for (int j = 0; j < 4; ++j) {
+                    const float keep = up ? pw[j + 4] : pw[j], send = up ? pw[j] : pw[j + 4];
+                    p4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
                 }
             }
             {
                 const bool up = (lane & 8) != 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float keep = up ? p16[j + 8] : p16[j], send = up ? p16[j] : p16[j + 8];
-                    p8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                }
-            }
-            {
-                const bool up = (lane & 4) != 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float keep = up ? p8[j + 4] : p8[j], send = up ? p8[j] : p8[j + 4];
-                    p4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                }
-            }
-            {
-                const bool up = (lane & 2) != 0;
-#pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const float keep = up ? p4[j + 2] : p4[j], send = up ? p4[j] : p4[j + 2];
-                    p2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                    p2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
                 }
             }
             float dist;
             {
-                const bool up = (lane & 1) != 0;
+                const bool up = (lane & 4) != 0;
                 const float keep = up ? p2[1] : p2[0], send = up ? p2[0] : p2[1];
-                dist = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                dist = keep + __shfl_xor_sync(0xffffffffu, send, 4);
             }
-            const int wi = grp * GROUP_W + lane;   // lane i owns word i of the group
+            dist += __shfl_xor_sync(0xffffffffu, dist, 2);
+            dist += __shfl_xor_sync(0xffffffffu, dist, 1);   // lanes 4i .. 4i+3 own word i of the sub-block now
+            const int wi = sb * SUB_W + (lane >> 2);
             unsigned long long bk = (wi < n_words) ? (((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)wi) : ~0ULL;
 #pragma unroll
-            for (int k = 16; k > 0; k >>= 1) {
+            for (int k = 16; k > 2; k >>= 1) {
                 const unsigned long long other = __shfl_xor_sync(0xffffffffu, bk, k);
                 bk = other < bk ? other : bk;
             }
-            if (lane == 0) atomicMin(&best[job], bk);   // a row with several candidate groups gets the best of them
+            if (lane == 0) atomicMin(&best[job], bk);   // a row with several entries gets the best of them
         }
     }
 }

@@ -106,6 +106,7 @@ struct mcl_ctx {
     int bow_score_smem = 0;         // dynamic shared memory opt-in of bow_score_kernel so far
     int64_t active_pairs_hint = -1; // (frame, image) pairs a host DOR mask leaves active, for the launch shape of small problems
     std::map<int64_t, LapPlan> lap_plans;   // by pixel count
+    int lap_smem_optin = 48 * 1024;
     // free list of device blocks for the query batches of mcl_queries_create_device: the per-step batches of the multi-GPU
     // driver come and go with the same few sizes, and cudaMalloc / cudaFree (which synchronises the device) cost more than
     // the ingest itself
@@ -921,6 +922,7 @@ int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
     unsigned long long* d_stats = c->flags.as<unsigned long long>() + 8;   // [0] candidates, [1] dirty pairs (bytes 64..79)
     const size_t n_pairs = (size_t)std::max(1, q->n_queries) * std::max(1, m->n_images);
     CU(c->dirty.ensure(n_pairs));
+    CU(cudaMemsetAsync(c->dirty.p, 0, n_pairs, st));
     CU(cudaMemsetAsync(d_overflow, 0, 4, st));
     for (int qb0 = 0; qb0 < n_qblocks_total; qb0 += batch_qblocks) {
         const int nqb = std::min(batch_qblocks, n_qblocks_total - qb0);
@@ -980,7 +982,7 @@ int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         CU(cudaGetLastError());
         {
             ProfScope ps(c, PROF_SIFT_FIX, st);
-            sift_fixup3_kernel<<<c->sm_count * 4, 256, 0, st>>>(c->cand.as<int4>(), d_cand_count, (unsigned)cap,
+            sift_fixup3_kernel<<<c->sm_count * 8, 256, 0, st>>>(c->cand.as<int4>(), d_cand_count, (unsigned)cap,
                                                                (const uint8_t*)q->d_desc, q->d_norm, q->d_frame,
                                                                (const uint8_t*)m->d_desc, m->d_norm, m->d_img_of, m->d_dst_off,
                                                                ratio, m->n_images, d_counts, d_rescans, d_stats);
@@ -1500,8 +1502,20 @@ extern "C" int mcl_bow_create(mcl_ctx* c, int n_locations, const int64_t* voc_ro
     BCU(cudaMalloc(&b->d_img_off, (size_t)(n_locations + 1) * 8));
     BCU(cudaMemcpyAsync(b->d_voc, voc, (size_t)b->voc_rows * 512, cudaMemcpyHostToDevice, st));
     BCU(cudaMemcpyAsync(b->d_idf, idf, (size_t)n_locations * W * 4, cudaMemcpyHostToDevice, st));
-    if (b->total_images)
-        BCU(cudaMemcpyAsync(b->d_imf, im_features, (size_t)b->total_images * W * 4, cudaMemcpyHostToDevice, st));
+    if (b->total_images) {
+        // the tf-idf rows are kept TRANSPOSED per location, (W, N_l): the score kernels read one contiguous row per query word
+        float* d_tmp = nullptr;
+        BCU(cudaMalloc(&d_tmp, (size_t)b->total_images * W * 4));
+        cudaError_t e1 = cudaMemcpyAsync(d_tmp, im_features, (size_t)b->total_images * W * 4, cudaMemcpyHostToDevice, st);
+        cudaError_t e2 = cudaMemcpyAsync(b->d_img_off, b->h_img_off.data(), (size_t)(n_locations + 1) * 8, cudaMemcpyHostToDevice, st);
+        c->launches++;
+        mcl::bow_transpose_imf_kernel<<<dim3((W + 31) / 32, n_locations), dim3(32, 8), 0, st>>>(d_tmp, b->d_img_off, W, b->d_imf);
+        cudaError_t e3 = cudaStreamSynchronize(st);
+        cudaFree(d_tmp);
+        BCU(e1);
+        BCU(e2);
+        BCU(e3);
+    }
     BCU(cudaMemcpyAsync(b->d_voc_off, b->h_voc_off.data(), (size_t)(n_locations + 1) * 8, cudaMemcpyHostToDevice, st));
     BCU(cudaMemcpyAsync(b->d_img_off, b->h_img_off.data(), (size_t)(n_locations + 1) * 8, cudaMemcpyHostToDevice, st));
     if (W * 12 > c->bow_score_smem) {   // only ever raised: a smaller index created later must not lower it under a live larger one
@@ -1539,8 +1553,8 @@ int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
             }
             const int n_qblocks = (n_q + QBLK - 1) / QBLK;
             const int64_t padded = (int64_t)n_qblocks * QBLK;
-            const int groups_per_loc = (b->max_words + GROUP - 1) / GROUP;
-            const int64_t n_buckets = (int64_t)b->n_loc * groups_per_loc;
+            const int subs_per_loc = (b->max_words + GROUP - 1) / GROUP * SUBS;   // 8-word sub-blocks per location
+            const int64_t n_buckets = (int64_t)b->n_loc * subs_per_loc;
             // work items = (code-book range, location, pair of query blocks): the number of ranges per location with the
             // smallest estimated makespan (rounds of items over the co-resident CTA pairs x (tiles per range + pipeline refill))
             const int n_qgroups = (n_qblocks + 1) / 2;
@@ -1559,18 +1573,19 @@ int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
             CU(c->bow_q8.ensure((size_t)padded * Shape<KIND_BOW>::ROW_BYTES));
             CU(c->bow_qaux.ensure((size_t)padded * 4));
             if (nbest >= ((size_t)1 << 29)) return fail(MCL_EINVAL, "bow: too many (location, row) pairs in one call");
-            CU(c->bow_tc_out.ensure((size_t)n_splits * nbest * 2 * sizeof(int4)));
-            // sort scratch: sorted[3 nbest] (int2) | job_grp[nbest][3] | queue[nbest] | bucket_cnt[n_buckets]
-            CU(c->bow_sort.ensure((10 * nbest + (size_t)n_buckets) * 4));
+            CU(c->bow_tc_out.ensure((size_t)n_splits * nbest * 3 * sizeof(int4)));
+            // sort scratch: sorted[12 nbest] (int2: a row has at most 3 groups x 4 sub-blocks) | job_sel[nbest][3] | queue[nbest] |
+            // bucket_cnt[n_buckets]
+            CU(c->bow_sort.ensure((28 * nbest + (size_t)n_buckets) * 4));
             int2* sorted = c->bow_sort.as<int2>();
-            int* job_grp = reinterpret_cast<int*>(sorted + 3 * nbest);
+            int* job_grp = reinterpret_cast<int*>(sorted + 12 * nbest);
             int* queue = job_grp + 3 * nbest;
             int* bucket = queue + nbest;
             int* bad = c->flags.as<int>() + 6;
             unsigned int* state = c->flags.as<unsigned int>() + 8;   // [8] queued rows, [9] SIMT flag, [10] rescans
             CU(cudaMemsetAsync(c->bow_q8.p, 0, (size_t)padded * Shape<KIND_BOW>::ROW_BYTES, st));
             CU(cudaMemsetAsync(c->bow_qaux.p, 0xFF, (size_t)padded * 4, st));
-            CU(cudaMemsetAsync(c->bow_tc_out.p, 0, (size_t)n_splits * nbest * 2 * sizeof(int4), st));
+            CU(cudaMemsetAsync(c->bow_tc_out.p, 0, (size_t)n_splits * nbest * 3 * sizeof(int4), st));
             CU(cudaMemsetAsync(bucket, 0, (size_t)n_buckets * 4, st));
             CU(cudaMemsetAsync(bad, 0, 4, st));
             CU(cudaMemsetAsync(state, 0, 8, st));
@@ -1608,13 +1623,13 @@ int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
             {
                 ProfScope ps(c, PROF_VQ_RESOLVE, st);
                 const int g = grid_for((int64_t)nbest, 256, c->sm_count * 8);
-                bow_merge_kernel<<<g, 256, 0, st>>>(c->bow_tc_out.as<int4>(), n_splits, n_q, b->n_loc, groups_per_loc, bad, job_grp,
+                bow_merge_kernel<<<g, 256, 0, st>>>(c->bow_tc_out.as<int4>(), n_splits, n_q, b->n_loc, subs_per_loc, bad, job_grp,
                                                     bucket, queue, state);
                 bow_scan_kernel<<<1, 1024, 0, st>>>(bucket, (int)n_buckets, state);
-                bow_scatter_kernel<<<g, 256, 0, st>>>(job_grp, n_q, (int64_t)nbest, groups_per_loc, bucket, sorted);
+                bow_scatter_kernel<<<g, 256, 0, st>>>(job_grp, n_q, (int64_t)nbest, subs_per_loc, bucket, sorted);
                 // entries per warp: enough warps for ~16 per SM, runs of 8..64 entries
                 const int run_len = (int)std::max<int64_t>(8, std::min<int64_t>(64, (int64_t)nbest / ((int64_t)c->sm_count * 16)));
-                bow_resolve_kernel<<<grid_for((3 * (int64_t)nbest + run_len - 1) / run_len * 32, 128, c->sm_count * 16), 128, 0, st>>>(
+                bow_resolve_kernel<<<grid_for((2 * (int64_t)nbest + run_len - 1) / run_len * 32, 128, c->sm_count * 32), 128, 0, st>>>(
                     sorted, state, run_len, d_q, n_q, b->d_voc, b->d_voc_off, c->bow_best.as<unsigned long long>());
             }
             {
@@ -1662,9 +1677,13 @@ extern "C" int mcl_bow_score_device(mcl_bow* b, mcl_queries* q, int32_t* d_words
         for (int f = 0; f < nf; ++f) max_rows = std::max(max_rows, q->h_off[f + 1] - q->h_off[f]);
         const int list_cap = (int)std::min<int64_t>(b->W, max_rows);   // distinct words of a frame <= its rows
         ProfScope ps(c, PROF_SCORE, st);
-        mcl::bow_score_kernel<<<grid, 256, (size_t)b->W * 4 + (size_t)list_cap * 8, st>>>(
-            c->bow_best.as<unsigned long long>(), n_q, q->d_off, b->d_idf, b->d_imf, b->d_img_off, b->W,
-            (int)b->total_images, list_cap, d_words, d_scores);
+        if (max_rows <= mcl::BOW_SPARSE_ROWS)
+            mcl::bow_score_sparse_kernel<<<grid, 256, 0, st>>>(c->bow_best.as<unsigned long long>(), n_q, q->d_off, b->d_idf, b->d_imf,
+                                                               b->d_img_off, b->W, (int)b->total_images, d_words, d_scores);
+        else
+            mcl::bow_score_kernel<<<grid, 256, (size_t)b->W * 4 + (size_t)list_cap * 8, st>>>(
+                c->bow_best.as<unsigned long long>(), n_q, q->d_off, b->d_idf, b->d_imf, b->d_img_off, b->W,
+                (int)b->total_images, list_cap, d_words, d_scores);
     }
     CU(cudaGetLastError());
     return MCL_OK;
@@ -1879,8 +1898,8 @@ int lap_plan_get(mcl_ctx* c, int64_t N, const LapPlan** out) {
 }
 
 int laplacian_common(mcl_ctx* c, int n, const uint8_t* const* imgs, const int* h, const int* w, const int* stride,
-                     int64_t* sums_out, double* var_out) {
-    if (!c || (n > 0 && (!imgs || !h || !w))) return fail(MCL_EINVAL, "mcl_laplacian: NULL argument");
+                     int64_t* sums_out, double* var_out, const uint8_t* packed = nullptr) {
+    if (!c || (n > 0 && ((!imgs && !packed) || !h || !w))) return fail(MCL_EINVAL, "mcl_laplacian: NULL argument");
     if (n <= 0) return MCL_OK;
     if (n > 65535) return fail(MCL_EINVAL, "at most 65535 images per call");
     CU(cudaSetDevice(c->device));
@@ -1889,7 +1908,7 @@ int laplacian_common(mcl_ctx* c, int n, const uint8_t* const* imgs, const int* h
     std::vector<int> pitch(n);
     int max_h = 0, max_w = 0;
     for (int i = 0; i < n; ++i) {
-        if (h[i] <= 0 || w[i] <= 0 || !imgs[i]) return fail(MCL_EINVAL, "image %d: bad size or NULL pointer", i);
+        if (h[i] <= 0 || w[i] <= 0 || (!packed && !imgs[i])) return fail(MCL_EINVAL, "image %d: bad size or NULL pointer", i);
         if (stride && stride[i] < w[i]) return fail(MCL_EINVAL, "image %d: stride < width", i);
         pitch[i] = (w[i] + 15) & ~15;   // rows start on 16-byte boundaries: one aligned 128-bit load per 16 pixels
         off[i + 1] = off[i] + (int64_t)h[i] * pitch[i];
@@ -1902,10 +1921,14 @@ int laplacian_common(mcl_ctx* c, int n, const uint8_t* const* imgs, const int* h
                  o_s = (o_p + (size_t)n * 4 + 7) & ~(size_t)7, o_v = o_s + (size_t)n * 16, total = o_v + (size_t)n * 8;
     CU(c->lap_meta.ensure(total));
     uint8_t* mb = c->lap_meta.as<uint8_t>();
-    for (int i = 0; i < n; ++i) {
-        const int s = stride ? stride[i] : w[i];
-        CU(cudaMemcpy2DAsync(c->lap_pix.as<uint8_t>() + off[i], (size_t)pitch[i], imgs[i], (size_t)s, (size_t)w[i], (size_t)h[i],
-                             cudaMemcpyHostToDevice, st));
+    if (packed) {   // the caller laid the images out exactly like the device buffer (16-byte row pitch, back to back): ONE copy
+        CU(cudaMemcpyAsync(c->lap_pix.p, packed, (size_t)off[n], cudaMemcpyHostToDevice, st));
+    } else {
+        for (int i = 0; i < n; ++i) {
+            const int s = stride ? stride[i] : w[i];
+            CU(cudaMemcpy2DAsync(c->lap_pix.as<uint8_t>() + off[i], (size_t)pitch[i], imgs[i], (size_t)s, (size_t)w[i], (size_t)h[i],
+                                 cudaMemcpyHostToDevice, st));
+        }
     }
     CU(cudaMemcpyAsync(mb, off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(mb + o_h, h, (size_t)n * 4, cudaMemcpyHostToDevice, st));
@@ -1952,11 +1975,27 @@ int laplacian_common(mcl_ctx* c, int n, const uint8_t* const* imgs, const int* h
             const int* t = pl->d_tab;
             const int* lst = c->lap_list.as<int>() + first;
             const int bx = std::max(1, std::min((nl + 31) / 32, std::max(1, 8 * c->sm_count / cnt)));
+            // widths of the group (images of one pixel count may still differ in shape): the thread-per-leaf kernel needs
+            // W % 8 == 0 and its staged rows (128 leaves x <= 128 pixels + 3 rows) within the shared-memory opt-in
+            bool fast = true;
+            int wmax = 0;
+            for (int i : g.second) { fast = fast && (w[i] % 8 == 0); wmax = std::max(wmax, w[i]); }
+            const size_t smem = (size_t)mcl::LAPV_LEAVES_PER_CTA * 128 + 4 * (size_t)wmax;
+            fast = fast && smem <= (size_t)c->prop.sharedMemPerBlockOptin;
+            if (fast && smem > (size_t)c->lap_smem_optin) {
+                CU(cudaFuncSetAttribute(mcl::lap_leaf8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                c->lap_smem_optin = (int)smem;
+            }
             {
                 ProfScope ps(c, PROF_LAP, st);
-                mcl::lap_leaf_kernel<<<dim3(bx, cnt), 256, 0, st>>>(c->lap_pix.as<uint8_t>(), (const int64_t*)mb, (const int*)(mb + o_p),
-                                                                    (const int*)(mb + o_h), (const int*)(mb + o_w), lst,
-                                                                    (const long long*)(mb + o_s), t, t + nl, nl, nv, c->lap_vals.as<double>());
+                if (fast)
+                    mcl::lap_leaf8_kernel<<<dim3((nl + mcl::LAPV_LEAVES_PER_CTA - 1) / mcl::LAPV_LEAVES_PER_CTA, cnt), mcl::LAPV_LEAVES_PER_CTA, smem, st>>>(
+                        c->lap_pix.as<uint8_t>(), (const int64_t*)mb, (const int*)(mb + o_p), (const int*)(mb + o_h), (const int*)(mb + o_w),
+                        lst, (const long long*)(mb + o_s), t, t + nl, nl, nv, c->lap_vals.as<double>());
+                else
+                    mcl::lap_leaf_kernel<<<dim3(bx, cnt), 256, 0, st>>>(c->lap_pix.as<uint8_t>(), (const int64_t*)mb, (const int*)(mb + o_p),
+                                                                        (const int*)(mb + o_h), (const int*)(mb + o_w), lst,
+                                                                        (const long long*)(mb + o_s), t, t + nl, nl, nv, c->lap_vals.as<double>());
             }
             c->launches++;
             mcl::lap_tree_kernel<<<cnt, 256, 0, st>>>(t + 2 * nl, t + 2 * nl + nn, t + 2 * nl + 2 * nn, pl->n_levels, nl, nv, lst,
@@ -1977,6 +2016,10 @@ extern "C" int mcl_laplacian_var(mcl_ctx* c, int n, const uint8_t* const* imgs, 
                                  double* out) {
     if (n > 0 && !out) return fail(MCL_EINVAL, "mcl_laplacian_var: out is NULL");
     return laplacian_common(c, n, imgs, h, w, stride, nullptr, out);
+}
+extern "C" int mcl_laplacian_var_packed(mcl_ctx* c, int n, const uint8_t* packed, const int* h, const int* w, double* out) {
+    if (n > 0 && (!out || !packed)) return fail(MCL_EINVAL, "mcl_laplacian_var_packed: NULL argument");
+    return laplacian_common(c, n, nullptr, h, w, nullptr, nullptr, out, packed);
 }
 extern "C" int mcl_laplacian_sums(mcl_ctx* c, int n, const uint8_t* const* imgs, const int* h, const int* w, const int* stride,
                                   int64_t* sums) {

@@ -24,7 +24,8 @@
 //   ORB, end of an image: best key H1 is exact; the second best is >= H2 (the best other group); a row whose ratio test
 //        fails with (H1, H2) fails with the true second best too and is dropped; the others go to a candidate list and
 //        orb_fixup_kernel recomputes the 32 rows of the best group with xor + popc on the packed descriptors.
-//   BOW, end of a code-book range: (the three best groups, their keys, the fourth-best key) per (range, location, row).
+//   BOW, end of a code-book range: (the three best groups, their keys, the fourth-best key, and the keys of the best group's
+//        four 8-word sub-blocks) per (range, location, row).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -88,7 +89,8 @@ struct Params {
     int n_images;
     int q_row_base;
     // BOW outputs
-    int4* out;                // [n_splits][n_loc][n_q][2]: {the three best groups, -}, {their key bits, fourth-best key bits}
+    int4* out;                // [n_splits][n_loc][n_q][3]: {the three best groups, -}, {their key bits, fourth-best key bits},
+                              // {key bits of the best group's four 8-word sub-blocks}
     int n_q, n_loc;
     int meta_cap;
 };
@@ -119,6 +121,15 @@ __device__ __forceinline__ void umma_f16_ts_if(uint32_t pred, uint32_t tmem_d, u
 __device__ __forceinline__ void mask_group(uint32_t (&v)[32], int nv) {
 #pragma unroll
     for (int c = 0; c < 32; ++c) v[c] = c < nv ? v[c] : (uint32_t)INT_MIN;
+}
+
+// maximum of a 32-column group through the maxima of its four 8-column sub-blocks (BOW keeps the best group's four)
+__device__ __forceinline__ int group_max_sub(const uint32_t (&v)[32], int (&m8)[4]) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+        m8[b] = max3(max3((int)v[8 * b], (int)v[8 * b + 1], (int)v[8 * b + 2]), max3((int)v[8 * b + 3], (int)v[8 * b + 4], (int)v[8 * b + 5]),
+                     max((int)v[8 * b + 6], (int)v[8 * b + 7]));
+    return max(max3(m8[0], m8[1], m8[2]), m8[3]);
 }
 
 template <int KIND, int CL>
@@ -251,7 +262,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
             // others; BOW keeps the THREE best groups and the fourth-best key (a near-tie between up to three groups is then
             // resolved inside those groups instead of over the whole code book)
             int H1 = NONE, H2 = NONE, H3 = NONE, H4 = NONE, pos = 0, pos2 = 0, pos3 = 0;
-            auto join = [&](int gm, int id) {
+            int S0 = NONE, S1 = NONE, S2 = NONE, S3 = NONE;   // BOW: maxima of the best group's four 8-word sub-blocks
+            auto join = [&](int gm, int id, const int (&m8)[4]) {
                 const bool g1 = gm > H1;
                 if (KIND == KIND_BOW) {
                     const bool g2 = gm > H2, g3 = gm > H3;
@@ -260,6 +272,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                     pos3 = g2 ? pos2 : (g3 ? id : pos3);
                     H2 = g1 ? H1 : (g2 ? gm : H2);
                     pos2 = g1 ? pos : (g2 ? id : pos2);
+                    S0 = g1 ? m8[0] : S0; S1 = g1 ? m8[1] : S1; S2 = g1 ? m8[2] : S2; S3 = g1 ? m8[3] : S3;
                 } else {
                     H2 = max(H2, g1 ? H1 : gm);
                 }
@@ -313,12 +326,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                 } else {
                     // ch.img_begin = location, ch.img_end = index of this code-book range among the location's splits
                     if (row_valid) {
-                        int4* o = p.out + 2 * (((size_t)ch.img_end * p.n_loc + ch.img_begin) * p.n_q + (p.q_row_base + qrow));
+                        int4* o = p.out + 3 * (((size_t)ch.img_end * p.n_loc + ch.img_begin) * p.n_q + (p.q_row_base + qrow));
                         o[0] = make_int4(pos, pos2, pos3, 0);
                         o[1] = make_int4(H1, H2, H3, H4);
+                        o[2] = make_int4(S0, S1, S2, S3);
                     }
                 }
                 H1 = NONE; H2 = NONE; H3 = NONE; H4 = NONE;
+                S0 = NONE; S1 = NONE; S2 = NONE; S3 = NONE;
             };
 #pragma unroll 1
             for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
@@ -335,18 +350,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                 tmem_fence_regs(v[1]);
                 const bool plain = r1.z != 0;   // warp-uniform
                 if (!plain) { mask_group(v[0], r1.x & 255); mask_group(v[1], (r1.x >> 8) & 255); }
-                const int g0 = sifttc3::group_max<0>(v[0]), g1 = sifttc3::group_max<0>(v[1]);
+                int sub[4][4];
+                const int g0 = KIND == KIND_BOW ? group_max_sub(v[0], sub[0]) : sifttc3::group_max<0>(v[0]);
+                const int g1 = KIND == KIND_BOW ? group_max_sub(v[1], sub[1]) : sifttc3::group_max<0>(v[1]);
                 tmem_ld64(tcol + 64, reinterpret_cast<uint32_t(&)[64]>(v));
                 tmem_wait_all();
                 tmem_fence_regs(v[0]);
                 tmem_fence_regs(v[1]);
                 if (lane == 0) mbar_arrive(&s.acc_empty[x]);   // both halves are out of tensor memory: the accumulator is free
                 if (!plain) { mask_group(v[0], (r1.x >> 16) & 255); mask_group(v[1], (r1.x >> 24) & 255); }
-                const int g2 = sifttc3::group_max<0>(v[0]), g3 = sifttc3::group_max<0>(v[1]);
+                const int g2 = KIND == KIND_BOW ? group_max_sub(v[0], sub[2]) : sifttc3::group_max<0>(v[0]);
+                const int g3 = KIND == KIND_BOW ? group_max_sub(v[1], sub[3]) : sifttc3::group_max<0>(v[1]);
                 // group position: ORB = padded row / 32 over the whole map; BOW = group index within the location
                 const int gbase = KIND == KIND_ORB ? 4 * t : r1.w;
                 if (plain) {
-                    join(g0, gbase); join(g1, gbase + 1); join(g2, gbase + 2); join(g3, gbase + 3);
+                    join(g0, gbase, sub[0]); join(g1, gbase + 1, sub[1]); join(g2, gbase + 2, sub[2]); join(g3, gbase + 3, sub[3]);
                     if (r1.y & 8) finalize(r0.x, t);
                 } else {
                     const int gm[4] = {g0, g1, g2, g3};
@@ -354,7 +372,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         if (sg[g] < 0) continue;   // padding group
-                        join(gm[g], gbase + g);
+                        join(gm[g], gbase + g, sub[g]);
                         if (r1.y & (1 << g)) finalize(sg[g], t);
                     }
                 }
