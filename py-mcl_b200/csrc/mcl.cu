@@ -172,6 +172,7 @@ struct mcl_bow {
     float* d_key_c = nullptr;
     struct Split { int n_splits = 0, n_chunks = 0; mcl::sifttc3::Chunk* d = nullptr; };
     std::vector<Split> splits;   // chunk tables: every location's tiles cut into 1, 2, 4, 8 ranges
+    int cap_tiles = 0, cap_loc = 0;   // what the tensor-core buffers were allocated for (k-means rebuilds them every iteration)
     bool tc_ok = false;
     float* d_voc = nullptr;
     float* d_idf = nullptr;
@@ -1388,6 +1389,7 @@ void bow_free_tc(mcl_bow* b) {
     for (auto& sp : b->splits) cudaFree(sp.d);
     b->d_tile_off = nullptr; b->d_tiles = nullptr; b->d_rec = nullptr; b->d_key_c = nullptr;
     b->splits.clear();
+    b->cap_tiles = b->cap_loc = 0;
     b->tc_ok = false;
 }
 
@@ -1395,7 +1397,6 @@ void bow_free_tc(mcl_bow* b) {
 int bow_build_tc(mcl_bow* b, cudaStream_t st) {
     using namespace mcl::tc9;
     mcl_ctx* c = b->ctx;
-    bow_free_tc(b);
     const int L = b->n_loc;
     b->h_tile_off.resize(L + 1);
     int32_t acc = 0;
@@ -1404,11 +1405,23 @@ int bow_build_tc(mcl_bow* b, cudaStream_t st) {
         acc += (int32_t)((b->h_voc_off[l + 1] - b->h_voc_off[l] + TILE_N - 1) / TILE_N);
     }
     b->h_tile_off[L] = acc;
-    CU(cudaMalloc(&b->d_tile_off, (size_t)(L + 1) * 4));
+    const bool reuse = b->d_tiles && acc <= b->cap_tiles && L == b->cap_loc;   // a rebuild that fits (k-means: k only shrinks)
+    if (!reuse) {
+        bow_free_tc(b);
+        CU(cudaMalloc(&b->d_tile_off, (size_t)(L + 1) * 4));
+        CU(cudaMalloc(&b->d_tiles, std::max<size_t>((size_t)acc * Shape<KIND_BOW>::TILE_BYTES, 256)));
+        CU(cudaMalloc(&b->d_rec, std::max<size_t>((size_t)acc * sizeof(TileRec), 256)));
+        CU(cudaMalloc(&b->d_key_c, (size_t)L * 4));
+        for (int ns : {1, 2, 4, 8}) {
+            mcl_bow::Split sp;
+            sp.n_splits = ns;
+            CU(cudaMalloc(&sp.d, std::max<size_t>((size_t)ns * L * sizeof(mcl::sifttc3::Chunk), 16)));
+            b->splits.push_back(sp);
+        }
+        b->cap_tiles = acc;
+        b->cap_loc = L;
+    }
     CU(cudaMemcpyAsync(b->d_tile_off, b->h_tile_off.data(), (size_t)(L + 1) * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMalloc(&b->d_tiles, std::max<size_t>((size_t)acc * Shape<KIND_BOW>::TILE_BYTES, 256)));
-    CU(cudaMalloc(&b->d_rec, std::max<size_t>((size_t)acc * sizeof(TileRec), 256)));
-    CU(cudaMalloc(&b->d_key_c, (size_t)L * 4));
     int* bad = c->flags.as<int>() + 6;
     CU(cudaMemsetAsync(bad, 0, 4, st));
     {
@@ -1418,8 +1431,11 @@ int bow_build_tc(mcl_bow* b, cudaStream_t st) {
     }
     c->launches++;
     CU(cudaGetLastError());
-    for (int ns : {1, 2, 4, 8}) {
-        std::vector<mcl::sifttc3::Chunk> ch;
+    std::vector<std::vector<mcl::sifttc3::Chunk>> tables;   // kept alive until the copies below have been consumed
+    for (auto& s : b->splits) {
+        const int ns = s.n_splits;
+        tables.emplace_back();
+        auto& ch = tables.back();
         for (int sp = 0; sp < ns; ++sp)
             for (int l = 0; l < L; ++l) {
                 const int t0 = b->h_tile_off[l], nt = b->h_tile_off[l + 1] - t0, per = (nt + ns - 1) / ns;
@@ -1430,13 +1446,8 @@ int bow_build_tc(mcl_bow* b, cudaStream_t st) {
                 k.img_end = sp;     // range index: where the range's records go
                 if (k.tile_end > k.tile_begin) ch.push_back(k);
             }
-        mcl_bow::Split s;
-        s.n_splits = ns;
         s.n_chunks = (int)ch.size();
-        CU(cudaMalloc(&s.d, std::max<size_t>(ch.size() * sizeof(mcl::sifttc3::Chunk), 16)));
-        b->splits.push_back(s);
         if (!ch.empty()) CU(cudaMemcpyAsync(s.d, ch.data(), ch.size() * sizeof(mcl::sifttc3::Chunk), cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));   // `ch` is a local
     }
     int h_bad = 0;
     CU(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, st));

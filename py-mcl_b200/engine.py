@@ -76,8 +76,8 @@ class ShardedMap(object):
     matches against its slice (mcl_match_counts_device), the int32 counts are all-gathered on the device, and ONE
     device-to-host copy returns them.  Other backends (gloo in the CPU tests, or a custom local matcher) take the host path."""
 
-    # batches below this many descriptor rows are uploaded whole by every rank (the collective would cost more than the copy)
-    SHARED_UPLOAD_MIN_ROWS = 32768
+    # batches below this many bytes are uploaded whole by every rank (the collective would cost more than the copy)
+    SHARED_UPLOAD_MIN_BYTES = 8 << 20
 
     def __init__(self, kind, descs, ctx=None, local_factory=None, group=None, local_only=False):
         """descs: every map image's descriptors (each rank keeps its slice), or -- local_only=True -- just THIS rank's
@@ -193,7 +193,7 @@ class ShardedMap(object):
         dq = self._buf("q_rows", (rows, row_elems), tdt)
         src = torch.from_numpy(cat) if rows else None
         plan = None
-        if rows >= self.SHARED_UPLOAD_MIN_ROWS and F >= 2 * self.world:
+        if cat.nbytes >= self.SHARED_UPLOAD_MIN_BYTES and F >= 2 * self.world:
             # frames in two parts (1/8, 7/8 of the rows): the second part's upload + all-gather runs on a side stream
             # under the first part's matching.  Inside a part the frames are dealt to the ranks in contiguous runs of
             # nearly equal row counts; each rank uploads its run, then the runs are all-gathered in place over NVLink.
@@ -414,7 +414,16 @@ class ShardedBow(object):
         stream = torch.cuda.current_stream()
         q = None
         if self.local is not None and w:
-            q = _lib.QueryBatch(self.local.ctx, _lib.BOWQ, q_descs)
+            # the batch is built from a cached device tensor (pooled blocks inside the library): a host-built batch would
+            # cudaMalloc / cudaFree per call, which costs milliseconds once NCCL has mapped its peers
+            off, cat, code = _lib.pack_descriptors(_lib.BOWQ, q_descs)
+            tdt = torch.from_numpy(np.empty(0, dtype=cat.dtype)).dtype
+            if getattr(self, "_dq", None) is None or self._dq.numel() < cat.size or self._dq.dtype != tdt:
+                self._dq = torch.empty(max(cat.size, 1), dtype=tdt, device="cuda")
+            dq = self._dq[:cat.size]
+            if cat.size:
+                dq.copy_(torch.from_numpy(cat).reshape(-1), non_blocking=True)
+            q = _lib.QueryBatch(self.local.ctx, _lib.BOWQ, device=(off, dq.data_ptr(), code, _stream_handle(stream)))
             self.local.score_device(q, self._tight.data_ptr(), stream=_stream_handle(stream))
             if self._tight is not self._mine:
                 self._mine[:, :w].copy_(self._tight[:, :w])

@@ -88,7 +88,7 @@ frames = [synth.sift_like(rng, int(n)) for n in rng.integers(700, 1300, size=44)
 for f in range(0, 44, 3):
     src = map_des[(5 * f) % 23]
     frames[f][:200] = synth.sift_noisy_copy(rng, src[:200], 4.0)
-assert sum(len(f) for f in frames) >= ShardedMap.SHARED_UPLOAD_MIN_ROWS
+assert sum(f.nbytes for f in frames) >= ShardedMap.SHARED_UPLOAD_MIN_BYTES
 sm = ShardedMap("SIFT", map_des, ctx=ctx)
 got_big = sm.match_counts(frames)
 mask = (rng.random((3, 24)) < 0.5).astype(np.uint8)
