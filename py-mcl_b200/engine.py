@@ -194,13 +194,20 @@ class ShardedMap(object):
         src = torch.from_numpy(cat) if rows else None
         plan = None
         if cat.nbytes >= self.SHARED_UPLOAD_MIN_BYTES and F >= 2 * self.world:
-            # frames in two parts (1/8, 7/8 of the rows): the second part's upload + all-gather runs on a side stream
-            # under the first part's matching.  Inside a part the frames are dealt to the ranks in contiguous runs of
-            # nearly equal row counts; each rank uploads its run, then the runs are all-gathered in place over NVLink.
-            cut = int(np.searchsorted(off, rows // 8, side="left"))
-            cut = min(max(cut, self.world), F - self.world)
+            # frames in two parts (1/8, 7/8 of the rows): only the first, small part's upload + all-gather is exposed; the
+            # second part's runs on a side stream under the first part's matching.  (Three parts, like mcl_match_counts' own
+            # host pipeline, measured worse at 4 GPUs: 1.5 instead of 1.0 ms over the resident step -- every part is another
+            # set of launches with its own tail.)  Inside a part the frames are dealt to the ranks in contiguous runs of
+            # nearly equal row counts; each rank uploads its run, then the runs are all-gathered over NVLink.
+            cuts = [0]
+            for frac in (1.0 / 8,):
+                c = int(np.searchsorted(off, int(rows * frac), side="left"))
+                c = min(max(c, cuts[-1] + self.world), F - self.world)
+                if c > cuts[-1]:
+                    cuts.append(c)
+            cuts.append(F)
             plan = []
-            for f0, f1 in ((0, cut), (cut, F)):
+            for f0, f1 in zip(cuts[:-1], cuts[1:]):
                 r0, r1 = int(off[f0]), int(off[f1])
                 edges = [r0 + (r1 - r0) * k // self.world for k in range(self.world + 1)]
                 fe = [int(np.searchsorted(off, e, side="left")) for e in edges]
@@ -428,12 +435,15 @@ class ShardedBow(object):
             if self._tight is not self._mine:
                 self._mine[:, :w].copy_(self._tight[:, :w])
         d.all_gather_into_tensor(self._all, self._mine, group=self.group)
-        self._host.copy_(self._all, non_blocking=True)
+        # the ranks' column blocks are put side by side ON THE DEVICE, then one D2H of the finished (F, total_images) matrix
+        if getattr(self, "_full", None) is None or self._full.shape != (F, self.total_images):
+            self._full = torch.empty((F, self.total_images), dtype=torch.float32, device="cuda")
+            self._full_host = torch.empty((F, self.total_images), dtype=torch.float32).pin_memory()
+        for r, (l, h) in enumerate(self.bounds):
+            if h > l:
+                self._full[:, l:h].copy_(self._all[r][:, :h - l])
+        self._full_host.copy_(self._full, non_blocking=True)
         stream.synchronize()
         if q is not None:
             q.close()
-        out = self._host.numpy()
-        full = np.empty((F, self.total_images), dtype=np.float32)
-        for r, (l, h) in enumerate(self.bounds):
-            full[:, l:h] = out[r][:, :h - l]
-        return full
+        return self._full_host.numpy().copy()
