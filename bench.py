@@ -311,7 +311,9 @@ def sift_distributions(ctx, _lib, np):
                     "rows_per_frame": rows_q / len(frames), "rows_per_image": rows_m / len(map_des),
                     "pairs_per_s": pairs / (ms * 1e-3), "ms": ms, "tensor_kernel_TOPs": ops / (tc / reps * 1e-3) / 1e12,
                     "candidates_per_row_image": (s1["sift_candidates"] - s0["sift_candidates"]) / reps / max(1, rows_q * len(map_des)),
+                    "good_matches_per_row_image": float(d.sum().item()) / max(1, rows_q * len(map_des)),
                     "fixup_share": fix / max(1e-9, tc + fix + simt), "repair_share": simt / max(1e-9, tc + fix + simt),
+                    "fixup_ms": fix / reps,
                     "exact_rescans": (s1["sift_rescans"] - s0["sift_rescans"]) // reps,
                     "repaired_pairs": (s1["repaired_pairs"] - s0["repaired_pairs"]) // reps,
                     "equals_exact_kernel": bool(np.array_equal(want, got))})

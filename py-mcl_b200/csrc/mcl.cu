@@ -97,6 +97,7 @@ struct mcl_ctx {
     // scratch
     DevBuf stage, cand, dirty, flags /* ints: [0]=cand_count [1]=overflow [2]=bad [3]=rescans [6]=bow bad [8..10]=bow state; bytes 64..: statistics */, row_arg, bow_best, lap_pix, lap_meta, filt, tmp_counts,
         tmp_mask, tmp_words, tmp_scores, chi2, tq_off, tq_desc, tq_norm, tq_frame, bow_q8, bow_qaux, bow_tc_out, bow_sort, orb_q;
+    int fixup_blocks = 0;
     bool tc9_attr = false;
     int tc9_clusters[2] = {0, 0};   // co-resident tc9 CTA pairs (ORB, BOW)
     size_t cand_cap_entries = 0;
@@ -983,10 +984,16 @@ int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         CU(cudaGetLastError());
         {
             ProfScope ps(c, PROF_SIFT_FIX, st);
-            sift_fixup3_kernel<<<c->sm_count * 8, 256, 0, st>>>(c->cand.as<int4>(), d_cand_count, (unsigned)cap,
-                                                               (const uint8_t*)q->d_desc, q->d_norm, q->d_frame,
-                                                               (const uint8_t*)m->d_desc, m->d_norm, m->d_img_of, m->d_dst_off,
-                                                               ratio, m->n_images, d_counts, d_rescans, d_stats);
+            // grid-stride over the candidates: exactly the co-resident blocks, so that no block starts a wave late
+            auto fix = sift_fixup3_kernel;
+            if (!c->fixup_blocks) {
+                int per_sm = 0;
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fix, 256, 0));
+                c->fixup_blocks = c->sm_count * std::max(1, per_sm);
+            }
+            fix<<<c->fixup_blocks, 256, 0, st>>>(c->cand.as<int4>(), d_cand_count, (unsigned)cap, (const uint8_t*)q->d_desc, q->d_norm,
+                                                 q->d_frame, (const uint8_t*)m->d_desc, m->d_norm, m->d_img_of, m->d_dst_off, ratio,
+                                                 m->n_images, d_counts, d_rescans, d_stats);
         }
         CU(cudaGetLastError());
     }

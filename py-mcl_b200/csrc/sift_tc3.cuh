@@ -170,7 +170,7 @@ __device__ __forceinline__ int group_max(const uint32_t (&v)[32]) {
 }
 
 // ------------------------------------------------------------------------------------------
-// exact resolution of candidates.  One warp per candidate; lane l owns rows l and l+32 of the 64-row tile that holds G1.
+// exact resolution of candidates.  One warp per candidate; eight lanes share a row of the tile that holds G1 (dots64).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int exact_key(const uint4 (&q)[8], const uint8_t* __restrict__ m_desc, int64_t mrow, int nm) {
     unsigned dot = 0;
@@ -196,43 +196,91 @@ __device__ __forceinline__ void warp_top2(int b1, int b2, int& best, int& second
     second = (__popc(eq) >= 2) ? m : s;
 }
 
-__global__ void sift_fixup3_kernel(const int4* __restrict__ cand, const unsigned int* __restrict__ cand_count,
+// Partial dot products of 64 consecutive map rows with one query row, 8 lanes per row: lane (sub = lane & 7, slot = lane >> 3)
+// reads the 16 bytes at physical chunk position `sub` of rows base + 4 j + slot (j = 0..15), so a warp-wide load covers four
+// whole 128-byte rows (coalesced), all 16 loads are independent, and a lane needs only the two query chunks those positions
+// hold under the SW128 swizzle (logical chunk = sub ^ (row & 7); row & 7 = 4 (j & 1) + slot).  A transposing butterfly over
+// the three sub bits then leaves lane `sub` with the complete dots of j = sub and j = 8 + sub.
+__device__ __forceinline__ void dots64(const uint8_t* __restrict__ m_desc, int64_t base, int sub, int slot, const uint4& q_even,
+                                       const uint4& q_odd, unsigned& d_lo, unsigned& d_hi) {
+    unsigned p[16];
+    uint4 b[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        b[j] = *reinterpret_cast<const uint4*>(m_desc + (size_t)(base + 4 * j + slot) * 128u + (size_t)(sub << 4));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint4& q = (j & 1) ? q_odd : q_even;
+        unsigned d = __dp4a(q.x, b[j].x, 0u);
+        d = __dp4a(q.y, b[j].y, d); d = __dp4a(q.z, b[j].z, d); d = __dp4a(q.w, b[j].w, d);
+        p[j] = d;
+    }
+    // butterfly: after the step on bit k, a lane keeps the j's whose bit k equals its own sub bit k
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const unsigned keep = (sub & 1) ? p[2 * i + 1] : p[2 * i], send = (sub & 1) ? p[2 * i] : p[2 * i + 1];
+        p[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);          // j = 2 i + b0
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const unsigned keep = (sub & 2) ? p[2 * i + 1] : p[2 * i], send = (sub & 2) ? p[2 * i] : p[2 * i + 1];
+        p[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);          // j = 4 i + 2 b1 + b0
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const unsigned keep = (sub & 4) ? p[2 * i + 1] : p[2 * i], send = (sub & 4) ? p[2 * i] : p[2 * i + 1];
+        p[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);          // j = 8 i + sub
+    }
+    d_lo = p[0];
+    d_hi = p[1];
+}
+
+__global__ void __launch_bounds__(256, 2)   // 120 registers, no spills; 3 blocks (80 registers) measured 3 % slower
+sift_fixup3_kernel(const int4* __restrict__ cand, const unsigned int* __restrict__ cand_count,
                                    unsigned int cand_cap, const uint8_t* __restrict__ q_desc,
                                    const int32_t* __restrict__ q_norm, const int32_t* __restrict__ q_frame,
                                    const uint8_t* __restrict__ m_desc, const int32_t* __restrict__ m_norm,
                                    const int32_t* __restrict__ m_img_of, const int64_t* __restrict__ m_dst_off,
                                    double ratio, int n_images, int32_t* __restrict__ counts,
                                    unsigned int* __restrict__ n_rescans, unsigned long long* __restrict__ n_candidates) {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane & 7, slot = lane >> 3;
     const unsigned n = min(*cand_count, cand_cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(n_candidates, (unsigned long long)n);   // statistics
     const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < n; c += n_warps) {
-        const int4 cd = cand[c];
+    unsigned c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int4 cd_next = c < n ? cand[c] : make_int4(0, 0, 0, 0);
+    for (; c < n; c += n_warps) {
+        const int4 cd = cd_next;
+        if (c + n_warps < n) cd_next = cand[c + n_warps];     // the next candidate's record travels under this one's work
         const int64_t qrow = cd.x;
-        uint4 q[8];
-#pragma unroll
-        for (int chunk = 0; chunk < 8; ++chunk) q[chunk] = *reinterpret_cast<const uint4*>(q_desc + sw128_chunk_offset(qrow, chunk));
-        const int Q = q_norm[qrow];
         // G1 is a 32-row group, a 64-row tile, or (flag, sift_tc4's merged brackets) a 128-row tile of one image:
-        // recompute the tile's rows of this image exactly (2 or 4 per lane)
+        // recompute the tile's rows of this image exactly
         const bool wide = (cd.y & (POS_WIDE << 6)) != 0;
         const int64_t g1row = (int64_t)(cd.y & ((POS_WIDE << 6) - 1));
-        const int img = m_img_of[g1row];
         const int64_t tile0 = g1row & ~(int64_t)((wide ? 2 * TILE_N : TILE_N) - 1);
-        int va = INT_MIN, vb = INT_MIN;
-        {
-            const int64_t ra = tile0 + lane, rb = tile0 + 32 + lane;
-            if (m_img_of[ra] == img) va = exact_key(q, m_desc, ra, m_norm[ra]);
-            if (m_img_of[rb] == img) vb = exact_key(q, m_desc, rb, m_norm[rb]);
+        const uint4 q_even = *reinterpret_cast<const uint4*>(q_desc + sw128_chunk_offset(qrow, sub ^ slot));
+        const uint4 q_odd = *reinterpret_cast<const uint4*>(q_desc + sw128_chunk_offset(qrow, sub ^ (4 + slot)));
+        const int Q = q_norm[qrow];
+        const int img = m_img_of[g1row];
+        // this lane ends up with the rows tile0 + 4 (8 i + sub) + slot, i = 0..1 (0..3 when wide)
+        int64_t row[4];
+        int nm[4], io[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            row[i] = tile0 + 4 * (8 * i + sub) + slot;
+            const bool on = i < 2 || wide;
+            nm[i] = on ? m_norm[row[i]] : -1;
+            io[i] = on ? m_img_of[row[i]] : -1;
         }
-        int m1 = max(va, vb), s1 = min(va, vb);
-        if (wide) {   // warp-uniform
-            const int64_t rc = tile0 + 64 + lane, rd = tile0 + 96 + lane;
-            const int vc = exact_key(q, m_desc, rc, m_norm[rc]), vd = exact_key(q, m_desc, rd, m_norm[rd]);   // one image by construction
-            const int m2 = max(vc, vd), s2 = min(vc, vd);
-            s1 = max(min(m1, m2), max(s1, s2));
-            m1 = max(m1, m2);
+        unsigned d[4] = {0, 0, 0, 0};
+        dots64(m_desc, tile0, sub, slot, q_even, q_odd, d[0], d[1]);
+        if (wide) dots64(m_desc, tile0 + 64, sub, slot, q_even, q_odd, d[2], d[3]);   // warp-uniform
+        int m1 = INT_MIN, s1 = INT_MIN;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = (nm[i] >= 0 && io[i] == img) ? (int)(2u * d[i]) - nm[i] : INT_MIN;
+            s1 = max(s1, min(m1, k));
+            m1 = max(m1, k);
         }
         int k1, k2;
         warp_top2(m1, s1, k1, k2);
@@ -263,6 +311,9 @@ __global__ void sift_fixup3_kernel(const int4* __restrict__ cand, const unsigned
         }
         if (!decided) {  // exact scan of the whole image (warp-uniform branch)
             const int64_t r0 = m_dst_off[img], r1 = m_dst_off[img + 1];
+            uint4 q[8];
+#pragma unroll
+            for (int chunk = 0; chunk < 8; ++chunk) q[chunk] = *reinterpret_cast<const uint4*>(q_desc + sw128_chunk_offset(qrow, chunk));
             int b1 = INT_MIN, b2 = INT_MIN;
             for (int64_t r = r0 + lane; r < r1; r += 32) {
                 const int k = exact_key(q, m_desc, r, m_norm[r]);
