@@ -94,8 +94,16 @@ def run_bow(args, H, ClockSampler, peaks):
     def step_resident():
         result["dev"] = sbow.score_device(queries)
 
-    def step_e2e():
-        result["host"] = sbow.score(frames)
+    packed = _lib.pack_descriptors(_lib.BOWQ, frames)                   # float32 rows, as cv2.SIFT hands them over
+    pin = _lib.pinned_empty(packed[1].shape, packed[1].dtype)
+    pin[...] = packed[1]
+    packed_pinned = (packed[0], pin, packed[2])
+
+    def step_e2e():                                                     # rows in one pinned buffer (like bench.py's SIFT e2e)
+        result["host"] = sbow.score(None, packed=packed_pinned)
+
+    def step_e2e_list():                                                # a Python list of per-frame arrays: + the packing pass
+        result["host_list"] = sbow.score(frames)
 
     step_resident()
     torch.cuda.synchronize()
@@ -121,6 +129,8 @@ def run_bow(args, H, ClockSampler, peaks):
     ctx.profile_enable(False)
     launches = (ctx.launch_count() - l0) * args.steps // max(1, args.steps + args.warmup)
     ms_e2e = H.timed(step_e2e, args.steps, max(1, args.warmup // 2), use_events=False)
+    ms_e2e_list = H.timed(step_e2e_list, args.steps, max(1, args.warmup // 2), use_events=False)
+    assert np.array_equal(result["host_list"], result["host"])
     time.sleep(0.2)
     sampler.stop()
     sampler.join(timeout=2)
@@ -177,8 +187,8 @@ def run_bow(args, H, ClockSampler, peaks):
                                  % (per_gpu * 79 * 36864 / 1e6, per_gpu * BOW_W * 512 / 1e6)},
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": q_bytes, "d2h_bytes_per_step": int(n_frames * total_loc * BOW_IMAGES * 4),
-                        "ms_per_step": ms_e2e / args.steps,
-                        "path": "ShardedBow.score(host float32 descriptors) -> H2D -> fp16 rows -> tcgen05 -> float32 resolve -> tf-idf score -> all-gather -> D2H"},
+                        "ms_per_step": ms_e2e / args.steps, "ms_per_step_from_a_list_of_frame_arrays": ms_e2e_list / args.steps,
+                        "path": "ShardedBow.score(host float32 descriptors, one pinned buffer) -> H2D -> fp16 rows -> tcgen05 -> float32 resolve -> tf-idf score -> all-gather -> D2H"},
                 "gpu_launches": int(launches), "parity_pairs_checked": checked, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     sbow.close()
@@ -272,8 +282,16 @@ def run_orb(args, H, ClockSampler, peaks):
     def step_resident():
         result["dev"] = smap.match_counts_device(queries, algo=algo)
 
-    def step_e2e():
-        result["host"] = smap.match_counts(frames, algo=algo)
+    packed = _lib.pack_descriptors(_lib.ORB, frames)
+    pin = _lib.pinned_empty(packed[1].shape, packed[1].dtype)
+    pin[...] = packed[1]
+    packed_pinned = (packed[0], pin, packed[2])
+
+    def step_e2e():                                                     # rows in one pinned buffer (like bench.py's SIFT e2e)
+        result["host"] = smap.match_counts(None, algo=algo, packed=packed_pinned)
+
+    def step_e2e_list():                                                # a Python list of per-frame arrays: + the packing pass
+        result["host_list"] = smap.match_counts(frames, algo=algo)
 
     step_resident()
     torch.cuda.synchronize()
@@ -296,6 +314,8 @@ def run_orb(args, H, ClockSampler, peaks):
     s1 = ctx.stats()
     launches = (ctx.launch_count() - l0) * args.steps // max(1, args.steps + args.warmup)
     ms_e2e = H.timed(step_e2e, args.steps, max(1, args.warmup // 2), use_events=False)
+    ms_e2e_list = H.timed(step_e2e_list, args.steps, max(1, args.warmup // 2), use_events=False)
+    assert np.array_equal(result["host_list"], result["host"])
     time.sleep(0.2)
     sampler.stop()
     sampler.join(timeout=2)
@@ -341,8 +361,8 @@ def run_orb(args, H, ClockSampler, peaks):
                                  % ((per_gpu * 512 + n_frames * 512) * 256 / 1e6, per_gpu * 512 * 256 / 1e6, n_frames * 512 * 256 / 1e6)},
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(n_frames * ORB_N * 32), "d2h_bytes_per_step": int(n_frames * total * 4),
-                        "ms_per_step": ms_e2e / args.steps,
-                        "path": "ShardedMap.match_counts(host uint8 descriptors) -> H2D -> +-1 rows -> tcgen05 -> popc fix-up -> all-gather -> D2H"},
+                        "ms_per_step": ms_e2e / args.steps, "ms_per_step_from_a_list_of_frame_arrays": ms_e2e_list / args.steps,
+                        "path": "ShardedMap.match_counts(host uint8 descriptors, one pinned buffer) -> H2D -> +-1 rows -> tcgen05 -> popc fix-up -> all-gather -> D2H"},
                 "gpu_launches": int(launches), "parity_pairs_checked": checked, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     smap.close()

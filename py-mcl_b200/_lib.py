@@ -535,9 +535,10 @@ class BowIndex:
         _check(self.ctx._lib.mcl_bow_score_device(self._h, queries._h, _p(d_words_ptr) if d_words_ptr else None,
                                                   _p(d_scores_ptr), _p(stream) if stream else None), "mcl_bow_score_device")
 
-    def score(self, q_descs, want_words=False):
-        """-> (scores (n_queries, total_images) f32, words (n_loc, total rows) int32 or None)."""
-        off, cat, code = pack_descriptors(BOWQ, q_descs)
+    def score(self, q_descs, want_words=False, packed=None):
+        """-> (scores (n_queries, total_images) f32, words (n_loc, total rows) int32 or None).  `packed` = (offsets, matrix,
+        dtype code) skips the packing (e.g. rows already in one pinned buffer)."""
+        off, cat, code = packed if packed is not None else pack_descriptors(BOWQ, q_descs)
         nq = len(off) - 1
         scores = np.zeros((nq, self.total_images), dtype=np.float32)
         words = np.zeros((self.n_loc, int(off[-1])), dtype=np.int32) if want_words else None

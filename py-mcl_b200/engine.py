@@ -364,16 +364,17 @@ class ShardedBow(object):
         return (self.world > 1 and d is not None and d.get_backend(self.group) == "nccl" and
                 (self.local is None or isinstance(self.local, _lib.BowIndex)))
 
-    def score(self, q_descs):
+    def score(self, q_descs, packed=None):
         """(n_queries, total_images) float32 on every rank: BOWMatch of every query against every location.  With NCCL the
-        scores stay on the device: mcl_bow_score_device, one all-gather of the (zero-padded) column blocks, one D2H."""
+        scores stay on the device: mcl_bow_score_device, one all-gather of the (zero-padded) column blocks, one D2H.
+        `packed` = (offsets, matrix, dtype code) skips the packing."""
         lo, hi = self.bounds[self.rank]
         if self._on_device():
-            return self._score_nccl(q_descs)
+            return self._score_nccl(q_descs, packed)
         if self.local is None:
-            local = np.zeros((len(q_descs), 0), dtype=np.float32)
+            local = np.zeros((len(packed[0]) - 1 if packed is not None else len(q_descs), 0), dtype=np.float32)
         else:
-            local = self.local.score(q_descs)[0]
+            local = self.local.score(q_descs, packed=packed)[0] if packed is not None else self.local.score(q_descs)[0]
         assert local.shape[1] == hi - lo
         return gather_columns(local, self.bounds, self.group)
 
@@ -404,10 +405,10 @@ class ShardedBow(object):
         d.all_gather_into_tensor(self._all, self._mine, group=self.group)
         return self._all
 
-    def _score_nccl(self, q_descs):
+    def _score_nccl(self, q_descs, packed=None):
         import torch
         d = _dist()
-        F = len(q_descs)
+        F = len(packed[0]) - 1 if packed is not None else len(q_descs)
         lo, hi = self.bounds[self.rank]
         w = hi - lo
         maxw = max(h - l for l, h in self.bounds)
@@ -423,7 +424,7 @@ class ShardedBow(object):
         if self.local is not None and w:
             # the batch is built from a cached device tensor (pooled blocks inside the library): a host-built batch would
             # cudaMalloc / cudaFree per call, which costs milliseconds once NCCL has mapped its peers
-            off, cat, code = _lib.pack_descriptors(_lib.BOWQ, q_descs)
+            off, cat, code = packed if packed is not None else _lib.pack_descriptors(_lib.BOWQ, q_descs)
             tdt = torch.from_numpy(np.empty(0, dtype=cat.dtype)).dtype
             if getattr(self, "_dq", None) is None or self._dq.numel() < cat.size or self._dq.dtype != tdt:
                 self._dq = torch.empty(max(cat.size, 1), dtype=tdt, device="cuda")
