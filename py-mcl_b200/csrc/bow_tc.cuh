@@ -101,30 +101,68 @@ __global__ void __launch_bounds__(256) bow_merge_kernel(const int4* __restrict__
     }
 }
 
-// exclusive prefix sum of the bucket counts (one CTA); cnt[] becomes the running fill position of every bucket
+// exclusive prefix sum of the bucket counts (one CTA); cnt[] becomes the running fill position of every bucket.
+// Coalesced: a pass covers SCAN_TILES tiles of 1024 consecutive counters, thread t owning counter t of every tile (all loads of
+// a pass are independent and issued together); a tile is scanned with warp shuffles, the 32 x SCAN_TILES warp totals by one
+// warp.  (The first version gave each thread a contiguous run of n / 1024 counters: strided loads, 40 us for 40 000 buckets.)
+constexpr int SCAN_TILES = 8;
 __global__ void __launch_bounds__(1024) bow_scan_kernel(int* __restrict__ cnt, int n, unsigned int* __restrict__ state) {
-    __shared__ int part[1024];
-    const int per = (n + 1023) / 1024;
-    const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += cnt[i];
-    part[threadIdx.x] = sum;
+    __shared__ int wtot[SCAN_TILES * 32];
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    for (int base = 0; base < n; base += SCAN_TILES * 1024) {
+        int v[SCAN_TILES], inc[SCAN_TILES];
+#pragma unroll
+        for (int t = 0; t < SCAN_TILES; ++t) {
+            const int i = base + t * 1024 + (int)threadIdx.x;
+            v[t] = i < n ? cnt[i] : 0;
+        }
+#pragma unroll
+        for (int t = 0; t < SCAN_TILES; ++t) {
+            int x = v[t];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            inc[t] = x;                                   // inclusive within the warp
+            if (lane == 31) wtot[t * 32 + warp] = x;
+        }
         __syncthreads();
-        part[threadIdx.x] += v;
+        if (warp == 0) {                                  // exclusive scan of the SCAN_TILES * 32 warp totals, tile-major
+            int run = carry_s;
+#pragma unroll
+            for (int t = 0; t < SCAN_TILES; ++t) {
+                const int w = wtot[t * 32 + lane];
+                int x = w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, x, o);
+                    if (lane >= o) x += y;
+                }
+                wtot[t * 32 + lane] = run + x - w;
+                run += __shfl_sync(0xffffffffu, x, 31);
+            }
+            if (lane == 0) carry_s = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < SCAN_TILES; ++t) {
+            const int i = base + t * 1024 + (int)threadIdx.x;
+            if (i < n) cnt[i] = wtot[t * 32 + warp] + inc[t] - v[t];
+        }
         __syncthreads();
     }
-    int run = part[threadIdx.x] - sum;
-    for (int i = lo; i < hi; ++i) { const int c = cnt[i]; cnt[i] = run; run += c; }
-    if (threadIdx.x == 1023) state[3] = (unsigned int)part[1023];   // entries of the sorted list
+    if (threadIdx.x == 0) state[3] = (unsigned int)carry_s;   // entries of the sorted list
 }
 
 __global__ void __launch_bounds__(256) bow_scatter_kernel(const int* __restrict__ job_sel, int n_q, int64_t n_jobs, int subs_per_loc,
                                                           int* __restrict__ bucket_pos, int2* __restrict__ sorted) {
     for (int64_t job = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; job < n_jobs; job += (int64_t)gridDim.x * blockDim.x) {
-        const int base = (int)(job / n_q) * subs_per_loc;
+        const int loc = (int)(job / n_q), row = (int)(job - (int64_t)loc * n_q);
+        const int base = loc * subs_per_loc;
 #pragma unroll
         for (int which = 0; which < TOPG; ++which) {
             const int sel = job_sel[TOPG * job + which];
@@ -133,7 +171,7 @@ __global__ void __launch_bounds__(256) bow_scatter_kernel(const int* __restrict_
             for (int j = 0; j < SUBS; ++j)
                 if (sel & (1 << j)) {
                     const int sb = (sel >> 4) * SUBS + j;
-                    sorted[atomicAdd(&bucket_pos[base + sb], 1)] = make_int2((int)job, sb);   // entry = (job, sub-block of its location)
+                    sorted[atomicAdd(&bucket_pos[base + sb], 1)] = make_int2(row, base + sb);   // entry = (query row, bucket)
                 }
         }
     }
@@ -150,40 +188,42 @@ __global__ void __launch_bounds__(256) bow_scatter_kernel(const int* __restrict_
 // the SIMT kernel's tie-breaking is preserved.
 __global__ void __launch_bounds__(128) bow_resolve_kernel(const int2* __restrict__ sorted, const unsigned int* __restrict__ state,
                                                           int RESOLVE_RUN, const float* __restrict__ q_desc,
-                                                          int n_q, const float* __restrict__ voc, const int64_t* __restrict__ voc_off,
-                                                          unsigned long long* __restrict__ best) {
+                                                          int n_q, int subs_per_loc, const float* __restrict__ voc,
+                                                          const int64_t* __restrict__ voc_off, unsigned long long* __restrict__ best) {
     static_assert(SUB_W == 8, "the reduction below is written for 8 words");
     const int lane = threadIdx.x & 31;
     const int64_t n_sorted = (int64_t)state[3];
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     float4 cw[SUB_W];
     for (int64_t run = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; run * RESOLVE_RUN < n_sorted; run += n_warps) {
-        int cur_loc = -1, cur_sb = -1, n_words = 0;
+        int cur_bucket = -1, n_valid = 0, word0 = 0;
+        int64_t job0 = 0;
         const int64_t begin = run * (int64_t)RESOLVE_RUN, end = min(n_sorted, begin + RESOLVE_RUN);
-        int2 e_next = sorted[begin];
-        float4 o_next = reinterpret_cast<const float4*>(q_desc + (size_t)(e_next.x % n_q) * 128)[lane];
+        int2 e_next = sorted[begin];                     // entry = (query row, bucket = location * subs_per_loc + sub-block)
+        float4 o_next = reinterpret_cast<const float4*>(q_desc + (size_t)e_next.x * 128)[lane];
 #pragma unroll 1
         for (int64_t i = begin; i < end; ++i) {
             const int2 e = e_next;
             const float4 o = o_next;
             if (i + 1 < end) {
                 e_next = sorted[i + 1];
-                o_next = reinterpret_cast<const float4*>(q_desc + (size_t)(e_next.x % n_q) * 128)[lane];
+                o_next = reinterpret_cast<const float4*>(q_desc + (size_t)e_next.x * 128)[lane];
             }
-            const int job = e.x, sb = e.y;
-            const int loc = job / n_q;
-            if (loc != cur_loc || sb != cur_sb) {   // warp-uniform
+            if (e.y != cur_bucket) {   // warp-uniform; the divisions are paid once per bucket, not per entry
+                const int loc = e.y / subs_per_loc, sb = e.y - loc * subs_per_loc;
                 const int64_t v0 = voc_off[loc];
-                n_words = (int)(voc_off[loc + 1] - v0);
+                const int n_words = (int)(voc_off[loc + 1] - v0);
 #pragma unroll
                 for (int j = 0; j < SUB_W; ++j) {
                     const int w = min(sb * SUB_W + j, n_words - 1);
                     cw[j] = reinterpret_cast<const float4*>(voc + (v0 + w) * 128)[lane];
                 }
-                cur_loc = loc;
-                cur_sb = sb;
+                cur_bucket = e.y;
+                word0 = sb * SUB_W;
+                n_valid = n_words - word0;               // <= 0: a sub-block beyond the code book
+                job0 = (int64_t)loc * n_q;
             }
-            if (sb * SUB_W >= n_words) continue;   // a sub-block beyond the code book (warp-uniform)
+            if (n_valid <= 0) continue;                  // warp-uniform
             float pw[SUB_W];
 #pragma unroll
             for (int j = 0; j < SUB_W; ++j) {
@@ -215,14 +255,13 @@ __global__ void __launch_bounds__(128) bow_resolve_kernel(const int2* __restrict
             }
             dist += __shfl_xor_sync(0xffffffffu, dist, 2);
             dist += __shfl_xor_sync(0xffffffffu, dist, 1);   // lanes 4i .. 4i+3 own word i of the sub-block now
-            const int wi = sb * SUB_W + (lane >> 2);
-            unsigned long long bk = (wi < n_words) ? (((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)wi) : ~0ULL;
-#pragma unroll
-            for (int k = 16; k > 2; k >>= 1) {
-                const unsigned long long other = __shfl_xor_sync(0xffffffffu, bk, k);
-                bk = other < bk ? other : bk;
-            }
-            if (lane == 0) atomicMin(&best[job], bk);   // a row with several entries gets the best of them
+            // smallest distance, lowest word on ties: non-negative floats order like their bit patterns, so a 32-bit min
+            // over the warp and the first lane that holds it replace a 64-bit (distance, word) butterfly
+            const unsigned key = ((lane >> 2) < n_valid) ? __float_as_uint(dist) : 0xffffffffu;
+            const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+            const unsigned who = __ballot_sync(0xffffffffu, key == kmin);
+            if (lane == 0)
+                atomicMin(&best[job0 + e.x], ((unsigned long long)kmin << 32) | (unsigned)(word0 + ((__ffs(who) - 1) >> 2)));
         }
     }
 }

@@ -1648,7 +1648,7 @@ int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
                 // entries per warp: enough warps for ~16 per SM, runs of 8..64 entries
                 const int run_len = (int)std::max<int64_t>(8, std::min<int64_t>(64, (int64_t)nbest / ((int64_t)c->sm_count * 16)));
                 bow_resolve_kernel<<<grid_for((2 * (int64_t)nbest + run_len - 1) / run_len * 32, 128, c->sm_count * 32), 128, 0, st>>>(
-                    sorted, state, run_len, d_q, n_q, b->d_voc, b->d_voc_off, c->bow_best.as<unsigned long long>());
+                    sorted, state, run_len, d_q, n_q, subs_per_loc, b->d_voc, b->d_voc_off, c->bow_best.as<unsigned long long>());
             }
             {
                 ProfScope ps(c, PROF_VQ_RESCAN, st);
