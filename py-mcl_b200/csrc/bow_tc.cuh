@@ -276,7 +276,7 @@ __global__ void bow_decide_kernel(const int* __restrict__ bad, int64_t n_jobs, u
 // float32 direct-difference scan, lowest index on ties, merged with a 64-bit atomicMin -- one CTA per row took 0.28 ms for a
 // 10 000-word code book however few rows were queued (312 dependent trips through L2 per warp).
 // best[] gets (distance bits << 32 | word) like bow_vq_kernel's atomicMin key (pre-set to all ones by the caller).
-constexpr int RESCAN_SLICES = 16;
+constexpr int RESCAN_SLICES = 64;   // 16 slices left 2 CTAs per SM for ~20 queued rows: 2.3 TB/s of a DRAM-bound scan
 __global__ void __launch_bounds__(256) bow_rescan_kernel(const int* __restrict__ queue, const float* __restrict__ q_desc, int n_q,
                                                          const float* __restrict__ voc, const int64_t* __restrict__ voc_off,
                                                          unsigned long long* __restrict__ best, unsigned int* __restrict__ state) {

@@ -95,7 +95,8 @@ struct mcl_ctx {
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[PROF_N];
     // scratch
-    DevBuf stage, cand, dirty, flags /* ints: [0]=cand_count [1]=overflow [2]=bad [3]=rescans [6]=bow bad [8..10]=bow state; bytes 64..: statistics */, row_arg, bow_best, lap_pix, lap_meta, filt, tmp_counts,
+    DevBuf dirty_list;   // (frame * n_images + image) of the dirty pairs, compacted on the device
+    DevBuf stage, cand, dirty, flags /* ints: [0]=cand_count [1]=overflow [2]=bad [3]=rescans [4]=dirty pairs listed [6]=bow bad [8..10]=bow state; bytes 64..: statistics */, row_arg, bow_best, lap_pix, lap_meta, filt, tmp_counts,
         tmp_mask, tmp_words, tmp_scores, chi2, tq_off, tq_desc, tq_norm, tq_frame, bow_q8, bow_qaux, bow_tc_out, bow_sort, orb_q;
     int fixup_blocks = 0;
     bool tc9_attr = false;
@@ -385,6 +386,7 @@ extern "C" void mcl_shutdown(mcl_ctx* c) {
     for (auto& kv : c->lap_plans) cudaFree(kv.second.d_tab);
     for (auto& b : c->pool) cudaFree(b.first);
     c->pool.clear();
+    c->dirty_list.release();
     c->lap_vals.release();
     c->lap_list.release();
     for (cudaEvent_t e : c->part_events) cudaEventDestroy(e);
@@ -923,9 +925,12 @@ int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
     unsigned int* d_rescans = c->flags.as<unsigned int>() + 3;
     unsigned long long* d_stats = c->flags.as<unsigned long long>() + 8;   // [0] candidates, [1] dirty pairs (bytes 64..79)
     const size_t n_pairs = (size_t)std::max(1, q->n_queries) * std::max(1, m->n_images);
+    unsigned int* d_nlist = c->flags.as<unsigned int>() + 4;   // entries of the dirty-pair list
     CU(c->dirty.ensure(n_pairs));
+    CU(c->dirty_list.ensure(n_pairs * sizeof(int)));
     CU(cudaMemsetAsync(c->dirty.p, 0, n_pairs, st));
     CU(cudaMemsetAsync(d_overflow, 0, 4, st));
+    CU(cudaMemsetAsync(d_nlist, 0, 4, st));
     for (int qb0 = 0; qb0 < n_qblocks_total; qb0 += batch_qblocks) {
         const int nqb = std::min(batch_qblocks, n_qblocks_total - qb0);
         const mcl_map::ChunkSet* cs = pick_chunks(m->chunk_sets, nqb, c->sm_count, m->n_tiles);
@@ -1000,10 +1005,11 @@ int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
     // exact repair of the dirty (frame, image) pairs, if any: the SIMT kernel overwrites their counts
     {
         ProfScope ps(c, PROF_SIFT_SIMT, st);
-        dim3 grid(std::max(1, m->n_images), std::max(1, q->n_queries));
-        mcl::sift_simt_kernel<<<grid, 128, 0, st>>>((const uint8_t*)q->d_desc, q->d_norm, q->d_off, (const uint8_t*)m->d_desc,
-                                                    m->d_norm, m->d_dst_off, m->d_src_off, m->n_images, ratio, c->dirty.as<uint8_t>(),
-                                                    d_overflow, d_counts, d_stats + 1);
+        mcl::compact_dirty_kernel<<<grid_for((int64_t)n_pairs, 256, c->sm_count * 4), 256, 0, st>>>(
+            c->dirty.as<uint8_t>(), (int64_t)n_pairs, d_overflow, c->dirty_list.as<int>(), d_nlist);
+        mcl::sift_simt_list_kernel<<<c->sm_count * 8, 128, 0, st>>>(c->dirty_list.as<int>(), d_nlist, (const uint8_t*)q->d_desc, q->d_norm,
+                                                                   q->d_off, (const uint8_t*)m->d_desc, m->d_norm, m->d_dst_off,
+                                                                   m->d_src_off, m->n_images, ratio, d_counts, d_stats + 1);
     }
     CU(cudaGetLastError());
     return MCL_OK;
@@ -1044,9 +1050,12 @@ int launch_orb_tc(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, c
     int* d_overflow = c->flags.as<int>() + 1;
     unsigned long long* d_stats = c->flags.as<unsigned long long>() + 8;
     const size_t n_pairs = (size_t)std::max(1, q->n_queries) * std::max(1, m->n_images);
+    unsigned int* d_nlist = c->flags.as<unsigned int>() + 4;   // entries of the dirty-pair list
     CU(c->dirty.ensure(n_pairs));
+    CU(c->dirty_list.ensure(n_pairs * sizeof(int)));
     CU(cudaMemsetAsync(c->dirty.p, 0, n_pairs, st));
     CU(cudaMemsetAsync(d_overflow, 0, 4, st));
+    CU(cudaMemsetAsync(d_nlist, 0, 4, st));
     for (int qb0 = 0; qb0 < n_qblocks_total; qb0 += batch_qblocks) {
         const int nqb = std::min(batch_qblocks, n_qblocks_total - qb0);
         const mcl_map::ChunkSet* cs = pick_chunks(m->chunk_sets, nqb, c->sm_count, m->n_tiles, 1.5);
@@ -1095,9 +1104,11 @@ int launch_orb_tc(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, c
         zero_where_mask_kernel<<<grid_for((int64_t)n_pairs, 256, c->sm_count * 4), 256, 0, st>>>(d_counts, c->dirty.as<uint8_t>(), (int64_t)n_pairs, d_overflow);
         int64_t max_q = 0;
         for (int f = 0; f < q->n_queries; ++f) max_q = std::max(max_q, q->h_off[f + 1] - q->h_off[f]);
-        dim3 grid(std::max(1, m->n_images), std::max(1, q->n_queries), (unsigned)std::max<int64_t>(1, (max_q + 127) / 128));
-        mcl::orb_knn_kernel<<<grid, 128, 0, st>>>((const uint4*)q->d_desc, q->d_off, (const uint4*)m->d_desc, m->d_src_off, m->n_images,
-                                                  ratio, c->dirty.as<uint8_t>(), d_counts, d_overflow, d_stats + 1);
+        mcl::compact_dirty_kernel<<<grid_for((int64_t)n_pairs, 256, c->sm_count * 4), 256, 0, st>>>(
+            c->dirty.as<uint8_t>(), (int64_t)n_pairs, d_overflow, c->dirty_list.as<int>(), d_nlist);
+        mcl::orb_knn_list_kernel<<<c->sm_count * 8, 128, 0, st>>>(c->dirty_list.as<int>(), d_nlist, (int)std::max<int64_t>(1, (max_q + 127) / 128),
+                                                                 (const uint4*)q->d_desc, q->d_off, (const uint4*)m->d_desc, m->d_src_off,
+                                                                 m->n_images, ratio, d_counts, d_stats + 1);
     }
     c->launches++;
     CU(cudaGetLastError());
@@ -1131,7 +1142,7 @@ int match_device(mcl_map* m, mcl_queries* q, int mode, double ratio, const uint8
                 dim3 grid(ni, nf);
                 mcl::sift_simt_kernel<<<grid, 128, 0, st>>>((const uint8_t*)q->d_desc, q->d_norm, q->d_off,
                                                             (const uint8_t*)m->d_desc, m->d_norm, m->d_dst_off, m->d_src_off,
-                                                            ni, ratio, d_mask, nullptr, d_counts, nullptr);
+                                                            ni, ratio, d_mask, d_counts, nullptr);
             }
             CU(cudaGetLastError());
         } else {
@@ -1155,7 +1166,7 @@ int match_device(mcl_map* m, mcl_queries* q, int mode, double ratio, const uint8
                 } else if (mode == MCL_KNN2_RATIO) {
                     ProfScope ps(c, PROF_ORB, st);
                     mcl::orb_knn_kernel<<<grid, bt, 0, st>>>((const uint4*)q->d_desc, q->d_off, (const uint4*)m->d_desc,
-                                                              m->d_src_off, ni, ratio, d_mask, d_counts, nullptr, nullptr);
+                                                              m->d_src_off, ni, ratio, d_mask, d_counts, nullptr);
                 } else if (mode == MCL_CROSSCHECK) {
                     CU(c->row_arg.ensure((size_t)q->rows * ni * 4));
                     {
