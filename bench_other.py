@@ -10,7 +10,7 @@ import time
 REPO = os.path.dirname(os.path.abspath(__file__))
 
 BOW_W, BOW_IMAGES, BOW_NQ, BOW_FRAMES, BOW_LOC_PER_GPU = 10000, 100, 300, 50, 32
-ORB_N, ORB_FRAMES, ORB_IMG_PER_GPU = 500, 200, 400
+ORB_N, ORB_FRAMES, ORB_IMG_PER_GPU = int(os.environ.get("MCL_BENCH_ORB_N", "500")), 200, 400   # (the override is for kernel experiments)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -95,6 +95,7 @@ struct mcl_ctx {
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[PROF_N];
     // scratch
+    DevBuf diag9;        // MCL_TC9_DIAG
     DevBuf dirty_list;   // (frame * n_images + image) of the dirty pairs, compacted on the device
     DevBuf stage, cand, dirty, flags /* ints: [0]=cand_count [1]=overflow [2]=bad [3]=rescans [4]=dirty pairs listed [6]=bow bad [8..10]=bow state; bytes 64..: statistics */, row_arg, bow_best, lap_pix, lap_meta, filt, tmp_counts,
         tmp_mask, tmp_words, tmp_scores, chi2, tq_off, tq_desc, tq_norm, tq_frame, bow_q8, bow_qaux, bow_tc_out, bow_sort, orb_q;
@@ -369,6 +370,14 @@ extern "C" int mcl_init(int device_id, mcl_ctx** out) {
     e = c->flags.ensure(256);
     if (e != cudaSuccess) { delete c; return fail(MCL_ECUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
     cudaMemset(c->flags.p, 0, 256);
+    if (const char* e = getenv("MCL_OPT")) {   // experiments: "option=value,option=value" presets mcl_set_option
+        int o = 0, v = 0, n = 0;
+        while (sscanf(e, "%d=%d%n", &o, &v, &n) == 2) {
+            if (o >= 0 && o < 8) c->opt[o] = v;
+            e += n;
+            if (*e == ',') ++e;
+        }
+    }
     *out = c;
     return MCL_OK;
 }
@@ -387,6 +396,7 @@ extern "C" void mcl_shutdown(mcl_ctx* c) {
     for (auto& b : c->pool) cudaFree(b.first);
     c->pool.clear();
     c->dirty_list.release();
+    c->diag9.release();
     c->lap_vals.release();
     c->lap_list.release();
     for (cudaEvent_t e : c->part_events) cudaEventDestroy(e);
@@ -1084,11 +1094,29 @@ int launch_orb_tc(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, c
         if (c->opt[5] == 2 || (c->opt[5] == 0 && ((nqb % 2 == 0 && nqb >= 2) || nqb >= 32))) cl = 2;
         if (cl == 2 && c->tc9_clusters[0] < 1) cl = 1;
         const int64_t n_items = (int64_t)((nqb + cl - 1) / cl) * cs->n;
+        const int grid9 = cl == 2 ? 2 * (int)std::min<int64_t>(n_items, c->tc9_clusters[0]) : (int)std::min<int64_t>(n_items, c->sm_count);
+        static const bool diag9 = getenv("MCL_TC9_DIAG") != nullptr;
+        if (diag9) {
+            CU(c->diag9.ensure((size_t)grid9 * 5 * sizeof(long long)));
+            CU(cudaMemsetAsync(c->diag9.p, 0, (size_t)grid9 * 5 * sizeof(long long), st));
+            p.diag = c->diag9.as<long long>();
+        }
         {
             ProfScope ps(c, PROF_ORB, st);
             constexpr size_t smem = sizeof(Smem<KIND_ORB>);
-            if (cl == 2) CU(launch_cluster(tc9_kernel<KIND_ORB, 2>, 2 * (int)std::min<int64_t>(n_items, c->tc9_clusters[0]), THREADS, smem, st, 2, p));
-            else tc9_kernel<KIND_ORB, 1><<<(int)std::min<int64_t>(n_items, c->sm_count), THREADS, smem, st>>>(p);
+            if (cl == 2) CU(launch_cluster(tc9_kernel<KIND_ORB, 2>, grid9, THREADS, smem, st, 2, p));
+            else tc9_kernel<KIND_ORB, 1><<<grid9, THREADS, smem, st>>>(p);
+        }
+        if (diag9) {   // where the MMA warp waits (diagnostic; synchronises)
+            std::vector<long long> h((size_t)grid9 * 5);
+            CU(cudaStreamSynchronize(st));
+            CU(cudaMemcpy(h.data(), p.diag, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            double a = 0, b = 0, ac = 0, tot = 0, tiles = 0, tmax = 0;
+            for (int i = 0; i < grid9; ++i) { a += h[5 * i]; b += h[5 * i + 1]; ac += h[5 * i + 2]; tot += h[5 * i + 3]; tiles += h[5 * i + 4]; tmax = std::max(tmax, (double)h[5 * i + 3]); }
+            fprintf(stderr, "[mcl] tc9 ORB: %d CTAs, %d chunks x %d query groups; per CTA: %.0f tiles, %.0f cycles (max %.0f) = %.0f per tile; "
+                            "MMA warp waits: query tiles %.1f %%, map tiles %.1f %%, accumulators %.1f %%\n",
+                    grid9, cs->n, (int)((nqb + cl - 1) / cl), tiles / grid9, tot / grid9, tmax, tot / std::max(1.0, tiles),
+                    100 * a / tot, 100 * b / tot, 100 * ac / tot);
         }
         CU(cudaGetLastError());
         {

@@ -46,18 +46,17 @@ constexpr int ATILES = 2;
 constexpr int QBLK = ATILES * QTILE;          // 256 query rows per work item
 constexpr int ATOM_BYTES = TILE_N * 128;      // 16 KB: 128 rows x 128 K-bytes, SWIZZLE_128B
 constexpr int EXT_BYTES = TILE_N * 32;        // 4 KB: 128 rows x 32 K-bytes, no swizzle (8 x 16 B core matrices, LBO 128, SBO 256)
-constexpr int B_STAGES = 4;
 constexpr int EPI_WARPS = ATILES * 4;
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr int TMEM_COLS = 512;
-constexpr int META_CAP = 1024;                // tile records staged per chunk (32 KB)
+constexpr int META_CAP = 512;                 // tile records staged per chunk (16 KB); longer chunks read them from global memory
 
 template <int KIND> struct Shape;
 // A_COLS: TMEM columns per query tile (4 K-bytes per column).  ACCS accumulators of 128 columns fill the rest of the 512
 // columns: ORB has room for three, used round robin by the two query tiles (one spare: the MMAs of a tile need not wait for
 // the epilogue of the tile before last), BOW for two.
-template <> struct Shape<KIND_ORB> { static constexpr int KSTEPS = 8, TILE_BYTES = 2 * ATOM_BYTES, ROW_BYTES = 256, A_COLS = 64, ACCS = 3; };
-template <> struct Shape<KIND_BOW> { static constexpr int KSTEPS = 9, TILE_BYTES = 2 * ATOM_BYTES + EXT_BYTES, ROW_BYTES = 288, A_COLS = 72, ACCS = 2; };
+template <> struct Shape<KIND_ORB> { static constexpr int KSTEPS = 8, TILE_BYTES = 2 * ATOM_BYTES, ROW_BYTES = 256, A_COLS = 64, ACCS = 3, STAGES = 6; };
+template <> struct Shape<KIND_BOW> { static constexpr int KSTEPS = 9, TILE_BYTES = 2 * ATOM_BYTES + EXT_BYTES, ROW_BYTES = 288, A_COLS = 72, ACCS = 2, STAGES = 5; };
 constexpr int MAX_ACCS = 3;
 
 // per 128-row map tile
@@ -65,7 +64,8 @@ struct TileRec {
     int32_t seg[4];        // segment (map image / location) of each 32-row group, -1 = padding group
     int32_t nvalid;        // real rows of each group, one byte per group (0..32)
     int32_t end_mask;      // bit g: group g is the last group of its segment
-    int32_t plain;         // 1 = all four groups full, one segment, no segment end before the tile's end
+    int32_t plain;         // bit 0: all four groups full, one segment, no segment end before the tile's end;
+                           // ORB, bit 8 + g: the image of group g has at least two descriptors (others count 0)
     int32_t first_group;   // index of group 0 within its segment (BOW: word = 32 * group index + column)
 };
 static_assert(sizeof(TileRec) == 32, "tile record size");
@@ -93,14 +93,16 @@ struct Params {
                               // {key bits of the best group's four 8-word sub-blocks}
     int n_q, n_loc;
     int meta_cap;
+    long long* diag;          // optional (MCL_TC9_DIAG): per CTA, cycles the MMA warp waited for {query tiles, map tiles, accumulators} + total
 };
 
 template <int KIND>
 struct Smem {
-    alignas(1024) uint8_t stage[B_STAGES][Shape<KIND>::TILE_BYTES];
+    alignas(1024) uint8_t stage[Shape<KIND>::STAGES][Shape<KIND>::TILE_BYTES];
     alignas(16) TileRec rec[META_CAP];
-    alignas(8) uint64_t b_full[B_STAGES];
-    uint64_t b_empty[B_STAGES];
+    int16_t ratio_thr[260];   // ORB: largest best distance that passes the ratio test against a second-best distance d1
+    alignas(8) uint64_t b_full[Shape<KIND>::STAGES];
+    uint64_t b_empty[Shape<KIND>::STAGES];
     uint64_t acc_full[MAX_ACCS], acc_empty[MAX_ACCS];
     uint64_t a_full, a_free;
     uint32_t tmem_base;
@@ -145,13 +147,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
     const uint32_t leader = lane == 0;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < B_STAGES; ++i) { mbar_init(&s.b_full[i], 1); mbar_init(&s.b_empty[i], CL); }
+        for (int i = 0; i < S::STAGES; ++i) { mbar_init(&s.b_full[i], 1); mbar_init(&s.b_empty[i], CL); }
         for (int a = 0; a < MAX_ACCS; ++a) { mbar_init(&s.acc_full[a], 1); mbar_init(&s.acc_empty[a], 4); }
         mbar_init(&s.a_full, EPI_WARPS);
         mbar_init(&s.a_free, 1);
         mbar_fence_init();
     }
     if (warp == EPI_WARPS + 1) tmem_alloc<TMEM_COLS>(&s.tmem_base);
+    if (KIND == KIND_ORB) {
+        // Matcher.py:280 on Hamming distances reported as floats: (double)d0 < ratio * (double)d1.  As a table over d1: the
+        // largest d0 that passes is ceil(ratio * d1) - 1 (the product is one IEEE multiplication, as in the fix-up kernels)
+        for (int d1 = threadIdx.x; d1 <= 256; d1 += blockDim.x) {
+            const double t = __dmul_rn(p.ratio, (double)d1);
+            const double c = ceil(t) - 1.0;
+            s.ratio_thr[d1] = (int16_t)(c < -1.0 ? -1.0 : (c > 1000.0 ? 1000.0 : c));
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync();   // the peer's barriers exist before any multicast copy or commit can reach them
@@ -170,7 +181,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
         for (int item = item0; item < n_items; item += item_step) {
             const Chunk ch = p.chunks[item / n_qgroups];
             for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
-                const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
+                const uint32_t bs = bn % S::STAGES, bph = (bn / S::STAGES) & 1;
                 mbar_wait(&s.b_empty[bs], bph ^ 1);
                 mbar_arrive_expect_tx_if(leader, &s.b_full[bs], S::TILE_BYTES);
                 const uint8_t* src = p.m_tiles + (size_t)t * S::TILE_BYTES;
@@ -187,13 +198,20 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
         constexpr uint32_t idesc = KIND == KIND_ORB ? umma_idesc(/*c=S32*/ 2, /*a=s8*/ 1, /*b=s8*/ 1, QTILE, TILE_N)
                                                     : umma_idesc(/*c=F32*/ 1, /*a=f16*/ 0, /*b=f16*/ 0, QTILE, TILE_N);
         uint32_t bn = 0, item_n = 0;
+        long long w_a = 0, w_b = 0, w_acc = 0;
+        const bool diag = p.diag != nullptr;
+        const long long t_begin = diag ? clock64() : 0;
         for (int item = item0; item < n_items; item += item_step, ++item_n) {
             const Chunk ch = p.chunks[item / n_qgroups];
+            long long t0 = diag ? clock64() : 0;
             mbar_wait(&s.a_full, item_n & 1);
+            if (diag) w_a += clock64() - t0;
             tc_fence_after();
             for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
-                const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
+                const uint32_t bs = bn % S::STAGES, bph = (bn / S::STAGES) & 1;
+                if (diag) t0 = clock64();
                 mbar_wait(&s.b_full[bs], bph);
+                if (diag) w_b += clock64() - t0;
                 const uint32_t sb = smem_u32(s.stage[bs]);
                 const uint64_t d0 = umma_desc_sw128(sb), d1 = umma_desc_sw128(sb + ATOM_BYTES);
                 const uint64_t de = umma_desc_noswizzle(sb + 2 * ATOM_BYTES, 128, 256);
@@ -201,7 +219,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                 for (int a = 0; a < ATILES; ++a) {
                     // the n-th (tile, query tile) product of this CTA goes to accumulator n mod ACCS
                     const uint32_t n = ATILES * bn + a, x = n % ACCS, use = n / ACCS;
+                    if (diag) t0 = clock64();
                     mbar_wait(&s.acc_empty[x], (use & 1) ^ 1);
+                    if (diag) w_acc += clock64() - t0;
                     tc_fence_after();
                     const uint32_t d = tmem_base + ACC_COL0 + x * TILE_N;
                     const uint32_t ta = tmem_base + a * A_COLS;
@@ -220,6 +240,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
             tc_commit_if(leader, &s.a_free);
             __syncwarp();
         }
+        if (diag && lane == 0) {
+            long long* o = p.diag + 5 * blockIdx.x;
+            o[0] = w_a; o[1] = w_b; o[2] = w_acc; o[3] = clock64() - t_begin; o[4] = bn;
+        }
     } else {
         // ================= epilogue warps ===========================================================================
         const int atile = warp >> 2;
@@ -227,37 +251,48 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
         const int row_in_blk = atile * QTILE + lane_base + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)lane_base << 16);
         uint32_t bn = 0, item_n = 0;
+        // ORB: the query row of an item is fetched into registers while the PREVIOUS item is being matched (the tensor pipe idles
+        // from the last MMA of an item until the next item's query tiles are in tensor memory: with the loads in that window
+        // the MMA warp waited 4 % of the kernel for them).  BOW (short items, two accumulators) measured 4 % slower with the
+        // row held across the tile loop: it fetches at the top of the item.
+        constexpr bool PREFETCH = KIND == KIND_ORB;
+        constexpr int QW = S::ROW_BYTES / 4;   // 32-bit words per query row
+        uint32_t wq[QW];
+        int aux_next = -1;
+        Chunk ch_next = {};
+        auto fetch = [&](int item) {
+            if (item >= n_items) return;
+            const int qb = min((item % n_qgroups) * CL + (int)crank, p.n_qblocks - 1);
+            const int64_t qrow = (int64_t)qb * QBLK + row_in_blk;
+            const uint4* src = reinterpret_cast<const uint4*>(p.q_rows + (size_t)qrow * S::ROW_BYTES);
+#pragma unroll
+            for (int c = 0; c < QW / 4; ++c) {
+                const uint4 x = __ldg(src + c);
+                wq[4 * c] = x.x; wq[4 * c + 1] = x.y; wq[4 * c + 2] = x.z; wq[4 * c + 3] = x.w;
+            }
+            aux_next = p.q_aux[qrow];
+            ch_next = p.chunks[item / n_qgroups];
+        };
+        if (PREFETCH) fetch(item0);
         for (int item = item0; item < n_items; item += item_step, ++item_n) {
+            if (!PREFETCH) fetch(item);
             const int qb_raw = (item % n_qgroups) * CL + (int)crank;
             const int qb = min(qb_raw, p.n_qblocks - 1);   // an odd tail: the second CTA repeats the last block and reports nothing
-            const Chunk ch = p.chunks[item / n_qgroups];
+            const Chunk ch = ch_next;
             const int64_t qrow = (int64_t)qb * QBLK + row_in_blk;
+            const bool row_valid = aux_next >= 0 && qb_raw < p.n_qblocks;
             {   // this thread's query row -> tensor memory (row = TMEM lane, 4 K-bytes per column)
-                const uint4* src = reinterpret_cast<const uint4*>(p.q_rows + (size_t)qrow * S::ROW_BYTES);
-                uint32_t w[32];
                 mbar_wait(&s.a_free, (item_n & 1) ^ 1);   // every MMA of the previous item has read its query tiles
                 tc_fence_after();
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const uint4 x = __ldg(src + half * 8 + c);
-                        w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
-                    }
-                    tmem_st32(t_lane + atile * A_COLS + half * 32, w);
-                }
-                if (S::ROW_BYTES > 256) {
-                    uint32_t e[8];
-                    const uint4 x = __ldg(src + 16), y = __ldg(src + 17);
-                    e[0] = x.x; e[1] = x.y; e[2] = x.z; e[3] = x.w; e[4] = y.x; e[5] = y.y; e[6] = y.z; e[7] = y.w;
-                    tmem_st8(t_lane + atile * A_COLS + 64, e);
-                }
+                tmem_st32(t_lane + atile * A_COLS, reinterpret_cast<uint32_t(&)[32]>(wq[0]));
+                tmem_st32(t_lane + atile * A_COLS + 32, reinterpret_cast<uint32_t(&)[32]>(wq[32]));
+                if (S::ROW_BYTES > 256) tmem_st8(t_lane + atile * A_COLS + 64, reinterpret_cast<uint32_t(&)[8]>(wq[QW - 8]));
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s.a_full);
             }
-            const bool row_valid = p.q_aux[qrow] >= 0 && qb_raw < p.n_qblocks;
+            if (PREFETCH) fetch(item + item_step);
             // running top keys over the GROUP maxima of the current segment: ORB keeps the best group and the best key of the
             // others; BOW keeps the THREE best groups and the fourth-best key (a near-tie between up to three groups is then
             // resolved inside those groups instead of over the whole code book)
@@ -297,17 +332,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                 return r;
             };
             // end of a segment: ORB -> ratio gate + candidate; BOW -> the range's record for this row
-            auto finalize = [&](int seg, int t) {
+            auto finalize = [&](int seg, int t, bool two_rows) {
                 if (KIND == KIND_ORB) {
-                    // warp-uniform: the image's descriptor count, and whether this chunk owns the image (neighbouring chunks
-                    // share the tile in which one's last image ends and the other's first begins)
-                    const int nrows = (seg >= ch.img_begin && seg < ch.img_end) ? p.seg_rows[seg] : 0;
+                    // warp-uniform: the image has at least two descriptors (tile record: no global load on this path), and this
+                    // chunk owns the image (neighbouring chunks share the tile in which one's last image ends and the other's
+                    // first begins)
+                    const bool counted = two_rows && seg >= ch.img_begin && seg < ch.img_end;
                     bool pass = false;
-                    if (row_valid && nrows >= 2) {
+                    if (row_valid && counted) {
                         // a.b = 256 - 2 d.  The best distance is exact; the second best is at most that of the best OTHER
                         // group (unknown when the image has a single group: then the fix-up decides)
                         const int d0 = (256 - H1) >> 1;
-                        pass = H2 <= NONE || (double)d0 < __dmul_rn(p.ratio, (double)((256 - H2) >> 1));
+                        pass = H2 <= NONE || d0 <= (int)s.ratio_thr[(256 - H2) >> 1];
                     }
                     const unsigned bal = __ballot_sync(0xffffffffu, pass);
                     if (bal) {
@@ -348,7 +384,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                 tmem_wait_all();
                 tmem_fence_regs(v[0]);
                 tmem_fence_regs(v[1]);
-                const bool plain = r1.z != 0;   // warp-uniform
+                const bool plain = (r1.z & 1) != 0;   // warp-uniform
                 if (!plain) { mask_group(v[0], r1.x & 255); mask_group(v[1], (r1.x >> 8) & 255); }
                 int sub[4][4];
                 const int g0 = KIND == KIND_BOW ? group_max_sub(v[0], sub[0]) : sifttc3::group_max<0>(v[0]);
@@ -365,7 +401,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                 const int gbase = KIND == KIND_ORB ? 4 * t : r1.w;
                 if (plain) {
                     join(g0, gbase, sub[0]); join(g1, gbase + 1, sub[1]); join(g2, gbase + 2, sub[2]); join(g3, gbase + 3, sub[3]);
-                    if (r1.y & 8) finalize(r0.x, t);
+                    if (r1.y & 8) finalize(r0.x, t, (r1.z & (1 << 11)) != 0);
                 } else {
                     const int gm[4] = {g0, g1, g2, g3};
                     const int sg[4] = {r0.x, r0.y, r0.z, r0.w};
@@ -373,11 +409,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                     for (int g = 0; g < 4; ++g) {
                         if (sg[g] < 0) continue;   // padding group
                         join(gm[g], gbase + g, sub[g]);
-                        if (r1.y & (1 << g)) finalize(sg[g], t);
+                        if (r1.y & (1 << g)) finalize(sg[g], t, (r1.z & (256 << g)) != 0);
                     }
                 }
             }
-            if (KIND == KIND_BOW && H1 > NONE) finalize(ch.img_begin, ch.tile_end - 1);   // a range that ends inside its location
+            if (KIND == KIND_BOW && H1 > NONE) finalize(ch.img_begin, ch.tile_end - 1, true);   // a range that ends inside its location
         }
     }
     tc_fence_before();
@@ -446,6 +482,7 @@ __global__ void orb_build_rec_kernel(const int32_t* __restrict__ img_of, const i
     TileRec r;
     int nvalid = 0, end_mask = 0;
     bool plain = true;
+    int two_rows = 0;
     for (int g = 0; g < 4; ++g) {
         const int64_t r0 = (int64_t)t * TILE_N + g * GROUP;
         const int im = img_of[r0];
@@ -454,6 +491,7 @@ __global__ void orb_build_rec_kernel(const int32_t* __restrict__ img_of, const i
         if (im >= 0) {
             const int64_t rows = src_off[im + 1] - src_off[im];
             nv = (int)min((int64_t)GROUP, rows - (r0 - dst_off[im]));
+            if (rows >= 2) two_rows |= 256 << g;
         }
         nvalid |= nv << (8 * g);
         const int64_t rn = r0 + GROUP;
@@ -464,7 +502,7 @@ __global__ void orb_build_rec_kernel(const int32_t* __restrict__ img_of, const i
     }
     r.nvalid = nvalid;
     r.end_mask = end_mask;
-    r.plain = plain ? 1 : 0;
+    r.plain = (plain ? 1 : 0) | two_rows;
     r.first_group = 0;
     rec[t] = r;
 }
