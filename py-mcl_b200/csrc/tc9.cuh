@@ -120,7 +120,10 @@ __device__ __forceinline__ void umma_f16_ts_if(uint32_t pred, uint32_t tmem_d, u
 }
 
 // columns c >= nv of a 32-column group never win (padding rows of the last group of a segment)
+// (warp-uniform nv: full groups skip the 64 instructions -- the epilogue of a non-plain tile is one warp's dependent chain,
+// and at 500-row images every fourth tile is one)
 __device__ __forceinline__ void mask_group(uint32_t (&v)[32], int nv) {
+    if (nv >= 32) return;
 #pragma unroll
     for (int c = 0; c < 32; ++c) v[c] = c < nv ? v[c] : (uint32_t)INT_MIN;
 }
@@ -280,7 +283,6 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
             const int qb = min(qb_raw, p.n_qblocks - 1);   // an odd tail: the second CTA repeats the last block and reports nothing
             const Chunk ch = ch_next;
             const int64_t qrow = (int64_t)qb * QBLK + row_in_blk;
-            const bool row_valid = aux_next >= 0 && qb_raw < p.n_qblocks;
             {   // this thread's query row -> tensor memory (row = TMEM lane, 4 K-bytes per column)
                 mbar_wait(&s.a_free, (item_n & 1) ^ 1);   // every MMA of the previous item has read its query tiles
                 tc_fence_after();
@@ -292,6 +294,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s.a_full);
             }
+            const bool row_valid = aux_next >= 0 && qb_raw < p.n_qblocks;
             if (PREFETCH) fetch(item + item_step);
             // running top keys over the GROUP maxima of the current segment: ORB keeps the best group and the best key of the
             // others; BOW keeps the THREE best groups and the fourth-best key (a near-tie between up to three groups is then
@@ -379,24 +382,49 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                 mbar_wait(&s.acc_full[x], use & 1);
                 tc_fence_after();
                 const uint32_t tcol = t_lane + ACC_COL0 + x * TILE_N;
-                uint32_t v[2][32];
-                tmem_ld64(tcol, reinterpret_cast<uint32_t(&)[64]>(v));
-                tmem_wait_all();
-                tmem_fence_regs(v[0]);
-                tmem_fence_regs(v[1]);
+                // BOW reads both halves of the accumulator before anything is computed: the accumulator goes back to the MMA warp
+                // one tcgen05.ld latency after it was filled (one accumulator per query tile -- the time to this arrive is on
+                // the tensor pipe's critical path).  ORB has a spare accumulator and 64 registers of prefetched query row:
+                // it reads and reduces half by half.
+                constexpr bool WHOLE = KIND == KIND_BOW;
+                uint32_t v[2][32], u[WHOLE ? 2 : 1][32];
                 const bool plain = (r1.z & 1) != 0;   // warp-uniform
-                if (!plain) { mask_group(v[0], r1.x & 255); mask_group(v[1], (r1.x >> 8) & 255); }
                 int sub[4][4];
-                const int g0 = KIND == KIND_BOW ? group_max_sub(v[0], sub[0]) : sifttc3::group_max<0>(v[0]);
-                const int g1 = KIND == KIND_BOW ? group_max_sub(v[1], sub[1]) : sifttc3::group_max<0>(v[1]);
-                tmem_ld64(tcol + 64, reinterpret_cast<uint32_t(&)[64]>(v));
-                tmem_wait_all();
-                tmem_fence_regs(v[0]);
-                tmem_fence_regs(v[1]);
-                if (lane == 0) mbar_arrive(&s.acc_empty[x]);   // both halves are out of tensor memory: the accumulator is free
-                if (!plain) { mask_group(v[0], (r1.x >> 16) & 255); mask_group(v[1], (r1.x >> 24) & 255); }
-                const int g2 = KIND == KIND_BOW ? group_max_sub(v[0], sub[2]) : sifttc3::group_max<0>(v[0]);
-                const int g3 = KIND == KIND_BOW ? group_max_sub(v[1], sub[3]) : sifttc3::group_max<0>(v[1]);
+                int g0, g1, g2, g3;
+                if (WHOLE) {
+                    tmem_ld64(tcol, reinterpret_cast<uint32_t(&)[64]>(v));
+                    tmem_ld64(tcol + 64, reinterpret_cast<uint32_t(&)[64]>(u));
+                    tmem_wait_all();
+                    tmem_fence_regs(v[0]);
+                    tmem_fence_regs(v[1]);
+                    tmem_fence_regs(u[0]);
+                    tmem_fence_regs(u[WHOLE ? 1 : 0]);
+                    if (lane == 0) mbar_arrive(&s.acc_empty[x]);   // the accumulator is free
+                    if (!plain) {
+                        mask_group(v[0], r1.x & 255); mask_group(v[1], (r1.x >> 8) & 255);
+                        mask_group(u[0], (r1.x >> 16) & 255); mask_group(u[WHOLE ? 1 : 0], (r1.x >> 24) & 255);
+                    }
+                    g0 = group_max_sub(v[0], sub[0]);
+                    g1 = group_max_sub(v[1], sub[1]);
+                    g2 = group_max_sub(u[0], sub[2]);
+                    g3 = group_max_sub(u[WHOLE ? 1 : 0], sub[3]);
+                } else {
+                    tmem_ld64(tcol, reinterpret_cast<uint32_t(&)[64]>(v));
+                    tmem_wait_all();
+                    tmem_fence_regs(v[0]);
+                    tmem_fence_regs(v[1]);
+                    if (!plain) { mask_group(v[0], r1.x & 255); mask_group(v[1], (r1.x >> 8) & 255); }
+                    g0 = KIND == KIND_BOW ? group_max_sub(v[0], sub[0]) : sifttc3::group_max<0>(v[0]);
+                    g1 = KIND == KIND_BOW ? group_max_sub(v[1], sub[1]) : sifttc3::group_max<0>(v[1]);
+                    tmem_ld64(tcol + 64, reinterpret_cast<uint32_t(&)[64]>(v));
+                    tmem_wait_all();
+                    tmem_fence_regs(v[0]);
+                    tmem_fence_regs(v[1]);
+                    if (lane == 0) mbar_arrive(&s.acc_empty[x]);   // both halves are out of tensor memory: the accumulator is free
+                    if (!plain) { mask_group(v[0], (r1.x >> 16) & 255); mask_group(v[1], (r1.x >> 24) & 255); }
+                    g2 = KIND == KIND_BOW ? group_max_sub(v[0], sub[2]) : sifttc3::group_max<0>(v[0]);
+                    g3 = KIND == KIND_BOW ? group_max_sub(v[1], sub[3]) : sifttc3::group_max<0>(v[1]);
+                }
                 // group position: ORB = padded row / 32 over the whole map; BOW = group index within the location
                 const int gbase = KIND == KIND_ORB ? 4 * t : r1.w;
                 if (plain) {
