@@ -185,6 +185,15 @@ class ShardedMap(object):
         row_elems = cat.shape[1] if cat.ndim == 2 else _lib.ROW_DIM[self.local.kind]
         tdt = torch.from_numpy(np.empty(0, dtype=cat.dtype)).dtype
         main = torch.cuda.current_stream()
+        tl = [] if os.environ.get("MCL_ENGINE_TIMELINE") else None   # (label, timing event): device timeline of the call
+
+        def mark(label, stream):
+            if tl is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                tl.append((label, ev))
+
+        mark("start", main)
         d_mask = None
         if mask is not None:
             m = np.ascontiguousarray(np.asarray(mask)[:, self.lo:self.hi], dtype=np.uint8)
@@ -238,12 +247,14 @@ class ShardedMap(object):
                     g = self._buf("gather%d" % pi, (self.world, maxrun, row_elems), tdt)
                     a, b = runs[self.rank]
                     g[self.rank, :b - a].copy_(src[a:b], non_blocking=True)
+                    mark("part %d own run uploaded" % pi, side)
                     d.all_gather_into_tensor(g.view(self.world * maxrun, row_elems), g[self.rank], group=self.group)
                     for r, (x, y) in enumerate(runs):
                         dq[x:y].copy_(g[r, :y - x], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(side)
                     events.append(ev)
+                    mark("part %d rows on every rank (side stream)" % pi, side)
         counts = self._buf("counts_out", (F, self.n_images), torch.int32)
         batches = []
         for (f0, f1), ev in zip(parts, events):
@@ -253,12 +264,21 @@ class ShardedMap(object):
             q = _lib.QueryBatch(self.local.ctx, self.local.kind,
                                 device=(off[f0:f1 + 1] - r0, dq.data_ptr() + r0 * row_elems * cat.dtype.itemsize, code, _stream_handle(main)))
             batches.append(q)
+            mark("frames %d-%d ingested, matching starts" % (f0, f1), main)
             part = self.match_counts_device(q, mode=mode, ratio=ratio, d_mask=None if d_mask is None else d_mask[f0:f1],
                                             fill_value=fill_value, algo=algo)
             counts[f0:f1].copy_(part)
+            mark("frames %d-%d matched + counts gathered" % (f0, f1), main)
         host = self._buf("counts_host", (F, self.n_images), torch.int32, pinned=True)
         host.copy_(counts, non_blocking=True)
+        mark("counts on the host", main)
         main.synchronize()
+        if tl is not None and self.rank == 0:
+            import sys
+            side_s = self._bufs.get("side_stream")
+            if side_s is not None:
+                side_s.synchronize()
+            print("[engine] " + "; ".join("%s @ %.2f ms" % (lab, tl[0][1].elapsed_time(ev)) for lab, ev in tl[1:]), file=sys.stderr)
         for q in batches:
             q.validate()
             q.close()
