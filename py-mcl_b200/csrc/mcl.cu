@@ -1025,6 +1025,20 @@ int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
     return MCL_OK;
 }
 
+// MCL_TC9_DIAG: where the MMA warp of tc9_kernel waited (diagnostic; synchronises the stream)
+int tc9_diag_report(mcl_ctx* c, cudaStream_t st, const char* what, const long long* d_diag, int grid, int n_chunks, int n_qgroups) {
+    std::vector<long long> h((size_t)grid * 5);
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(h.data(), d_diag, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    double a = 0, b = 0, ac = 0, tot = 0, tiles = 0, tmax = 0;
+    for (int i = 0; i < grid; ++i) { a += h[5 * i]; b += h[5 * i + 1]; ac += h[5 * i + 2]; tot += h[5 * i + 3]; tiles += h[5 * i + 4]; tmax = std::max(tmax, (double)h[5 * i + 3]); }
+    fprintf(stderr, "[mcl] tc9 %s: %d CTAs, %d chunks x %d query groups; per CTA: %.0f tiles, %.0f cycles (max %.0f) = %.0f per tile; "
+                    "MMA warp waits: query tiles %.1f %%, map tiles %.1f %%, accumulators %.1f %%\n",
+            what, grid, n_chunks, n_qgroups, tiles / grid, tot / grid, tmax, tot / std::max(1.0, tiles), 100 * a / tot, 100 * b / tot, 100 * ac / tot);
+    (void)c;
+    return MCL_OK;
+}
+
 // ORB 2-NN + ratio on the tensor cores: tc9_kernel<KIND_ORB> (exact best key, lower bound of the second) + orb_fixup_kernel
 // (xor + popc on the best group) per batch of query blocks, then the SIMT kernel on the (frame, image) pairs that lost a
 // candidate to a full list.
@@ -1107,16 +1121,9 @@ int launch_orb_tc(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, c
             if (cl == 2) CU(launch_cluster(tc9_kernel<KIND_ORB, 2>, grid9, THREADS, smem, st, 2, p));
             else tc9_kernel<KIND_ORB, 1><<<grid9, THREADS, smem, st>>>(p);
         }
-        if (diag9) {   // where the MMA warp waits (diagnostic; synchronises)
-            std::vector<long long> h((size_t)grid9 * 5);
-            CU(cudaStreamSynchronize(st));
-            CU(cudaMemcpy(h.data(), p.diag, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-            double a = 0, b = 0, ac = 0, tot = 0, tiles = 0, tmax = 0;
-            for (int i = 0; i < grid9; ++i) { a += h[5 * i]; b += h[5 * i + 1]; ac += h[5 * i + 2]; tot += h[5 * i + 3]; tiles += h[5 * i + 4]; tmax = std::max(tmax, (double)h[5 * i + 3]); }
-            fprintf(stderr, "[mcl] tc9 ORB: %d CTAs, %d chunks x %d query groups; per CTA: %.0f tiles, %.0f cycles (max %.0f) = %.0f per tile; "
-                            "MMA warp waits: query tiles %.1f %%, map tiles %.1f %%, accumulators %.1f %%\n",
-                    grid9, cs->n, (int)((nqb + cl - 1) / cl), tiles / grid9, tot / grid9, tmax, tot / std::max(1.0, tiles),
-                    100 * a / tot, 100 * b / tot, 100 * ac / tot);
+        if (diag9) {
+            const int r = tc9_diag_report(c, st, "ORB", p.diag, grid9, cs->n, (int)((nqb + cl - 1) / cl));
+            if (r) return r;
         }
         CU(cudaGetLastError());
         {
@@ -1670,11 +1677,22 @@ int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
             if (c->opt[5] == 2 || (c->opt[5] == 0 && n_qblocks >= 2 && (n_qblocks % 2 == 0 || n_qblocks >= 16))) cl = 2;
             if (cl == 2 && c->tc9_clusters[1] < 1) cl = 1;
             const int64_t n_items = (int64_t)((n_qblocks + cl - 1) / cl) * sp->n_chunks;
+            const int grid9 = cl == 2 ? 2 * (int)std::min<int64_t>(n_items, c->tc9_clusters[1]) : (int)std::min<int64_t>(n_items, c->sm_count);
+            static const bool diag9 = getenv("MCL_TC9_DIAG") != nullptr;
+            if (diag9) {
+                CU(c->diag9.ensure((size_t)grid9 * 5 * sizeof(long long)));
+                CU(cudaMemsetAsync(c->diag9.p, 0, (size_t)grid9 * 5 * sizeof(long long), st));
+                p.diag = c->diag9.as<long long>();
+            }
             {
                 ProfScope ps(c, PROF_VQ_TC, st);
                 constexpr size_t smem = sizeof(Smem<KIND_BOW>);
-                if (cl == 2) CU(launch_cluster(tc9_kernel<KIND_BOW, 2>, 2 * (int)std::min<int64_t>(n_items, c->tc9_clusters[1]), THREADS, smem, st, 2, p));
-                else tc9_kernel<KIND_BOW, 1><<<(int)std::min<int64_t>(n_items, c->sm_count), THREADS, smem, st>>>(p);
+                if (cl == 2) CU(launch_cluster(tc9_kernel<KIND_BOW, 2>, grid9, THREADS, smem, st, 2, p));
+                else tc9_kernel<KIND_BOW, 1><<<grid9, THREADS, smem, st>>>(p);
+            }
+            if (diag9) {
+                const int r = tc9_diag_report(c, st, "BOW", p.diag, grid9, sp->n_chunks, (int)((n_qblocks + cl - 1) / cl));
+                if (r) return r;
             }
             CU(cudaGetLastError());
             {

@@ -256,8 +256,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
         uint32_t bn = 0, item_n = 0;
         // ORB: the query row of an item is fetched into registers while the PREVIOUS item is being matched (the tensor pipe idles
         // from the last MMA of an item until the next item's query tiles are in tensor memory: with the loads in that window
-        // the MMA warp waited 4 % of the kernel for them).  BOW (short items, two accumulators) measured 4 % slower with the
-        // row held across the tile loop: it fetches at the top of the item.
+        // the MMA warp waited 4 % of the kernel for them).  BOW measured slower with the row held across the tile loop (1294 ->
+        // 1319 cycles per tile pair although its wait for query tiles fell from 5.1 to 2.9 %: 72 more live registers in an
+        // epilogue that already holds the whole accumulator): it fetches at the top of the item.
         constexpr bool PREFETCH = KIND == KIND_ORB;
         constexpr int QW = S::ROW_BYTES / 4;   // 32-bit words per query row
         uint32_t wq[QW];
