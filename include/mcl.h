@@ -66,7 +66,8 @@ void mcl_host_free(void* p);
  * global memory; option 2 = 1: BOW word assignment on the float32 SIMT kernel only; option 3 = n > 0: cap the SIFT / ORB
  * candidate list at n entries (tests: forces the dirty-pair -> exact SIMT repair path); option 5: thread-block clusters of 2
  * sharing the map tiles by multicast, 0 = automatic, 1 = never, 2 = always; option 6 = n > 0: degrees between neighbouring map
- * images for mcl_filter_step's forward-command rule (the reference's 15, analyze.py:331-335). */
+ * images for mcl_filter_step's forward-command rule (the reference's 15, analyze.py:331-335).
+ * The environment variable MCL_OPT="option=value,..." presets these at mcl_init (experiments). */
 int mcl_set_option(mcl_ctx* ctx, int option, int value);
 /* number of kernels this library launched since mcl_init (bench.py's gpu_launches) */
 int64_t mcl_launch_count(mcl_ctx* ctx);
