@@ -34,7 +34,7 @@ constexpr float KEY_ABS = 4.0f;
 // k1 >= k2 >= k3, the fourth-best key k4 and the keys s[0..3] of the best group's four 8-word SUB-BLOCKS.  With the margin
 // 2 E(k1): the first k_i that trails k1 by more than the margin proves that the argmin lies in the groups before it, and
 // inside the best group only sub-blocks whose key is within the margin of k1 can hold it.  Every such sub-block becomes one
-// ENTRY (job, sub-block) -- most rows end with a single entry of 8 words -- the groups without sub-block keys (second,
+// ENTRY (query row, bucket = location x sub-blocks + sub-block) -- most rows end with a single entry of 8 words -- the groups without sub-block keys (second,
 // third) contribute all four of theirs; the resolve combines a row's entries with a 64-bit atomicMin on (distance, word).
 // If even k4 is within the margin the row is queued for a full rescan.
 // state: [0] = queued rows, [1] = run-the-SIMT-kernel flag (bow_decide_kernel), [2] = rows rescanned (statistics),

@@ -1017,6 +1017,7 @@ int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         ProfScope ps(c, PROF_SIFT_SIMT, st);
         mcl::compact_dirty_kernel<<<grid_for((int64_t)n_pairs, 256, c->sm_count * 4), 256, 0, st>>>(
             c->dirty.as<uint8_t>(), (int64_t)n_pairs, d_overflow, c->dirty_list.as<int>(), d_nlist);
+        c->launches++;   // two kernels in this scope
         mcl::sift_simt_list_kernel<<<c->sm_count * 8, 128, 0, st>>>(c->dirty_list.as<int>(), d_nlist, (const uint8_t*)q->d_desc, q->d_norm,
                                                                    q->d_off, (const uint8_t*)m->d_desc, m->d_norm, m->d_dst_off,
                                                                    m->d_src_off, m->n_images, ratio, d_counts, d_stats + 1);
@@ -1141,6 +1142,7 @@ int launch_orb_tc(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, c
         for (int f = 0; f < q->n_queries; ++f) max_q = std::max(max_q, q->h_off[f + 1] - q->h_off[f]);
         mcl::compact_dirty_kernel<<<grid_for((int64_t)n_pairs, 256, c->sm_count * 4), 256, 0, st>>>(
             c->dirty.as<uint8_t>(), (int64_t)n_pairs, d_overflow, c->dirty_list.as<int>(), d_nlist);
+        c->launches += 2;   // three kernels in this scope
         mcl::orb_knn_list_kernel<<<c->sm_count * 8, 128, 0, st>>>(c->dirty_list.as<int>(), d_nlist, (int)std::max<int64_t>(1, (max_q + 127) / 128),
                                                                  (const uint4*)q->d_desc, q->d_off, (const uint4*)m->d_desc, m->d_src_off,
                                                                  m->n_images, ratio, d_counts, d_stats + 1);

@@ -16,8 +16,9 @@
 // Pipeline (per CTA, persistent): TWO query tiles of 128 rows stationary in TENSOR MEMORY (64 / 72 columns each: row = lane,
 // 4 K-bytes per column), 128-column accumulators in the rest (BOW: two, one per query tile -- while the epilogue warps drain
 // one, the tensor pipe fills the other, 8-9 MMAs of 64 cycles each, twice sift_tc4's time per tile, so two tiles suffice where
-// sift_tc4 needs three; ORB: three, taken round robin, which first measured 78 % -> see DESIGN.md), 128-row map tiles (two SWIZZLE_128B atoms of 16 KB + a 4 KB no-swizzle extension slice) streamed by
-// ONE linear bulk copy each into a 4-stage ring; CTA pairs (clusters of 2) fetch every tile once and multicast it.
+// sift_tc4 needs three; ORB: three, taken round robin -- two measured 78 % of the tensor pipe), 128-row map
+// tiles (two SWIZZLE_128B atoms of 16 KB + a 4 KB no-swizzle extension slice) streamed by ONE linear bulk copy each into a ring
+// of 6 (ORB) / 5 (BOW) stages; CTA pairs (clusters of 2) fetch every tile once and multicast it.
 // Warps 0-7: epilogue (query tile = warp / 4, TMEM lane quadrant = warp % 4), warp 8: TMA producer, warp 9: MMA issuer.
 // Epilogue per 128 x 128 tile and thread: two tcgen05.ld.x64, four 32-column max trees, top-2 over GROUP maxima with the
 // best group's position.  Keys are exact (ORB) or approximate (BOW), there are no norm brackets.
