@@ -897,6 +897,20 @@ int tc9_prepare(mcl_ctx* c) {
     return MCL_OK;
 }
 
+// MCL_TC9_DIAG: where the MMA warp of tc9_kernel waited (diagnostic; synchronises the stream)
+int tc9_diag_report(mcl_ctx* c, cudaStream_t st, const char* what, const long long* d_diag, int grid, int n_chunks, int n_qgroups) {
+    std::vector<long long> h((size_t)grid * 5);
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(h.data(), d_diag, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    double a = 0, b = 0, ac = 0, tot = 0, tiles = 0, tmax = 0;
+    for (int i = 0; i < grid; ++i) { a += h[5 * i]; b += h[5 * i + 1]; ac += h[5 * i + 2]; tot += h[5 * i + 3]; tiles += h[5 * i + 4]; tmax = std::max(tmax, (double)h[5 * i + 3]); }
+    fprintf(stderr, "[mcl] tc9 %s: %d CTAs, %d chunks x %d query groups; per CTA: %.0f tiles, %.0f cycles (max %.0f) = %.0f per tile; "
+                    "MMA warp waits: query tiles %.1f %%, map tiles %.1f %%, accumulators %.1f %%\n",
+            what, grid, n_chunks, n_qgroups, tiles / grid, tot / grid, tmax, tot / std::max(1.0, tiles), 100 * a / tot, 100 * b / tot, 100 * ac / tot);
+    (void)c;
+    return MCL_OK;
+}
+
 // SIFT on the tensor cores: sift_tc4_kernel (bracketed pre-filter, candidates) + sift_fixup3_kernel (exact resolution) per
 // batch of query blocks, then the exact SIMT kernel on the (frame, image) pairs that lost a candidate to a full list.
 int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, cudaStream_t st) {
@@ -975,6 +989,13 @@ int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         }
         const int64_t n_items = (int64_t)((nqb + cl - 1) / cl) * cs->n;
         const int grid = cl > 1 ? cl * (int)std::min<int64_t>(n_items, c->max_clusters2) : (int)std::min<int64_t>(n_items, c->sm_count);
+        p.diag = nullptr;
+        static const bool diag4 = getenv("MCL_TC9_DIAG") != nullptr;
+        if (diag4 && c->opt[0] == 0) {
+            CU(c->diag9.ensure((size_t)grid * 5 * sizeof(long long)));
+            CU(cudaMemsetAsync(c->diag9.p, 0, (size_t)grid * 5 * sizeof(long long), st));
+            p.diag = c->diag9.as<long long>();
+        }
         {
             ProfScope ps(c, PROF_SIFT_TC, st);
             const int T = mcl::sifttc4::THREADS;
@@ -997,6 +1018,10 @@ int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
             else sift_tc4_kernel<0><<<grid, T, smem, st>>>(p);
         }
         CU(cudaGetLastError());
+        if (p.diag) {
+            const int r = tc9_diag_report(c, st, "SIFT (sift_tc4, tiles of 64 rows x 3 query tiles)", p.diag, grid, cs->n, (int)((nqb + cl - 1) / cl));
+            if (r) return r;
+        }
         {
             ProfScope ps(c, PROF_SIFT_FIX, st);
             // grid-stride over the candidates: exactly the co-resident blocks, so that no block starts a wave late
@@ -1023,20 +1048,6 @@ int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
                                                                    m->d_src_off, m->n_images, ratio, d_counts, d_stats + 1);
     }
     CU(cudaGetLastError());
-    return MCL_OK;
-}
-
-// MCL_TC9_DIAG: where the MMA warp of tc9_kernel waited (diagnostic; synchronises the stream)
-int tc9_diag_report(mcl_ctx* c, cudaStream_t st, const char* what, const long long* d_diag, int grid, int n_chunks, int n_qgroups) {
-    std::vector<long long> h((size_t)grid * 5);
-    CU(cudaStreamSynchronize(st));
-    CU(cudaMemcpy(h.data(), d_diag, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    double a = 0, b = 0, ac = 0, tot = 0, tiles = 0, tmax = 0;
-    for (int i = 0; i < grid; ++i) { a += h[5 * i]; b += h[5 * i + 1]; ac += h[5 * i + 2]; tot += h[5 * i + 3]; tiles += h[5 * i + 4]; tmax = std::max(tmax, (double)h[5 * i + 3]); }
-    fprintf(stderr, "[mcl] tc9 %s: %d CTAs, %d chunks x %d query groups; per CTA: %.0f tiles, %.0f cycles (max %.0f) = %.0f per tile; "
-                    "MMA warp waits: query tiles %.1f %%, map tiles %.1f %%, accumulators %.1f %%\n",
-            what, grid, n_chunks, n_qgroups, tiles / grid, tot / grid, tmax, tot / std::max(1.0, tiles), 100 * a / tot, 100 * b / tot, 100 * ac / tot);
-    (void)c;
     return MCL_OK;
 }
 

@@ -69,6 +69,7 @@ struct Params {
     int n_images;
     int q_row_base;
     int meta_cap;             // chunks up to this many tiles stage their metadata in shared memory (<= META_CAP)
+    long long* diag;          // optional (MCL_TC9_DIAG): per CTA, cycles the MMA warp waited for {query tiles, map tiles, accumulators} + total
 };
 
 // ------------------------------------------------------------------------------------------

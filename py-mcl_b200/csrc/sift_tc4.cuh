@@ -135,23 +135,32 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
         // ================= MMA issuer: A from tensor memory, B from shared memory, N = 128 ==============================
         constexpr uint32_t idesc = umma_idesc(/*c=S32*/ 2, /*a=u8*/ 0, /*b=u8*/ 0, QTILE, TILE_N);
         uint32_t bn = 0, item_n = 0;
+        long long w_a = 0, w_b = 0, w_acc = 0, t0 = 0;
+        const bool diag = p.diag != nullptr;
+        const long long t_begin = diag ? clock64() : 0;
         for (int item = item0; item < n_items; item += item_step, ++item_n) {
             const Chunk ch = p.chunks[item / n_qgroups];
+            if (diag) t0 = clock64();
             if (SS < ATILES) mbar_wait(&s.a_full, item_n & 1);
             if (SS > 0) mbar_wait(&s.as_full[item_n & 1], (item_n >> 1) & 1);
+            if (diag) w_a += clock64() - t0;
             tc_fence_after();
             for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
                 const uint32_t bs = bn % B_STAGES, bph = (bn / B_STAGES) & 1;
                 long long tm[8];
                 if (MODE == 5) tm[0] = clock64();
+                if (diag) t0 = clock64();
                 mbar_wait(&s.b_full[bs], bph);
+                if (diag) w_b += clock64() - t0;
                 if (MODE == 5) tm[1] = clock64();
                 const uint64_t b_desc = umma_desc_sw128(smem_u32(s.stage[bs]));
                 // round robin over the A tiles: accumulator a was filled first last time, so it is drained first; a blocking
                 // try_wait wakes ~60 cycles after the arrive, a polling loop over three barriers costs ~150 per probe
 #pragma unroll
                 for (int a = 0; a < ATILES; ++a) {
+                    if (diag) t0 = clock64();
                     mbar_wait(&s.acc_empty[a], (bn & 1) ^ 1);
+                    if (diag) w_acc += clock64() - t0;
                     tc_fence_after();
                     if (MODE == 5) tm[2 + a] = clock64();
                     const uint32_t d = tmem_base + ACC_COL0 + a * TILE_N;
@@ -177,6 +186,10 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
             tc_commit_if(leader, &s.a_free);
             if (SS > 0) tc_commit_if(leader, &s.as_empty[item_n & 1]);
             __syncwarp();
+        }
+        if (diag && lane == 0) {
+            long long* o = p.diag + 5 * blockIdx.x;
+            o[0] = w_a; o[1] = w_b; o[2] = w_acc; o[3] = clock64() - t_begin; o[4] = bn;
         }
     } else {
         // ================= epilogue warps ===========================================================================
