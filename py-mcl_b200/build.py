@@ -27,7 +27,9 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, os.path.join(CSRC, "mcl.cu")]
+    # MCL_NVCC_EXTRA: extra compile flags for experiments, e.g. "-DMCL_TC_DIAG" (the MMA-warp wait probe read by MCL_TC9_DIAG=1)
+    extra = os.environ.get("MCL_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, os.path.join(CSRC, "mcl.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         # with -Xptxas -v the tail of stderr is resource usage: show the diagnostics, not the last 4000 characters

@@ -990,7 +990,11 @@ int launch_sift_tc4(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts,
         const int64_t n_items = (int64_t)((nqb + cl - 1) / cl) * cs->n;
         const int grid = cl > 1 ? cl * (int)std::min<int64_t>(n_items, c->max_clusters2) : (int)std::min<int64_t>(n_items, c->sm_count);
         p.diag = nullptr;
+        #ifdef MCL_TC_DIAG
         static const bool diag4 = getenv("MCL_TC9_DIAG") != nullptr;
+#else
+        constexpr bool diag4 = false;
+#endif
         if (diag4 && c->opt[0] == 0) {
             CU(c->diag9.ensure((size_t)grid * 5 * sizeof(long long)));
             CU(cudaMemsetAsync(c->diag9.p, 0, (size_t)grid * 5 * sizeof(long long), st));
@@ -1121,7 +1125,11 @@ int launch_orb_tc(mcl_map* m, mcl_queries* q, double ratio, int32_t* d_counts, c
         if (cl == 2 && c->tc9_clusters[0] < 1) cl = 1;
         const int64_t n_items = (int64_t)((nqb + cl - 1) / cl) * cs->n;
         const int grid9 = cl == 2 ? 2 * (int)std::min<int64_t>(n_items, c->tc9_clusters[0]) : (int)std::min<int64_t>(n_items, c->sm_count);
+        #ifdef MCL_TC_DIAG
         static const bool diag9 = getenv("MCL_TC9_DIAG") != nullptr;
+#else
+        constexpr bool diag9 = false;
+#endif
         if (diag9) {
             CU(c->diag9.ensure((size_t)grid9 * 5 * sizeof(long long)));
             CU(cudaMemsetAsync(c->diag9.p, 0, (size_t)grid9 * 5 * sizeof(long long), st));
@@ -1691,7 +1699,11 @@ int bow_assign(mcl_bow* b, const float* d_q, int n_q, cudaStream_t st) {
             if (cl == 2 && c->tc9_clusters[1] < 1) cl = 1;
             const int64_t n_items = (int64_t)((n_qblocks + cl - 1) / cl) * sp->n_chunks;
             const int grid9 = cl == 2 ? 2 * (int)std::min<int64_t>(n_items, c->tc9_clusters[1]) : (int)std::min<int64_t>(n_items, c->sm_count);
-            static const bool diag9 = getenv("MCL_TC9_DIAG") != nullptr;
+            #ifdef MCL_TC_DIAG
+        static const bool diag9 = getenv("MCL_TC9_DIAG") != nullptr;
+#else
+        constexpr bool diag9 = false;
+#endif
             if (diag9) {
                 CU(c->diag9.ensure((size_t)grid9 * 5 * sizeof(long long)));
                 CU(cudaMemsetAsync(c->diag9.p, 0, (size_t)grid9 * 5 * sizeof(long long), st));

@@ -136,7 +136,13 @@ __global__ void __launch_bounds__(THREADS, 1) sift_tc4_kernel(const __grid_const
         constexpr uint32_t idesc = umma_idesc(/*c=S32*/ 2, /*a=u8*/ 0, /*b=u8*/ 0, QTILE, TILE_N);
         uint32_t bn = 0, item_n = 0;
         long long w_a = 0, w_b = 0, w_acc = 0, t0 = 0;
+        // the wait-time probe is compiled in only with -DMCL_TC_DIAG: even disabled at run time its branches in this loop cost the
+        // kernel 3.7 % (one issuing warp per query tile instead of one for all three was measured too: no difference)
+#ifdef MCL_TC_DIAG
         const bool diag = p.diag != nullptr;
+#else
+        constexpr bool diag = false;
+#endif
         const long long t_begin = diag ? clock64() : 0;
         for (int item = item0; item < n_items; item += item_step, ++item_n) {
             const Chunk ch = p.chunks[item / n_qgroups];

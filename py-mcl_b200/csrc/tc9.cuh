@@ -203,7 +203,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                                                     : umma_idesc(/*c=F32*/ 1, /*a=f16*/ 0, /*b=f16*/ 0, QTILE, TILE_N);
         uint32_t bn = 0, item_n = 0;
         long long w_a = 0, w_b = 0, w_acc = 0;
+#ifdef MCL_TC_DIAG   // compiled out by default: even disabled at run time the probe's branches slow the issue loop (BOW: 4 %)
         const bool diag = p.diag != nullptr;
+#else
+        constexpr bool diag = false;
+#endif
         const long long t_begin = diag ? clock64() : 0;
         for (int item = item0; item < n_items; item += item_step, ++item_n) {
             const Chunk ch = p.chunks[item / n_qgroups];
