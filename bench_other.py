@@ -153,7 +153,11 @@ def run_bow(args, H, ClockSampler, peaks):
                     "simt_fallback_ms_per_step": prof["bow_vq"], "score_ms_per_step": prof["bow_score"],
                     "vq_plus_resolve_over_tensor_pass": (prof["bow_vq_tc"] + prof["bow_resolve"] + prof["bow_rescan"]) / prof["bow_vq_tc"],
                     "resolve_entries_last_call": st["bow_resolve_entries"], "rows_x_locations": n_frames * BOW_NQ * per_gpu,
-                    "algorithmic_flops_per_unit": 2.0 * BOW_NQ * BOW_W * 128 / BOW_IMAGES, "traffic": None}
+                    "algorithmic_flops_per_unit": 2.0 * BOW_NQ * BOW_W * 128 / BOW_IMAGES,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default configuration (ncu --set full,
+                    # profiles/r2_bow_tc9_final_ncu_full.md): the fp16 tiles (93 MB) once + the records written
+                    "traffic": 111.4e6 if (n_frames == BOW_FRAMES and per_gpu == BOW_LOC_PER_GPU) else None,
+                    "traffic_unit": "bytes per launch (ncu, profiles/r2_bow_tc9_final_ncu_full.md)"}
         cpu, checked = None, 0
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -339,7 +343,11 @@ def run_orb(args, H, ClockSampler, peaks):
                     "fixup_ms_per_step": prof["orb_fixup"], "prep_ms_per_step": prof["ingest"],
                     "candidates_per_row_image": (s1["orb_candidates"] - s0["orb_candidates"]) / (args.steps + args.warmup) / (n_frames * ORB_N * per_gpu),
                     "repaired_pairs_per_step": (s1["repaired_pairs"] - s0["repaired_pairs"]) / (args.steps + args.warmup),
-                    "algorithmic_ops_per_unit": 2.0 * ORB_N * ORB_N * 256, "traffic": None}
+                    "algorithmic_ops_per_unit": 2.0 * ORB_N * ORB_N * 256,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default configuration (ncu --set full,
+                    # profiles/r2_orb_tc9_final_ncu_full.md): map tiles 52 MB + query rows 26 MB once, the rest from L2
+                    "traffic": 83.2e6 if (n_frames == ORB_FRAMES and per_gpu == ORB_IMG_PER_GPU and args.algo == 1 and ORB_N == 500) else None,
+                    "traffic_unit": "bytes per launch (ncu, profiles/r2_orb_tc9_final_ncu_full.md)"}
         cpu, checked = None, 0
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
