@@ -255,7 +255,14 @@ class ShardedMap(object):
                     ev.record(side)
                     events.append(ev)
                     mark("part %d rows on every rank (side stream)" % pi, side)
-        counts = self._buf("counts_out", (F, self.n_images), torch.int32)
+        # this rank's counts of every part land in ONE (F, widest shard) block, gathered once at the end: a gather per part put a
+        # rendezvous of all ranks in the middle of the call (at 8 GPUs the step waited there for the slowest process)
+        w = self.hi - self.lo
+        maxw = max(h - l for l, h in self.bounds)
+        mine = self._buf("counts_local", (F, maxw), torch.int32)
+        if w < maxw:
+            mine.zero_()
+        tight = mine if w == maxw else self._buf("counts_tight", (F, max(w, 1)), torch.int32)
         batches = []
         for (f0, f1), ev in zip(parts, events):
             if ev is not None:
@@ -265,10 +272,23 @@ class ShardedMap(object):
                                 device=(off[f0:f1 + 1] - r0, dq.data_ptr() + r0 * row_elems * cat.dtype.itemsize, code, _stream_handle(main)))
             batches.append(q)
             mark("frames %d-%d ingested, matching starts" % (f0, f1), main)
-            part = self.match_counts_device(q, mode=mode, ratio=ratio, d_mask=None if d_mask is None else d_mask[f0:f1],
-                                            fill_value=fill_value, algo=algo)
-            counts[f0:f1].copy_(part)
-            mark("frames %d-%d matched + counts gathered" % (f0, f1), main)
+            if w:
+                self.local.match_counts_device(q, tight[f0:f1].data_ptr(), mode=mode, ratio=ratio,
+                                               d_mask_ptr=None if d_mask is None else d_mask[f0:f1].data_ptr(),
+                                               fill_value=fill_value, algo=algo, stream=_stream_handle(main))
+            mark("frames %d-%d matched" % (f0, f1), main)
+        if w and tight is not mine:
+            mine[:, :w].copy_(tight)
+        allc = self._buf("counts_all", (self.world, F, maxw), torch.int32)
+        d.all_gather_into_tensor(allc, mine, group=self.group)
+        counts = self._buf("counts_out", (F, self.n_images), torch.int32)
+        if all(h - l == maxw for l, h in self.bounds):
+            counts.view(F, self.world, maxw).copy_(allc.permute(1, 0, 2))
+        else:
+            for r, (l, h) in enumerate(self.bounds):
+                if h > l:
+                    counts[:, l:h].copy_(allc[r][:, :h - l])
+        mark("counts gathered", main)
         host = self._buf("counts_host", (F, self.n_images), torch.int32, pinned=True)
         host.copy_(counts, non_blocking=True)
         mark("counts on the host", main)
