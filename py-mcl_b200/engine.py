@@ -181,6 +181,8 @@ class ShardedMap(object):
         d = _dist()
         off, cat, code = packed if packed is not None else _lib.pack_descriptors(self.local.kind, q_descs)
         F = len(off) - 1
+        if F == 0:
+            return np.zeros((0, self.n_images), dtype=np.int32)
         rows = int(off[-1])
         row_elems = cat.shape[1] if cat.ndim == 2 else _lib.ROW_DIM[self.local.kind]
         tdt = torch.from_numpy(np.empty(0, dtype=cat.dtype)).dtype
