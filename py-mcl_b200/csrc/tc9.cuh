@@ -174,16 +174,29 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
     const uint32_t tmem_base = s.tmem_base;
     // work items: (chunk, group of CL query blocks); CTA `crank` of the cluster takes query block group * CL + crank
     const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    // ORB: items are numbered query-group major (item = query group * n_chunks + chunk) and every cluster takes a CONTIGUOUS
+    // range of them: consecutive items then share their query tiles, which stay in tensor memory -- the tiles are reloaded (and
+    // the tensor pipe drained for it) only when the query group changes, once or twice per cluster instead of once per item
+    // (1102 -> 1063 cycles per tile pair).  BOW keeps items dealt round robin, chunk major (item = chunk * n_qgroups + query
+    // group): all clusters then stream the SAME code-book range at the same time; with contiguous ranges its wait for query
+    // tiles fell from 5.1 to 1.0 % but the wait for map tiles rose from 4.8 to 7.8 % (93 MB of tiles read in 32 places at
+    // once) -- 1294 -> 1309 cycles.
+    constexpr bool CONTIG = KIND == KIND_ORB;
     const int n_qgroups = (p.n_qblocks + CL - 1) / CL;
     const int n_items = n_qgroups * p.n_chunks;
-    const int item0 = blockIdx.x / CL, item_step = gridDim.x / CL;
+    const int n_workers = gridDim.x / CL, worker = blockIdx.x / CL;
+    const int item_begin = CONTIG ? (int)((int64_t)n_items * worker / n_workers) : worker;
+    const int item_end = CONTIG ? (int)((int64_t)n_items * (worker + 1) / n_workers) : n_items;
+    const int item_step = CONTIG ? 1 : n_workers;
+    auto qg_of = [&](int item) { return CONTIG ? item / p.n_chunks : item % n_qgroups; };
+    auto ck_of = [&](int item) { return CONTIG ? item % p.n_chunks : item / n_qgroups; };
     constexpr uint16_t ALL_CTAS = (1u << CL) - 1u;
 
     if (warp == EPI_WARPS) {
         // ================= TMA producer: one 128-row map tile per stage ===============================================
         uint32_t bn = 0;
-        for (int item = item0; item < n_items; item += item_step) {
-            const Chunk ch = p.chunks[item / n_qgroups];
+        for (int item = item_begin; item < item_end; item += item_step) {
+            const Chunk ch = p.chunks[ck_of(item)];
             for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
                 const uint32_t bs = bn % S::STAGES, bph = (bn / S::STAGES) & 1;
                 mbar_wait(&s.b_empty[bs], bph ^ 1);
@@ -201,7 +214,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
         // ================= MMA issuer: A from tensor memory, B from shared memory, N = 128 ==============================
         constexpr uint32_t idesc = KIND == KIND_ORB ? umma_idesc(/*c=S32*/ 2, /*a=s8*/ 1, /*b=s8*/ 1, QTILE, TILE_N)
                                                     : umma_idesc(/*c=F32*/ 1, /*a=f16*/ 0, /*b=f16*/ 0, QTILE, TILE_N);
-        uint32_t bn = 0, item_n = 0;
+        uint32_t bn = 0, load_n = 0;
+        int prev_qg = -1;
         long long w_a = 0, w_b = 0, w_acc = 0;
 #ifdef MCL_TC_DIAG   // compiled out by default: even disabled at run time the probe's branches slow the issue loop (BOW: 4 %)
         const bool diag = p.diag != nullptr;
@@ -209,12 +223,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
         constexpr bool diag = false;
 #endif
         const long long t_begin = diag ? clock64() : 0;
-        for (int item = item0; item < n_items; item += item_step, ++item_n) {
-            const Chunk ch = p.chunks[item / n_qgroups];
+        for (int item = item_begin; item < item_end; item += item_step) {
+            const int qg = qg_of(item);
+            const Chunk ch = p.chunks[ck_of(item)];
             long long t0 = diag ? clock64() : 0;
-            mbar_wait(&s.a_full, item_n & 1);
-            if (diag) w_a += clock64() - t0;
-            tc_fence_after();
+            if (qg != prev_qg) {   // new query tiles
+                mbar_wait(&s.a_full, load_n & 1);
+                if (diag) w_a += clock64() - t0;
+                tc_fence_after();
+                prev_qg = qg;
+            }
             for (int t = ch.tile_begin; t < ch.tile_end; ++t, ++bn) {
                 const uint32_t bs = bn % S::STAGES, bph = (bn / S::STAGES) & 1;
                 if (diag) t0 = clock64();
@@ -245,7 +263,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                 else tc_commit_multicast_if(leader, &s.b_empty[bs], ALL_CTAS);
                 __syncwarp();
             }
-            tc_commit_if(leader, &s.a_free);
+            if (item + item_step >= item_end || qg_of(item + item_step) != qg) {   // the last item that reads these query tiles
+                tc_commit_if(leader, &s.a_free);
+                ++load_n;
+            }
             __syncwarp();
         }
         if (diag && lane == 0) {
@@ -258,20 +279,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
         const int lane_base = (warp & 3) * 32;
         const int row_in_blk = atile * QTILE + lane_base + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)lane_base << 16);
-        uint32_t bn = 0, item_n = 0;
-        // ORB: the query row of an item is fetched into registers while the PREVIOUS item is being matched (the tensor pipe idles
-        // from the last MMA of an item until the next item's query tiles are in tensor memory: with the loads in that window
-        // the MMA warp waited 4 % of the kernel for them).  BOW measured slower with the row held across the tile loop (1294 ->
-        // 1319 cycles per tile pair although its wait for query tiles fell from 5.1 to 2.9 %: 72 more live registers in an
-        // epilogue that already holds the whole accumulator): it fetches at the top of the item.
+        uint32_t bn = 0, load_n = 0;
+        int prev_qg = -1;
+        // ORB: the query row of the NEXT query group is fetched into registers while the current one is being matched (the
+        // tensor pipe idles from the last MMA on a set of query tiles until the next set is in tensor memory).  BOW measured
+        // slower with the row held across the tile loop (72 more live registers in an epilogue that already holds the whole
+        // accumulator): it fetches when the group changes.
         constexpr bool PREFETCH = KIND == KIND_ORB;
         constexpr int QW = S::ROW_BYTES / 4;   // 32-bit words per query row
         uint32_t wq[QW];
         int aux_next = -1;
-        Chunk ch_next = {};
-        auto fetch = [&](int item) {
-            if (item >= n_items) return;
-            const int qb = min((item % n_qgroups) * CL + (int)crank, p.n_qblocks - 1);
+        auto fetch = [&](int qg) {
+            const int qb = min(qg * CL + (int)crank, p.n_qblocks - 1);
             const int64_t qrow = (int64_t)qb * QBLK + row_in_blk;
             const uint4* src = reinterpret_cast<const uint4*>(p.q_rows + (size_t)qrow * S::ROW_BYTES);
 #pragma unroll
@@ -280,17 +299,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                 wq[4 * c] = x.x; wq[4 * c + 1] = x.y; wq[4 * c + 2] = x.z; wq[4 * c + 3] = x.w;
             }
             aux_next = p.q_aux[qrow];
-            ch_next = p.chunks[item / n_qgroups];
         };
-        if (PREFETCH) fetch(item0);
-        for (int item = item0; item < n_items; item += item_step, ++item_n) {
-            if (!PREFETCH) fetch(item);
-            const int qb_raw = (item % n_qgroups) * CL + (int)crank;
+        static_assert(!PREFETCH || CONTIG, "the prefetch below assumes contiguous item ranges");
+        if (PREFETCH && item_begin < item_end) fetch(qg_of(item_begin));
+        bool row_valid = false;
+        for (int item = item_begin; item < item_end; item += item_step) {
+            const int qg = qg_of(item);
+            const Chunk ch = p.chunks[ck_of(item)];
+            const int qb_raw = qg * CL + (int)crank;
             const int qb = min(qb_raw, p.n_qblocks - 1);   // an odd tail: the second CTA repeats the last block and reports nothing
-            const Chunk ch = ch_next;
             const int64_t qrow = (int64_t)qb * QBLK + row_in_blk;
-            {   // this thread's query row -> tensor memory (row = TMEM lane, 4 K-bytes per column)
-                mbar_wait(&s.a_free, (item_n & 1) ^ 1);   // every MMA of the previous item has read its query tiles
+            if (qg != prev_qg) {   // this thread's query row -> tensor memory (row = TMEM lane, 4 K-bytes per column)
+                if (!PREFETCH) fetch(qg);
+                mbar_wait(&s.a_free, (load_n & 1) ^ 1);   // every MMA on the previous query tiles has retired
                 tc_fence_after();
                 tmem_st32(t_lane + atile * A_COLS, reinterpret_cast<uint32_t(&)[32]>(wq[0]));
                 tmem_st32(t_lane + atile * A_COLS + 32, reinterpret_cast<uint32_t(&)[32]>(wq[32]));
@@ -299,9 +320,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc9_kernel(const __grid_constant__
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s.a_full);
+                ++load_n;
+                prev_qg = qg;
+                row_valid = aux_next >= 0 && qb_raw < p.n_qblocks;
+                if (PREFETCH && (int64_t)(qg + 1) * p.n_chunks < item_end) fetch(qg + 1);   // the group this cluster takes next
             }
-            const bool row_valid = aux_next >= 0 && qb_raw < p.n_qblocks;
-            if (PREFETCH) fetch(item + item_step);
             // running top keys over the GROUP maxima of the current segment: ORB keeps the best group and the best key of the
             // others; BOW keeps the THREE best groups and the fourth-best key (a near-tie between up to three groups is then
             // resolved inside those groups instead of over the whole code book)
