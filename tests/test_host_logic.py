@@ -175,7 +175,10 @@ class OracleLocal(object):
         self.descs = descs
         self.n_images = len(descs)
 
-    def match_counts(self, q_descs, mode=0, ratio=0.7, mask=None, fill_value=1, algo=0):
+    def match_counts(self, q_descs, mode=0, ratio=0.7, mask=None, fill_value=1, algo=0, packed=None):
+        if packed is not None:   # (offsets, matrix, dtype code): the rows of all frames in one buffer
+            off, cat, _ = packed
+            q_descs = [cat[off[f]:off[f + 1]] for f in range(len(off) - 1)]
         out = np.zeros((len(q_descs), len(self.descs)), dtype=np.int32)
         for f, q in enumerate(q_descs):
             for i, m in enumerate(self.descs):
@@ -193,7 +196,10 @@ class OracleBow:
         self.locations = locations
         self.W = num_words
 
-    def score(self, q_descs, want_words=False):
+    def score(self, q_descs, want_words=False, packed=None):
+        if packed is not None:
+            off, cat, _ = packed
+            q_descs = [cat[off[f]:off[f + 1]] for f in range(len(off) - 1)]
         cols = sum(len(l[0]) for l in self.locations)
         out = np.zeros((len(q_descs), cols), dtype=np.float32)
         for f, q in enumerate(q_descs):
@@ -235,6 +241,20 @@ def test_sharded_map_single_process_matches_unsharded():
     sm = engine.ShardedMap("SIFT", map_des, local_factory=OracleLocal)
     want = OracleLocal(map_des).match_counts(frames)
     assert np.array_equal(sm.match_counts(frames), want)
+    # the same batch handed over as one packed buffer (what bench.py's end-to-end path does with pinned memory)
+    packed = _lib.pack_descriptors(_lib.SIFT, frames)
+    assert np.array_equal(sm.match_counts(None, packed=packed), want)
+
+
+def test_sharded_bow_accepts_a_packed_batch():
+    locs = synthetic_bow_locations(4, 3)
+    rng = np.random.default_rng(5)
+    frames = [synth.sift_like(rng, 17), synth.sift_like(rng, 9), None]
+    sb = engine.ShardedBow(len(locs), lambda i: locs[i], local_factory=OracleBow)
+    want = sb.score(frames)
+    packed = _lib.pack_descriptors(_lib.BOWQ, frames)
+    assert packed[0].tolist() == [0, 17, 26, 26]
+    assert np.array_equal(sb.score(None, packed=packed), want)
 
 
 WORKER = r'''
